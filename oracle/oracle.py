@@ -1,0 +1,270 @@
+"""ctypes binding of the CPU ORACLE (oracle/libnls_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py. Never imported by the product
+package. See oracle/nls_oracle.h for what is restated and the reference
+file:line each function follows.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MAT_LINEAR, MAT_EXPONENTIAL, MAT_PLASTIC, MAT_NEOHOOKEAN = 0, 1, 2, 3
+REASONS = ["NOT_YET_CONVERGED", "CONVERGED_RELATIVE", "CONVERGED_ABSOLUTE",
+           "DIVERGED_MAXITS", "DIVERGED_STEP", "DIVERGED_LINEAR_SOLVE"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_bp = C.POINTER(C.c_uint8)
+
+
+class _Model(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nen", C.c_int32), ("nn", C.c_int64), ("nel", C.c_int64),
+                ("conn", _ip), ("coords", _dp), ("p", C.c_int32), ("nq", C.c_int32),
+                ("mat_kind", C.c_int32), ("mat", C.c_double * 8), ("area", C.c_double),
+                ("ndir", C.c_int64), ("dir_dofs", _lp), ("dir_vals", _dp),
+                ("nneu", C.c_int64), ("neu_dofs", _lp), ("neu_vals", _dp),
+                ("sig", _dp), ("alp", _dp), ("kap", _dp), ("gam", _dp), ("dsig", _dp),
+                ("sig_n", _dp), ("alp_n", _dp), ("kap_n", _dp), ("gam_n", _dp), ("u_n", _dp),
+                ("nthreads", C.c_int32)]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("type_modified", C.c_int32), ("atol", C.c_double), ("rtol", C.c_double),
+                ("dtol", C.c_double), ("maxits", C.c_int32), ("lin_rtol", C.c_double),
+                ("lin_maxits", C.c_int32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("reason", C.c_int32), ("iterations", C.c_int32), ("lin_its_total", C.c_int32),
+                ("nhist", C.c_int32), ("norm_r", C.c_double), ("norm_r0", C.c_double)]
+
+
+def build(force=False):
+    """Compile oracle/libnls_oracle.so with the committed Makefile."""
+    so = os.path.join(_HERE, "libnls_oracle.so")
+    src = os.path.join(_HERE, "nls_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_pattern.restype = C.c_int64
+        _LIB.orc_integrate.restype = C.c_double
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+# ---- building blocks -------------------------------------------------------
+def lagrange_nodes(p, kind="chebyshev2"):
+    x = np.zeros(p + 1)
+    lib().orc_lagrange_nodes(C.c_int32(p), C.c_int32(0 if kind == "chebyshev2" else 1), _d(x))
+    return x
+
+
+def lagrange_weights(nodes):
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    w = np.zeros_like(nodes)
+    lib().orc_lagrange_weights(C.c_int32(len(nodes)), _d(nodes), _d(w))
+    return w
+
+
+def shape_N(nodes, w, xi):
+    out = np.zeros(len(nodes))
+    lib().orc_shape_N(C.c_int32(len(nodes)), _d(np.ascontiguousarray(nodes)), _d(np.ascontiguousarray(w)),
+                      C.c_double(xi), _d(out))
+    return out
+
+
+def shape_dN(nodes, w, xi):
+    out = np.zeros(len(nodes))
+    lib().orc_shape_dN(C.c_int32(len(nodes)), _d(np.ascontiguousarray(nodes)), _d(np.ascontiguousarray(w)),
+                       C.c_double(xi), _d(out))
+    return out
+
+
+def gauss(nq):
+    x, w = np.zeros(nq), np.zeros(nq)
+    if lib().orc_gauss(C.c_int32(nq), _d(x), _d(w)) != 0:
+        raise ValueError("Gauss quadrature not implemented for n = %d" % nq)
+    return x, w
+
+
+def integrate(nq, fvals):
+    f = np.ascontiguousarray(fvals, dtype=np.float64)
+    return lib().orc_integrate(C.c_int32(nq), _d(f))
+
+
+def dense_solve(A, b):
+    A = np.array(A, dtype=np.float64, order="C")
+    b = np.array(b, dtype=np.float64)
+    rc = lib().orc_dense_solve(C.c_int64(len(b)), _d(A), _d(b))
+    return rc, b
+
+
+# ---- model -----------------------------------------------------------------
+class OracleModel:
+    """Holds the arrays an `orc_model` points at (FEMModel + material + BCs)."""
+
+    def __init__(self, dim, conn, coords, p=1, nq=2, mat_kind=MAT_NEOHOOKEAN, mat=(1.0, 1.0), area=3e-4,
+                 nthreads=1):
+        self.conn = np.ascontiguousarray(conn, dtype=np.int32)
+        self.coords = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, dim)
+        self.dim = dim
+        self.nel, self.nen = self.conn.shape
+        self.nn = self.coords.shape[0]
+        self.ndof = self.nn * dim
+        self.m = _Model()
+        m = self.m
+        m.dim, m.nen, m.nn, m.nel = dim, self.nen, self.nn, self.nel
+        m.conn = self.conn.ctypes.data_as(_ip)
+        m.coords = _d(self.coords)
+        m.p, m.nq, m.mat_kind = p, nq, mat_kind
+        for i, v in enumerate(mat):
+            m.mat[i] = v
+        m.area = area
+        m.nthreads = nthreads
+        self.set_dirichlet([], [])
+        self.set_neumann([], [])
+        if mat_kind == MAT_PLASTIC:
+            n = self.nel * nq
+            self._state = {k: np.zeros(n) for k in
+                           ("sig", "alp", "kap", "gam", "dsig", "sig_n", "alp_n", "kap_n", "gam_n")}
+            self._state["u_n"] = np.zeros(self.nel * self.nen)
+            for k, v in self._state.items():
+                setattr(m, k, _d(v))
+            lib().orc_init_state(C.byref(m))
+        self._pattern = None
+
+    def set_threads(self, n):
+        self.m.nthreads = n
+
+    def set_dirichlet(self, dofs, vals):
+        self.dir_dofs = np.ascontiguousarray(dofs, dtype=np.int64)
+        self.dir_vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self.m.ndir = len(self.dir_dofs)
+        self.m.dir_dofs = self.dir_dofs.ctypes.data_as(_lp)
+        self.m.dir_vals = _d(self.dir_vals)
+
+    def set_neumann(self, dofs, vals):
+        self.neu_dofs = np.ascontiguousarray(dofs, dtype=np.int64)
+        self.neu_vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self.m.nneu = len(self.neu_dofs)
+        self.m.neu_dofs = self.neu_dofs.ctypes.data_as(_lp)
+        self.m.neu_vals = _d(self.neu_vals)
+
+    def state(self, name):
+        return self._state[name].reshape(self.nel, -1)
+
+    def commit_state(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        lib().orc_commit_state(C.byref(self.m), _d(U))
+
+    def pattern(self):
+        if self._pattern is None:
+            rowptr = np.zeros(self.ndof + 1, dtype=np.int64)
+            nnz = lib().orc_pattern(C.byref(self.m), rowptr.ctypes.data_as(_lp), None)
+            colind = np.zeros(nnz, dtype=np.int32)
+            lib().orc_pattern(C.byref(self.m), rowptr.ctypes.data_as(_lp), colind.ctypes.data_as(_ip))
+            self._pattern = (rowptr, colind)
+        return self._pattern
+
+    def residual(self, U):
+        """Returns (U_with_dirichlet, R) -- the reference mutates U in place (residual.jl:13)."""
+        U = np.array(U, dtype=np.float64)
+        R = np.zeros(self.ndof)
+        lib().orc_residual(C.byref(self.m), _d(U), _d(R))
+        return U, R
+
+    def jacobian_dense(self, U):
+        U = np.array(U, dtype=np.float64)
+        K = np.zeros((self.ndof, self.ndof))
+        lib().orc_jacobian_dense(C.byref(self.m), _d(U), _d(K))
+        return K
+
+    def jacobian_csr(self, U):
+        U = np.array(U, dtype=np.float64)
+        rowptr, colind = self.pattern()
+        vals = np.zeros(len(colind))
+        lib().orc_jacobian_csr(C.byref(self.m), _d(U), rowptr.ctypes.data_as(_lp),
+                               colind.ctypes.data_as(_ip), _d(vals))
+        return vals
+
+    def element(self, e, ue):
+        ue = np.ascontiguousarray(ue, dtype=np.float64).ravel()
+        nd = self.nen * self.dim
+        fe, Ke = np.zeros(nd), np.zeros((nd, nd))
+        lib().orc_element(C.byref(self.m), C.c_int64(e), _d(ue), _d(fe), _d(Ke))
+        return fe, Ke
+
+    def spmv(self, vals, x):
+        rowptr, colind = self.pattern()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.ndof)
+        lib().orc_spmv(C.c_int64(self.ndof), rowptr.ctypes.data_as(_lp), colind.ctypes.data_as(_ip),
+                       _d(np.ascontiguousarray(vals)), _d(x), _d(y), C.c_int32(self.m.nthreads))
+        return y
+
+    def constrained_mask(self):
+        con = np.zeros(self.ndof, dtype=np.uint8)
+        con[self.dir_dofs] = 1
+        return con
+
+    def pcg(self, vals, b, rtol=1e-12, maxits=10000):
+        rowptr, colind = self.pattern()
+        con = self.constrained_mask()
+        x = np.zeros(self.ndof)
+        relres, its = C.c_double(0), C.c_int32(0)
+        rc = lib().orc_pcg(C.c_int64(self.ndof), rowptr.ctypes.data_as(_lp), colind.ctypes.data_as(_ip),
+                           _d(np.ascontiguousarray(vals)), con.ctypes.data_as(_bp),
+                           _d(np.ascontiguousarray(b, dtype=np.float64)), _d(x), C.c_double(rtol),
+                           C.c_int32(maxits), C.byref(relres), C.byref(its), C.c_int32(self.m.nthreads))
+        return rc, x, its.value, relres.value
+
+    def newton(self, U0=None, rtol=1e-16, atol=1e-16, dtol=1e6, maxits=100, modified=False,
+               linear="dense", lin_rtol=1e-12, lin_maxits=100000):
+        """solve!(::NewtonSolver, U0) (newton_fem.jl:132-190). linear='dense' is the
+        faithful variant (LU); 'pcg' the scalable one (CSR + Jacobi-PCG)."""
+        U0 = np.zeros(self.ndof) if U0 is None else np.ascontiguousarray(U0, dtype=np.float64)
+        U, R = np.zeros(self.ndof), np.zeros(self.ndof)
+        hist = np.zeros(maxits + 2)
+        o = _Opts(int(modified), atol, rtol, dtol, maxits, lin_rtol, lin_maxits)
+        res = _Result()
+        if linear == "dense":
+            lib().orc_newton_dense(C.byref(self.m), C.byref(o), _d(U0), _d(U), _d(R), _d(hist), C.byref(res))
+        else:
+            rowptr, colind = self.pattern()
+            vals = np.zeros(len(colind))
+            lib().orc_newton_pcg(C.byref(self.m), C.byref(o), rowptr.ctypes.data_as(_lp),
+                                 colind.ctypes.data_as(_ip), _d(vals), _d(U0), _d(U), _d(R), _d(hist),
+                                 C.byref(res))
+        return dict(U=U, R=R, reason=REASONS[res.reason], iterations=res.iterations,
+                    lin_its=res.lin_its_total, hist=hist[:res.nhist].copy(),
+                    norm_r=res.norm_r, norm_r0=res.norm_r0)
+
+    def partition(self, nranks, node_off, rank):
+        off = np.ascontiguousarray(node_off, dtype=np.int64)
+        ne, ng = C.c_int64(0), C.c_int64(0)
+        sp = np.zeros(nranks + 1, dtype=np.int64)
+        lib().orc_partition(C.byref(self.m), C.c_int32(nranks), off.ctypes.data_as(_lp), C.c_int32(rank),
+                            C.byref(ne), None, C.byref(ng), None, sp.ctypes.data_as(_lp), None)
+        le = np.zeros(ne.value, dtype=np.int64)
+        gn = np.zeros(ng.value, dtype=np.int64)
+        sn = np.zeros(sp[-1], dtype=np.int64)
+        lib().orc_partition(C.byref(self.m), C.c_int32(nranks), off.ctypes.data_as(_lp), C.c_int32(rank),
+                            C.byref(ne), le.ctypes.data_as(_lp), C.byref(ng), gn.ctypes.data_as(_lp),
+                            sp.ctypes.data_as(_lp), sn.ctypes.data_as(_lp))
+        return dict(loc_elems=le, ghost_nodes=gn, send_ptr=sp, send_nodes=sn)
