@@ -1,0 +1,570 @@
+// kernels_assembly.cu -- the element loop of NonlinearSolids.jl as sm_100a CUDA kernels.
+//
+// Replaces (paths relative to the reference source tree):
+//   compute_internalforce / compute_dinternalforce   src/materials/defaults.jl:29-46, 68-82
+//   _internalforce_el / _dinternalforce_el           src/materials/defaults.jl:2-26
+//   plastic element kernels + update_state_el!       src/materials/linearelastoplasticity.jl:23-93
+//   restrict! / unrestrict! / assemble!              src/fem/element.jl:64-70
+//   Dirichlet / Neumann apply!                       src/fem/boundary.jl:29,39
+// The 2-D / 3-D Q1 Neo-Hookean kernels are the builder-defined tensor-product extension
+// (SURVEY.md 8c); they keep the same restrict -> qfunc -> integrate -> scatter structure.
+//
+// All arithmetic is FP64. Scatter is FP64 atomics (RED.E.ADD.F64) into R and the CSR
+// values; element -> CSR slot comes from a precomputed per-element position map.
+#include "nls_internal.h"
+
+struct AsmArgs {
+  int64_t nel, n_owned;
+  const int32_t *conn;
+  const double *coords;
+  const double *U;
+  double *R;
+  double *vals;
+  const int64_t *browptr;
+  const uint16_t *pos;
+  double *st[9];   // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
+  const double *u_n;
+};
+
+__device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
+
+// ------------------------------------------------------------------------------------
+// 1-D bar, order p = M-1 Lagrange on Chebyshev-2 nodes, nq Gauss points.
+// One thread per element. Operation order follows defaults.jl:7-9,23 and
+// quadrature.jl:69 (sum over q ascending) -- see SURVEY.md Appendix C.
+// ------------------------------------------------------------------------------------
+template <int M, bool DO_R, bool DO_K>
+__global__ void __launch_bounds__(128)
+k_asm_1d(const AsmArgs A, const __grid_constant__ Tab1D T, const __grid_constant__ MatParams mp) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= A.nel) return;
+  int nd[M];
+  double u[M], fe[M], Ke[M * M], B[M];
+#pragma unroll
+  for (int a = 0; a < M; ++a) { nd[a] = A.conn[e * M + a]; u[a] = A.U[nd[a]]; }
+  const double dxdxi = (A.coords[nd[M - 1]] - A.coords[nd[0]]) / 2.0;  // length(el)/2, element.jl:15
+  const double inv = 1.0 / dxdxi;
+  const double area = mp.area;
+  const int nq = T.nq;
+  const bool plastic = mp.kind == NLS_MAT_ELASTOPLASTIC_1D;
+  for (int q = 0; q < nq; ++q) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) B[i] = T.dN[q][i] * inv;  // B = gradN' * (1/dxdxi)
+    double s = 0.0, d = 0.0;
+    if (plastic) {
+      const int64_t k = e * nq + q;
+      if (DO_R) {  // update_state_el!, linearelastoplasticity.jl:68-91 (residual pass only)
+        double deps = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          const double du = u[i] - A.u_n[e * M + i];
+          deps = (i == 0) ? B[0] * du : deps + B[i] * du;
+        }
+        const double E = mp.p[0], Hk = mp.p[1], Ha = mp.p[2], Eep = mp.p[5];
+        const double s_tr = A.st[5][k] + E * deps;
+        const double rel = s_tr - A.st[6][k];
+        const double sgn = rel > 0.0 ? 1.0 : (rel < 0.0 ? -1.0 : 0.0);
+        const double f_tr = fabs(rel) - A.st[7][k];
+        double alp, kap, gam;
+        if (f_tr > 1e-5) {
+          const double dg = f_tr / (E + Hk + Ha);
+          s = s_tr - E * dg * sgn;
+          alp = A.st[6][k] + Ha * dg * sgn;
+          kap = A.st[7][k] + Hk * dg;
+          gam = A.st[8][k] + dg;
+          d = Eep;
+        } else {
+          s = s_tr; alp = A.st[6][k]; kap = A.st[7][k]; gam = A.st[8][k]; d = E;
+        }
+        A.st[0][k] = s; A.st[1][k] = alp; A.st[2][k] = kap; A.st[3][k] = gam; A.st[4][k] = d;
+      } else {     // Jacobian pass reads the stored tangent, linearelastoplasticity.jl:42-47
+        d = A.st[4][k];
+      }
+    } else {
+      double eps = 0.0;  // eps = B * u
+#pragma unroll
+      for (int i = 0; i < M; ++i) eps = (i == 0) ? B[0] * u[0] : eps + B[i] * u[i];
+      if (mp.kind == NLS_MAT_LINEAR_ELASTIC_1D) { s = mp.p[0] * eps; d = mp.p[0]; }
+      else {  // exponential.jl:20-21
+        const double ex = exp(-mp.p[1] * eps);
+        s = mp.p[0] * (1.0 - ex);
+        d = mp.p[1] * mp.p[0] * ex;
+      }
+    }
+    const double w = T.w[q];
+    if (DO_R) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        const double v = ((B[i] * s) * area) * dxdxi;
+        fe[i] = (q == 0) ? v * w : fe[i] + v * w;
+      }
+    }
+    if (DO_K) {
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          const double v = (((B[i] * d) * B[j]) * area) * dxdxi;
+          Ke[i * M + j] = (q == 0) ? v * w : Ke[i * M + j] + v * w;
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    if (nd[i] >= A.n_owned) continue;
+    if (DO_R) red_add(A.R + nd[i], fe[i]);
+    if (DO_K) {
+      const int64_t base = A.browptr[nd[i]];
+#pragma unroll
+      for (int j = 0; j < M; ++j) red_add(A.vals + base + A.pos[(e * M + i) * M + j], Ke[i * M + j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Small dense helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double inv2(const double *M, double *Mi) {
+  const double det = M[0] * M[3] - M[1] * M[2];
+  const double id = 1.0 / det;
+  Mi[0] = M[3] * id; Mi[1] = -M[1] * id; Mi[2] = -M[2] * id; Mi[3] = M[0] * id;
+  return det;
+}
+__device__ __forceinline__ double inv3(const double *M, double *Mi) {
+  const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+  const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+  const double id = 1.0 / det;
+  Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+  Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+  Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+  return det;
+}
+
+// ------------------------------------------------------------------------------------
+// 2-D plane-strain Q1 compressible Neo-Hookean. One thread per element.
+//   F = I + sum_a u_a (x) dN_a/dX,  P = mu (F - F^-T) + lam lnJ F^-T
+//   K_{ai,bk} = w detJ [ mu d_ik (G_a.G_b) + lam g_ai g_bk + (mu - lam lnJ) g_ak g_bi ],
+//   G_a = dN_a/dX,  g_a = F^-T G_a  (spatial form of the tangent of SURVEY.md 8c).
+// ------------------------------------------------------------------------------------
+template <bool DO_R, bool DO_K>
+__global__ void __launch_bounds__(128)
+k_asm_q1_2d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= A.nel) return;
+  const int4 c4 = reinterpret_cast<const int4 *>(A.conn)[e];
+  const int nd[4] = {c4.x, c4.y, c4.z, c4.w};
+  double X[4][2], u[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double2 x = reinterpret_cast<const double2 *>(A.coords)[nd[a]];
+    const double2 v = reinterpret_cast<const double2 *>(A.U)[nd[a]];
+    X[a][0] = x.x; X[a][1] = x.y; u[a][0] = v.x; u[a][1] = v.y;
+  }
+  const double mu = mp.p[0], lam = mp.p[1];
+  double fe[8], Ke[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    fe[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Ke[i][j] = 0.0;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+#pragma unroll
+        for (int D = 0; D < 2; ++D) J[d * 2 + D] += X[a][d] * T.dN[q][a][D];
+    const double detJ = inv2(J, Ji);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int D = 0; D < 2; ++D) G[a][D] = T.dN[q][a][0] * Ji[D] + T.dN[q][a][1] * Ji[2 + D];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int Jc = 0; Jc < 2; ++Jc) F[i * 2 + Jc] += u[a][i] * G[a][Jc];
+    const double detF = inv2(F, Fi);
+    const double lnJ = log(detF);
+    const double wd = T.w[q] * detJ;
+    if (DO_R) {
+      double P[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int Jc = 0; Jc < 2; ++Jc)
+          P[i * 2 + Jc] = wd * (mu * (F[i * 2 + Jc] - Fi[Jc * 2 + i]) + lam * lnJ * Fi[Jc * 2 + i]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) fe[a * 2 + i] += P[i * 2] * G[a][0] + P[i * 2 + 1] * G[a][1];
+    }
+    if (DO_K) {
+      double g[4][2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) g[a][i] = G[a][0] * Fi[i] + G[a][1] * Fi[2 + i];
+      const double c1 = wd * mu, c2 = wd * lam, c3 = wd * (mu - lam * lnJ);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double c2g[2] = {c2 * g[a][0], c2 * g[a][1]};
+        const double c3g[2] = {c3 * g[a][0], c3 * g[a][1]};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double dab = c1 * (G[a][0] * G[b][0] + G[a][1] * G[b][1]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              Ke[a * 2 + i][b * 2 + k] += c2g[i] * g[b][k] + c3g[k] * g[b][i] + (i == k ? dab : 0.0);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (nd[a] >= A.n_owned) continue;
+    if (DO_R) { red_add(A.R + 2 * (int64_t)nd[a], fe[a * 2]); red_add(A.R + 2 * (int64_t)nd[a] + 1, fe[a * 2 + 1]); }
+    if (DO_K) {
+      const int64_t b0 = A.browptr[nd[a]];
+      const int64_t deg = A.browptr[nd[a] + 1] - b0;
+      const uint2 pp = reinterpret_cast<const uint2 *>(A.pos)[e * 4 + a];  // 4 x uint16
+      const int pb[4] = {(int)(pp.x & 0xffff), (int)(pp.x >> 16), (int)(pp.y & 0xffff), (int)(pp.y >> 16)};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        double *row = A.vals + 4 * b0 + i * 2 * deg;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          red_add(row + 2 * pb[b], Ke[a * 2 + i][b * 2]);
+          red_add(row + 2 * pb[b] + 1, Ke[a * 2 + i][b * 2 + 1]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// 3-D Q1 hexahedron, compressible Neo-Hookean. EIGHT lanes per element (4 elements per
+// warp): K_e (24x24 doubles) does not fit one thread's registers.
+//   phase 0: lane a gathers node a (X_a, u_a) into shared memory
+//   phase 1: lane q evaluates quadrature point q: J, dN/dX, F, F^-1, lnJ, P, g -> smem
+//   phase 2: lane a owns row block a of K_e (3 x 24 accumulators) and f_a; loops q, b
+//   scatter: lane a adds its rows (FP64 RED), only if node a is owned by this rank
+// Shared-memory layout per element (doubles): 8 qp blocks of 62 {Gg[8][6], P[9], c[3], pad 2}
+// then Xu[8][6]; 62*8B = 31 16-byte units per lane -> conflict-free STS.128 in phase 1;
+// phase-2 reads are broadcasts within the 8-lane group.
+// ------------------------------------------------------------------------------------
+#define H8_EPB 16
+#define H8_QSTRIDE 62
+#define H8_ESTRIDE (8 * H8_QSTRIDE + 48)
+
+template <bool DO_R, bool DO_K>
+__global__ void __launch_bounds__(128, 2)
+k_asm_q1_3d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int le = tid >> 3;        // element within block
+  const int ln = tid & 7;         // lane within element: node index (phases 0,2) / qp index (phase 1)
+  const int64_t e = blockIdx.x * (int64_t)H8_EPB + le;
+  const bool active = e < A.nel;
+  double *S = smem + le * H8_ESTRIDE;
+  double *Xu = S + 8 * H8_QSTRIDE;
+  const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));
+
+  int node = 0;
+  if (active) {
+    node = A.conn[e * 8 + ln];
+    const double *xc = A.coords + 3 * (int64_t)node;
+    const double *uc = A.U + 3 * (int64_t)node;
+    Xu[ln * 6 + 0] = xc[0]; Xu[ln * 6 + 1] = xc[1]; Xu[ln * 6 + 2] = xc[2];
+    Xu[ln * 6 + 3] = uc[0]; Xu[ln * 6 + 4] = uc[1]; Xu[ln * 6 + 5] = uc[2];
+  }
+  __syncwarp(gmask);
+
+  const double mu = mp.p[0], lam = mp.p[1];
+  if (active) {
+    // ---- phase 1: this lane's quadrature point q = ln --------------------------------
+    const int q = ln;
+    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Ji[9], F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Fi[9];
+    double G[8][3];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const double dn0 = T.dN[q][a][0], dn1 = T.dN[q][a][1], dn2 = T.dN[q][a][2];
+      G[a][0] = dn0; G[a][1] = dn1; G[a][2] = dn2;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double x = Xu[a * 6 + d];
+        J[d * 3 + 0] += x * dn0; J[d * 3 + 1] += x * dn1; J[d * 3 + 2] += x * dn2;
+      }
+    }
+    const double detJ = inv3(J, Ji);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const double d0 = G[a][0], d1 = G[a][1], d2 = G[a][2];
+#pragma unroll
+      for (int D = 0; D < 3; ++D) G[a][D] = d0 * Ji[D] + d1 * Ji[3 + D] + d2 * Ji[6 + D];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double ui = Xu[a * 6 + 3 + i];
+        F[i * 3 + 0] += ui * G[a][0]; F[i * 3 + 1] += ui * G[a][1]; F[i * 3 + 2] += ui * G[a][2];
+      }
+    }
+    const double detF = inv3(F, Fi);
+    const double lnJ = log(detF);
+    const double wd = T.w[q] * detJ;
+    double *Q = S + q * H8_QSTRIDE;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      double2 *dst = reinterpret_cast<double2 *>(Q + a * 6);
+      const double g0 = G[a][0] * Fi[0] + G[a][1] * Fi[3] + G[a][2] * Fi[6];
+      const double g1 = G[a][0] * Fi[1] + G[a][1] * Fi[4] + G[a][2] * Fi[7];
+      const double g2 = G[a][0] * Fi[2] + G[a][1] * Fi[5] + G[a][2] * Fi[8];
+      dst[0] = make_double2(G[a][0], G[a][1]);
+      dst[1] = make_double2(G[a][2], g0);
+      dst[2] = make_double2(g1, g2);
+    }
+    const double cl = lam * lnJ;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int Jc = 0; Jc < 3; ++Jc)
+        Q[48 + i * 3 + Jc] = wd * (mu * (F[i * 3 + Jc] - Fi[Jc * 3 + i]) + cl * Fi[Jc * 3 + i]);
+    Q[57] = wd * mu; Q[58] = wd * lam; Q[59] = wd * (mu - cl);
+  }
+  __syncwarp(gmask);
+  if (!active) return;
+
+  // ---- phase 2: lane a = ln owns row block a ------------------------------------------
+  const int a = ln;
+  double fe[3] = {0, 0, 0};
+  double Kr[8][3][3];
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Kr[b][i][k] = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < 8; ++q) {
+    const double *Q = S + q * H8_QSTRIDE;
+    const double2 t0 = reinterpret_cast<const double2 *>(Q + a * 6)[0];
+    const double2 t1 = reinterpret_cast<const double2 *>(Q + a * 6)[1];
+    const double2 t2 = reinterpret_cast<const double2 *>(Q + a * 6)[2];
+    const double Ga[3] = {t0.x, t0.y, t1.x}, ga[3] = {t1.y, t2.x, t2.y};
+    if (DO_R) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        fe[i] += Q[48 + i * 3] * Ga[0] + Q[48 + i * 3 + 1] * Ga[1] + Q[48 + i * 3 + 2] * Ga[2];
+    }
+    if (DO_K) {
+      const double c1 = Q[57], c2 = Q[58], c3 = Q[59];
+      const double c1G[3] = {c1 * Ga[0], c1 * Ga[1], c1 * Ga[2]};
+      const double c2g[3] = {c2 * ga[0], c2 * ga[1], c2 * ga[2]};
+      const double c3g[3] = {c3 * ga[0], c3 * ga[1], c3 * ga[2]};
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const double2 s0 = reinterpret_cast<const double2 *>(Q + b * 6)[0];
+        const double2 s1 = reinterpret_cast<const double2 *>(Q + b * 6)[1];
+        const double2 s2 = reinterpret_cast<const double2 *>(Q + b * 6)[2];
+        const double gb[3] = {s1.y, s2.x, s2.y};
+        const double dab = c1G[0] * s0.x + c1G[1] * s0.y + c1G[2] * s1.x;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            Kr[b][i][k] += c2g[i] * gb[k] + c3g[k] * gb[i] + (i == k ? dab : 0.0);
+      }
+    }
+  }
+  if (node >= A.n_owned) return;
+  if (DO_R) {
+    double *r = A.R + 3 * (int64_t)node;
+    red_add(r, fe[0]); red_add(r + 1, fe[1]); red_add(r + 2, fe[2]);
+  }
+  if (DO_K) {
+    const int64_t b0 = A.browptr[node];
+    const int64_t deg = A.browptr[node + 1] - b0;
+    const uint4 pp = reinterpret_cast<const uint4 *>(A.pos)[e * 8 + a];  // 8 x uint16
+    const unsigned pw[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double *row = A.vals + 9 * b0 + i * 3 * deg;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int pb = (int)((pw[b >> 1] >> (16 * (b & 1))) & 0xffff);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) red_add(row + 3 * pb + k, Kr[b][i][k]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Boundary kernels and one-time index kernels
+// ------------------------------------------------------------------------------------
+// Dirichlet apply!: D[bc.nodes] .= bc.values (boundary.jl:29). The list is deduplicated on
+// the host (last write wins, as sequential application would).
+__global__ void k_apply_dirichlet(int64_t n, const int64_t *dofs, const double *vals, double *U) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < n) U[dofs[k]] = vals[k];
+}
+// R .-= Fext with Fext[bc.nodes] .+= bc.values (residual.jl:24-25, boundary.jl:39); duplicates allowed
+__global__ void k_neumann(int64_t n, const int64_t *dofs, const double *vals, double *R, int64_t nrows) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < n && dofs[k] < nrows) atomicAdd(R + dofs[k], -vals[k]);
+}
+
+// position of node b in the (ascending) block row of node a, for every element node pair
+__global__ void k_build_pos(int64_t nel, int nen, int64_t n_owned, const int32_t *conn,
+                            const int64_t *browptr, const int32_t *bcol, uint16_t *pos) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nel * nen) return;
+  const int64_t e = t / nen;
+  const int na = conn[t];
+  uint16_t *out = pos + t * nen;
+  if (na >= n_owned) { for (int b = 0; b < nen; ++b) out[b] = 0; return; }
+  const int64_t lo0 = browptr[na], hi0 = browptr[na + 1];
+  for (int b = 0; b < nen; ++b) {
+    const int nb = conn[e * nen + b];
+    int64_t lo = lo0, hi = hi0 - 1;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (bcol[mid] < nb) lo = mid + 1; else hi = mid; }
+    out[b] = (uint16_t)(lo - lo0);
+  }
+}
+
+// scalar CSR = dim x dim expansion of the node-level pattern; also the diagonal offsets
+__global__ void k_expand_pattern(int64_t n_owned, int dim, const int64_t *browptr, const int32_t *bcol,
+                                 int64_t *rowptr, int32_t *colind, int32_t *diag) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nrows = n_owned * dim;
+  if (r > nrows) return;
+  if (r == nrows) { rowptr[r] = (int64_t)dim * dim * browptr[n_owned]; return; }
+  const int64_t a = r / dim;
+  const int i = (int)(r % dim);
+  const int64_t b0 = browptr[a], deg = browptr[a + 1] - b0;
+  const int64_t start = (int64_t)dim * dim * b0 + (int64_t)i * dim * deg;
+  rowptr[r] = start;
+  for (int64_t j = 0; j < deg; ++j) {
+    const int32_t nb = bcol[b0 + j];
+    for (int k = 0; k < dim; ++k) colind[start + j * dim + k] = nb * dim + k;
+    if (nb == a) diag[r] = (int32_t)(j * dim + i);
+  }
+}
+
+// save_state! (linearelastoplasticity.jl:96-103): u_n <- restrict(U); *_n <- *
+__global__ void k_commit_state(int64_t nel, int nen, int nq, const int32_t *conn, const double *U,
+                               double *u_n, double *sig, double *alp, double *kap, double *gam,
+                               double *sig_n, double *alp_n, double *kap_n, double *gam_n) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  for (int a = 0; a < nen; ++a) u_n[e * nen + a] = U[conn[e * nen + a]];
+  for (int q = 0; q < nq; ++q) {
+    const int64_t k = e * nq + q;
+    sig_n[k] = sig[k]; alp_n[k] = alp[k]; kap_n[k] = kap[k]; gam_n[k] = gam[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+#define NLS_KCHECK(h) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+  (h)->err = std::string("kernel launch: ") + cudaGetErrorString(e_); return NLS_ERR_CUDA; } (h)->launches++; } while (0)
+
+template <int M>
+static int launch_1d(nls_context *h, const AsmArgs &a, bool r, bool k) {
+  const unsigned g = nblk(h->nel, 128);
+  if (r && k) k_asm_1d<M, true, true><<<g, 128, 0, h->stream>>>(a, h->tab1, h->mat);
+  else if (r) k_asm_1d<M, true, false><<<g, 128, 0, h->stream>>>(a, h->tab1, h->mat);
+  else        k_asm_1d<M, false, true><<<g, 128, 0, h->stream>>>(a, h->tab1, h->mat);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_assembly(nls_context *h, bool want_r, bool want_k) {
+  if (!want_r && !want_k) return NLS_OK;
+  if (h->nel == 0) return NLS_OK;
+  AsmArgs a{};
+  a.nel = h->nel; a.n_owned = h->n_owned; a.conn = h->d_conn; a.coords = h->d_coords; a.U = h->d_U;
+  a.R = h->d_R; a.vals = h->d_vals; a.browptr = h->d_browptr; a.pos = h->d_pos;
+  for (int i = 0; i < 9; ++i) a.st[i] = h->d_state[i];
+  a.u_n = h->d_u_n;
+  if (h->dim == 1) {
+    switch (h->nen) {
+      case 2: return launch_1d<2>(h, a, want_r, want_k);
+      case 3: return launch_1d<3>(h, a, want_r, want_k);
+      case 4: return launch_1d<4>(h, a, want_r, want_k);
+      case 5: return launch_1d<5>(h, a, want_r, want_k);
+      case 6: return launch_1d<6>(h, a, want_r, want_k);
+      case 7: return launch_1d<7>(h, a, want_r, want_k);
+      case 8: return launch_1d<8>(h, a, want_r, want_k);
+      default: NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D elements support p = 1..7");
+    }
+  }
+  if (h->dim == 2) {
+    const unsigned g = nblk(h->nel, 128);
+    if (want_r && want_k) k_asm_q1_2d<true, true><<<g, 128, 0, h->stream>>>(a, h->tabq, h->mat);
+    else if (want_r)      k_asm_q1_2d<true, false><<<g, 128, 0, h->stream>>>(a, h->tabq, h->mat);
+    else                  k_asm_q1_2d<false, true><<<g, 128, 0, h->stream>>>(a, h->tabq, h->mat);
+    NLS_KCHECK(h);
+    return NLS_OK;
+  }
+  const unsigned g = nblk(h->nel, H8_EPB);
+  const size_t shm = sizeof(double) * H8_EPB * H8_ESTRIDE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_asm_q1_3d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    cudaFuncSetAttribute(k_asm_q1_3d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    cudaFuncSetAttribute(k_asm_q1_3d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    attr_set = true;
+  }
+  if (want_r && want_k) k_asm_q1_3d<true, true><<<g, 128, shm, h->stream>>>(a, h->tabq, h->mat);
+  else if (want_r)      k_asm_q1_3d<true, false><<<g, 128, shm, h->stream>>>(a, h->tabq, h->mat);
+  else                  k_asm_q1_3d<false, true><<<g, 128, shm, h->stream>>>(a, h->tabq, h->mat);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_apply_dirichlet(nls_context *h, double *U) {
+  if (h->ndir == 0) return NLS_OK;
+  k_apply_dirichlet<<<nblk(h->ndir, 256), 256, 0, h->stream>>>(h->ndir, h->d_dir_dofs, h->d_dir_vals, U);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_neumann(nls_context *h, double *R) {
+  if (h->nneu == 0) return NLS_OK;
+  k_neumann<<<nblk(h->nneu, 256), 256, 0, h->stream>>>(h->nneu, h->d_neu_dofs, h->d_neu_vals, R, h->nrows);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_build_pos(nls_context *h) {
+  if (h->nel == 0) return NLS_OK;
+  k_build_pos<<<nblk(h->nel * h->nen, 256), 256, 0, h->stream>>>(h->nel, h->nen, h->n_owned, h->d_conn,
+                                                                 h->d_browptr, h->d_bcol, h->d_pos);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_expand_pattern(nls_context *h) {
+  k_expand_pattern<<<nblk(h->nrows + 1, 256), 256, 0, h->stream>>>(h->n_owned, h->dim, h->d_browptr, h->d_bcol,
+                                                                   h->d_rowptr, h->d_colind, h->d_diag);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_commit_state(nls_context *h, const double *dU) {
+  if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D || h->nel == 0) return NLS_OK;
+  k_commit_state<<<nblk(h->nel, 256), 256, 0, h->stream>>>(h->nel, h->nen, h->nq, h->d_conn, dU, h->d_u_n,
+      h->d_state[0], h->d_state[1], h->d_state[2], h->d_state[3],
+      h->d_state[5], h->d_state[6], h->d_state[7], h->d_state[8]);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}

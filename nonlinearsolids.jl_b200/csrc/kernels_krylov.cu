@@ -1,0 +1,383 @@
+// kernels_krylov.cu -- the linear-solve and vector steps of the Newton loop as sm_100a kernels.
+//
+// Replaces (paths relative to the reference source tree):
+//   dofs(K) \ dofs(-R)            src/nonlinearsolvers/newton_fem.jl:158   -> Jacobi-PCG (SpMV + fused dot/axpy)
+//   norm(dofs(fem, R))            src/nonlinearsolvers/newton_fem.jl:141,180 -> masked 2-norm reduction
+//   norm(dU), U .+= dU            src/nonlinearsolvers/newton_fem.jl:168,173
+//   dofs()/expand()               src/fem/fem.jl:93-108 -> constrained mask: identity rows/cols, x_c = 0
+//
+// The PCG loop is device-resident: scalars (alpha, beta, rz, convergence flag) live in a
+// control block in HBM; every kernel reads the flag and becomes a no-op once converged, so
+// the host may queue iterations ahead without synchronising. Reductions are deterministic:
+// per-block partials, summed in block order by the last block to finish.
+#include "nls_internal.h"
+#include "nccl_dyn.h"
+
+#define RED_BLOCKS_MAX 2048
+
+struct RedScratch {
+  double *partial;     // [3][RED_BLOCKS_MAX]
+  unsigned *counter;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-reduce NV values, store per-block partials; the last block to arrive sums all
+// partials in block order and writes out[0..NV). Returns true in thread 0 of that block.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partial, unsigned *counter, double *out) {
+  __shared__ double sh[NV][32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = warp_sum(v[i]);
+    if (lane == 0) sh[i][wid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = lane < nw ? sh[i][lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) partial[i * RED_BLOCKS_MAX + blockIdx.x] = s;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  // fixed-order sum: thread j accumulates partials j, j+blockDim, ... then a block tree
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      acc[i] += reinterpret_cast<volatile double *>(partial)[i * RED_BLOCKS_MAX + b];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = warp_sum(acc[i]);
+    if (lane == 0) sh[i][wid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = lane < nw ? sh[i][lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) out[i] = s;
+    }
+  }
+  if (threadIdx.x == 0) { *counter = 0; __threadfence(); }
+  return threadIdx.x == 0;
+}
+
+// ------------------------------------------------------------------------------------
+// CSR SpMV, T lanes per row (T | 32), grid-stride over row groups.
+//   y[row] = mask ? 0 : sum_k vals[k] x[colind[k]]
+// With DOT: also reduces sum_row x[row]*y[row] into ctl->red[0] (p.Ap of PCG).
+// ------------------------------------------------------------------------------------
+template <int T, bool DOT>
+__global__ void __launch_bounds__(256)
+k_spmv(int64_t nrows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+       const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+       const uint8_t *__restrict__ con, PcgCtl *ctl, RedScratch rs) {
+  if (DOT) {
+    if (ctl->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->rz = ctl->red[1];  // rz <- rz_new of the previous update
+  }
+  const int lane = threadIdx.x % T;
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x / T;
+  double dot[1] = {0.0};
+  for (int64_t base = 0; base < nrows; base += stride) {
+    // every thread runs the same trip count, so whole warps stay converged for the shuffles
+    const int64_t row = base + gid;
+    const bool valid = row < nrows;
+    double s = 0.0;
+    if (valid) {
+      const int64_t b = rowptr[row], e = rowptr[row + 1];
+      for (int64_t k = b + lane; k < e; k += T) s += vals[k] * x[colind[k]];
+    }
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (valid && lane == 0) {
+      if (con && con[row]) s = 0.0;
+      y[row] = s;
+      if (DOT) dot[0] += x[row] * s;
+    }
+  }
+  if (DOT) grid_reduce<1>(dot, rs.partial, rs.counter, &ctl->red[0]);
+}
+
+// diagonal -> Jacobi preconditioner; constrained rows get 0 (their residual is 0 anyway)
+__global__ void k_extract_dinv(int64_t nrows, const int64_t *rowptr, const int32_t *diag, const double *vals,
+                               const uint8_t *con, double *dinv) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  dinv[r] = con[r] ? 0.0 : 1.0 / vals[rowptr[r] + diag[r]];
+}
+
+// PCG start: x = 0, r = masked b, p = z = dinv r; reduces rz and bb.
+__global__ void __launch_bounds__(256)
+k_pcg_init(int64_t nrows, const double *__restrict__ b, const uint8_t *__restrict__ con,
+           const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+           double *__restrict__ p, PcgCtl *ctl, RedScratch rs) {
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = con[i] ? 0.0 : b[i];
+    const double zi = dinv[i] * ri;
+    x[i] = 0.0; r[i] = ri; p[i] = zi;
+    v[0] += ri * zi; v[1] += ri * ri;
+  }
+  grid_reduce<2>(v, rs.partial, rs.counter, &ctl->red[1]);  // red[1] = rz, red[2] = bb
+}
+__global__ void k_pcg_after_init(PcgCtl *ctl, double tol2, int maxits) {
+  ctl->bb = ctl->red[2]; ctl->rr = ctl->red[2]; ctl->rz = ctl->red[1];
+  ctl->tol2 = tol2; ctl->iters = 0; ctl->maxits = maxits;
+  ctl->done = (ctl->red[2] == 0.0) ? 1 : 0;
+}
+
+// x += alpha p; r -= alpha Ap; reduces rz_new = r.(dinv r) and rr = r.r
+__global__ void __launch_bounds__(256)
+k_pcg_update(int64_t nrows, const double *__restrict__ p, const double *__restrict__ Ap,
+             const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+             PcgCtl *ctl, RedScratch rs) {
+  if (ctl->done) return;
+  const double pAp = ctl->red[0];
+  if (!(pAp > 0.0)) {  // breakdown (not SPD, NaN): every thread sees the same value
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->done = 3;
+    return;
+  }
+  const double alpha = ctl->rz / pAp;
+  double v[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    v[0] += ri * (dinv[i] * ri); v[1] += ri * ri;
+  }
+  if (grid_reduce<2>(v, rs.partial, rs.counter, &ctl->red[1])) ctl->iters += 1;
+}
+
+// convergence test, then p = dinv r + beta p
+__global__ void __launch_bounds__(256)
+k_pcg_pupdate(int64_t nrows, const double *__restrict__ r, const double *__restrict__ dinv,
+              double *__restrict__ p, PcgCtl *ctl) {
+  if (ctl->done) return;
+  const double rr = ctl->red[2];
+  if (!(rr == rr)) { if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->done = 3; ctl->rr = rr; } return; }
+  if (rr <= ctl->tol2 * ctl->bb) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->done = 1; ctl->rr = rr; }
+    return;
+  }
+  const double beta = ctl->red[1] / ctl->rz;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = dinv[i] * r[i] + beta * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->rr = rr;
+}
+
+// generic masked dot: out = sum_{i<n, !con[i]} x_i y_i
+__global__ void __launch_bounds__(256)
+k_dot(int64_t n, const double *__restrict__ x, const double *__restrict__ y, const uint8_t *__restrict__ con,
+      double *out, RedScratch rs) {
+  double v[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!con || !con[i]) v[0] += x[i] * y[i];
+  grid_reduce<1>(v, rs.partial, rs.counter, out);
+}
+
+__global__ void __launch_bounds__(256)
+k_axpy(int64_t n, double a, const double *__restrict__ x, double *__restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+__global__ void __launch_bounds__(256)
+k_negate(int64_t n, const double *__restrict__ x, double *__restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = -x[i];
+}
+
+// halo pack/unpack: node lists -> dim doubles per node
+__global__ void k_pack(int64_t nnodes, int dim, const int32_t *nodes, const double *v, double *buf) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nnodes * dim) return;
+  buf[t] = v[(int64_t)nodes[t / dim] * dim + t % dim];
+}
+__global__ void k_unpack(int64_t nnodes, int dim, const int32_t *nodes, const double *buf, double *v) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nnodes * dim) return;
+  v[(int64_t)nodes[t / dim] * dim + t % dim] = buf[t];
+}
+
+// ------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------
+#define NLS_KCHECK(h) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+  (h)->err = std::string("kernel launch: ") + cudaGetErrorString(e_); return NLS_ERR_CUDA; } (h)->launches++; } while (0)
+
+static inline RedScratch red_of(nls_context *h) {
+  RedScratch rs;
+  rs.partial = h->d_partial;
+  rs.counter = reinterpret_cast<unsigned *>(h->d_partial + 3 * RED_BLOCKS_MAX);
+  return rs;
+}
+static inline unsigned vec_grid(nls_context *h, int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g > RED_BLOCKS_MAX) g = RED_BLOCKS_MAX;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+template <int T>
+static int spmv_t(nls_context *h, const double *x, double *y, const uint8_t *con, bool dot) {
+  int64_t g = (h->nrows * T + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g > RED_BLOCKS_MAX) g = RED_BLOCKS_MAX;
+  if (g < 1) g = 1;
+  if (dot) k_spmv<T, true><<<(unsigned)g, 256, 0, h->stream>>>(h->nrows, h->d_rowptr, h->d_colind, h->d_vals, x, y, con, h->d_ctl, red_of(h));
+  else     k_spmv<T, false><<<(unsigned)g, 256, 0, h->stream>>>(h->nrows, h->d_rowptr, h->d_colind, h->d_vals, x, y, con, h->d_ctl, red_of(h));
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_spmv(nls_context *h, const double *x, double *y, bool masked, bool with_dot) {
+  if (h->nrows == 0) return NLS_OK;
+  const uint8_t *con = masked ? h->d_con : nullptr;
+  const double avg = (double)h->nnz / (double)h->nrows;
+  if (avg <= 3.0) return spmv_t<1>(h, x, y, con, with_dot);
+  if (avg <= 6.0) return spmv_t<2>(h, x, y, con, with_dot);
+  if (avg <= 12.0) return spmv_t<4>(h, x, y, con, with_dot);
+  if (avg <= 40.0) return spmv_t<8>(h, x, y, con, with_dot);
+  return spmv_t<16>(h, x, y, con, with_dot);
+}
+
+int nls_launch_extract_dinv(nls_context *h) {
+  if (h->nrows == 0) return NLS_OK;
+  k_extract_dinv<<<(unsigned)((h->nrows + 255) / 256), 256, 0, h->stream>>>(h->nrows, h->d_rowptr, h->d_diag, h->d_vals, h->d_con, h->d_dinv);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, double *out) {
+  k_dot<<<vec_grid(h, n), 256, 0, h->stream>>>(n, x, y, nullptr, h->d_scal, red_of(h));
+  NLS_KCHECK(h);
+  if (h->distributed) { int rc = nls_allreduce_sum(h, h->d_scal, 1); if (rc) return rc; }
+  NLS_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  *out = h->h_scal[0];
+  return NLS_OK;
+}
+
+// sqrt(sum v_i^2) over owned rows, optionally skipping constrained DoFs -- norm(dofs(fem, R))
+double nls_dev_masked_norm2(nls_context *h, const double *v, bool masked, int *rc) {
+  *rc = NLS_OK;
+  k_dot<<<vec_grid(h, h->nrows), 256, 0, h->stream>>>(h->nrows, v, v, masked ? h->d_con : nullptr, h->d_scal, red_of(h));
+  h->launches++;
+  if (h->distributed) { *rc = nls_allreduce_sum(h, h->d_scal, 1); if (*rc) return 0.0; }
+  cudaError_t e = cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { h->err = std::string("norm: ") + cudaGetErrorString(e); *rc = NLS_ERR_CUDA; return 0.0; }
+  return sqrt(h->h_scal[0]);
+}
+
+int nls_launch_axpy(nls_context *h, int64_t n, double a, const double *x, double *y) {
+  if (n == 0) return NLS_OK;
+  k_axpy<<<vec_grid(h, n), 256, 0, h->stream>>>(n, a, x, y);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+// ---- communication: neighbour halo (ghost-DoF) exchange + scalar allreduce over NCCL ----
+int nls_halo_exchange(nls_context *h, double *v) {
+  if (!h->distributed || h->nneigh == 0) return NLS_OK;
+  const int dim = h->dim;
+  const int64_t nsend = h->send_ptr[h->nneigh], nrecv = h->recv_ptr[h->nneigh];
+  if (nsend > 0) {
+    k_pack<<<(unsigned)((nsend * dim + 255) / 256), 256, 0, h->stream>>>(nsend, dim, h->d_send_nodes, v, h->d_sendbuf);
+    NLS_KCHECK(h);
+  }
+  NcclApi *nc = h->nccl;
+  if (nc->GroupStart() != 0) NLS_FAIL(h, NLS_ERR_NCCL, "ncclGroupStart failed");
+  for (int q = 0; q < h->nneigh; ++q) {
+    const int64_t s0 = h->send_ptr[q] * dim, s1 = h->send_ptr[q + 1] * dim;
+    const int64_t r0 = h->recv_ptr[q] * dim, r1 = h->recv_ptr[q + 1] * dim;
+    int e1 = 0, e2 = 0;
+    if (s1 > s0) e1 = nc->Send(h->d_sendbuf + s0, (size_t)(s1 - s0), NCCL_DYN_FLOAT64, h->neigh[q], h->comm, h->stream);
+    if (r1 > r0) e2 = nc->Recv(h->d_recvbuf + r0, (size_t)(r1 - r0), NCCL_DYN_FLOAT64, h->neigh[q], h->comm, h->stream);
+    if (e1 || e2) { nc->GroupEnd(); NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclSend/Recv: ") + nc->GetErrorString(e1 ? e1 : e2)); }
+  }
+  int ge = nc->GroupEnd();
+  if (ge != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclGroupEnd: ") + nc->GetErrorString(ge));
+  if (nrecv > 0) {
+    k_unpack<<<(unsigned)((nrecv * dim + 255) / 256), 256, 0, h->stream>>>(nrecv, dim, h->d_recv_nodes, h->d_recvbuf, v);
+    NLS_KCHECK(h);
+  }
+  return NLS_OK;
+}
+
+int nls_allreduce_sum(nls_context *h, double *dptr, int count) {
+  if (!h->distributed) return NLS_OK;
+  int e = h->nccl->AllReduce(dptr, dptr, (size_t)count, NCCL_DYN_FLOAT64, NCCL_DYN_SUM, h->comm, h->stream);
+  if (e != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclAllReduce: ") + h->nccl->GetErrorString(e));
+  return NLS_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Jacobi-PCG driver on the handle's current CSR values. rhs = h->d_b (masked inside),
+// solution -> h->d_dU (zero on constrained DoFs = expand(), fem.jl:98-102).
+//   fixed_iters > 0: run exactly that many iterations without convergence checks (bench).
+//   status: 0 converged, 1 maxits, 2 breakdown
+// ------------------------------------------------------------------------------------
+int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int *its, double *relres, int *status) {
+  int rc;
+  const int64_t n = h->nrows;
+  RedScratch rs = red_of(h);
+  if ((rc = nls_launch_extract_dinv(h))) return rc;
+  k_pcg_init<<<vec_grid(h, n), 256, 0, h->stream>>>(n, h->d_b, h->d_con, h->d_dinv, h->d_dU, h->d_r, h->d_p, h->d_ctl, rs);
+  NLS_KCHECK(h);
+  if ((rc = nls_allreduce_sum(h, &h->d_ctl->red[1], 2))) return rc;
+  const double tol2 = fixed_iters > 0 ? -1.0 : rtol * rtol;
+  k_pcg_after_init<<<1, 1, 0, h->stream>>>(h->d_ctl, tol2, maxits);
+  NLS_KCHECK(h);
+  if ((rc = nls_halo_exchange(h, h->d_p))) return rc;
+  const int total = fixed_iters > 0 ? fixed_iters : maxits;
+  const int chunk = fixed_iters > 0 ? fixed_iters : 16;
+  int launched = 0;
+  h->h_ctl->done = 0; h->h_ctl->iters = 0;
+  while (launched < total) {
+    const int todo = (total - launched < chunk) ? (total - launched) : chunk;
+    for (int i = 0; i < todo; ++i) {
+      if ((rc = nls_launch_spmv(h, h->d_p, h->d_Ap, true, true))) return rc;
+      if ((rc = nls_allreduce_sum(h, &h->d_ctl->red[0], 1))) return rc;
+      k_pcg_update<<<vec_grid(h, n), 256, 0, h->stream>>>(n, h->d_p, h->d_Ap, h->d_dinv, h->d_dU, h->d_r, h->d_ctl, rs);
+      NLS_KCHECK(h);
+      if ((rc = nls_allreduce_sum(h, &h->d_ctl->red[1], 2))) return rc;
+      k_pcg_pupdate<<<vec_grid(h, n), 256, 0, h->stream>>>(n, h->d_r, h->d_dinv, h->d_p, h->d_ctl);
+      NLS_KCHECK(h);
+      if ((rc = nls_halo_exchange(h, h->d_p))) return rc;
+    }
+    launched += todo;
+    NLS_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->h_ctl->done) break;
+  }
+  const PcgCtl &c = *h->h_ctl;
+  if (its) *its = c.iters;
+  if (relres) *relres = c.bb > 0.0 ? sqrt(c.rr / c.bb) : 0.0;
+  if (status) *status = (c.done == 1) ? 0 : (c.done == 3 ? 2 : (fixed_iters > 0 ? 0 : 1));
+  return NLS_OK;
+}

@@ -1,0 +1,710 @@
+// nls_api.cu -- the C ABI of libnls_b200.so (see include/nls_b200.h) and the host-side
+// control flow around the kernels: model setup, CSR pattern, operator calls and the
+// Newton loop of solve!(::NewtonSolver) (src/nonlinearsolvers/newton_fem.jl:132-190).
+// There is no CPU fallback anywhere in this file: without a CUDA device nls_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include "nls_internal.h"
+#include "nccl_dyn.h"
+
+static std::string g_noctx_error = "no error";
+static NcclApi g_nccl;
+
+#define RED_BLOCKS_MAX 2048
+
+#define NLS_ENTER(h) do { if (!(h)) { g_noctx_error = "null handle"; return NLS_ERR_ARG; } \
+  cudaError_t e0_ = cudaSetDevice((h)->device); if (e0_ != cudaSuccess) { \
+  (h)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e0_); return NLS_ERR_CUDA; } } while (0)
+#define NLS_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+
+template <typename T>
+static int dev_alloc(nls_context *h, T **p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) count = 1;
+  NLS_CUDA(h, cudaMalloc((void **)p, count * sizeof(T)));
+  return NLS_OK;
+}
+template <typename T>
+static void dev_free(T **p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+__global__ void k_set_mask(int64_t n, const int64_t *dofs, uint8_t *mask) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < n) mask[dofs[k]] = 1;
+}
+__global__ void k_fill(int64_t n, double *p, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_negate_into(int64_t n, const double *x, double *y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = -x[i];
+}
+
+static void free_pattern(nls_context *h) {
+  dev_free(&h->d_browptr); dev_free(&h->d_bcol); dev_free(&h->d_rowptr); dev_free(&h->d_colind);
+  dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
+  h->h_browptr.clear(); h->h_bcol.clear();
+  h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
+}
+
+static int alloc_state(nls_context *h) {
+  if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D || !h->have_mesh || !h->have_disc) return NLS_OK;
+  if (h->d_state[0]) return NLS_OK;
+  for (int i = 0; i < 9; ++i) NLS_TRY(dev_alloc(h, &h->d_state[i], (size_t)(h->nel * h->nq)));
+  NLS_TRY(dev_alloc(h, &h->d_u_n, (size_t)(h->nel * h->nen)));
+  return nls_init_state(h);
+}
+
+// ---- lifecycle ----------------------------------------------------------------------
+extern "C" const char *nls_version(void) { return "nls_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *nls_last_error(nls_handle h) { return h ? h->err.c_str() : g_noctx_error.c_str(); }
+
+extern "C" int32_t nls_create(int32_t device, nls_handle *out) {
+  if (!out) { g_noctx_error = "nls_create: null output pointer"; return NLS_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_noctx_error = std::string("nls_create: no CUDA device (") + cudaGetErrorString(e) +
+                    "); libnls_b200 has no CPU fallback";
+    return NLS_ERR_NOGPU;
+  }
+  if (device < 0 || device >= ndev) { g_noctx_error = "nls_create: device index out of range"; return NLS_ERR_ARG; }
+  nls_context *h = new nls_context();
+  h->device = device;
+  h->err = "no error";
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_noctx_error = std::string(#call) + ": " + \
+  cudaGetErrorString(e_); delete h; return NLS_ERR_CUDA; } } while (0)
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+  CK(cudaEventCreate(&h->ev2)); CK(cudaEventCreate(&h->ev3));
+  CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CK(cudaMalloc((void **)&h->d_ctl, sizeof(PcgCtl)));
+  CK(cudaMemset(h->d_ctl, 0, sizeof(PcgCtl)));
+  CK(cudaMallocHost((void **)&h->h_ctl, sizeof(PcgCtl)));
+  CK(cudaMalloc((void **)&h->d_scal, 8 * sizeof(double)));
+  CK(cudaMallocHost((void **)&h->h_scal, 8 * sizeof(double)));
+  CK(cudaMalloc((void **)&h->d_partial, (3 * RED_BLOCKS_MAX + 2) * sizeof(double)));
+  CK(cudaMemset(h->d_partial, 0, (3 * RED_BLOCKS_MAX + 2) * sizeof(double)));
+#undef CK
+  h->mat.area = 3e-4;  // get(fem.data, :A, 3e-4), defaults.jl:3
+  *out = h;
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_destroy(nls_handle h) {
+  if (!h) return NLS_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
+  free_pattern(h);
+  dev_free(&h->d_conn); dev_free(&h->d_coords);
+  dev_free(&h->d_dir_dofs); dev_free(&h->d_dir_vals); dev_free(&h->d_con);
+  dev_free(&h->d_neu_dofs); dev_free(&h->d_neu_vals);
+  dev_free(&h->d_U); dev_free(&h->d_R); dev_free(&h->d_dU); dev_free(&h->d_r); dev_free(&h->d_p);
+  dev_free(&h->d_Ap); dev_free(&h->d_dinv); dev_free(&h->d_b); dev_free(&h->d_tmp);
+  dev_free(&h->d_partial); dev_free(&h->d_ctl); dev_free(&h->d_scal);
+  for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
+  dev_free(&h->d_u_n);
+  dev_free(&h->d_send_nodes); dev_free(&h->d_recv_nodes); dev_free(&h->d_sendbuf); dev_free(&h->d_recvbuf);
+  if (h->d_flush) cudaFree(h->d_flush);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return NLS_OK;
+}
+
+// ---- model description ------------------------------------------------------------------
+extern "C" int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64_t nelem, int32_t nen,
+                                const int32_t *conn0, const double *coords) {
+  NLS_ENTER(h);
+  if (dim < 1 || dim > 3) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: dim must be 1, 2 or 3");
+  if (nnodes < 1 || nelem < 0 || !coords || (nelem > 0 && !conn0)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: bad sizes or null arrays");
+  if (nnodes * (int64_t)dim > 2147483647LL) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: local DoF count exceeds int32 column indices");
+  if ((dim == 1 && (nen < 2 || nen > NLS_MAX_NEN1D)) || (dim == 2 && nen != 4) || (dim == 3 && nen != 8))
+    NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: nen must be p+1 (2..8) in 1-D, 4 in 2-D, 8 in 3-D");
+  for (int64_t k = 0; k < nelem * nen; ++k)
+    if (conn0[k] < 0 || conn0[k] >= nnodes) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: connectivity entry out of range (expects 0-based node ids)");
+  free_pattern(h);
+  h->dim = dim; h->nen = nen; h->nn = nnodes; h->nel = nelem; h->n_owned = nnodes;
+  h->h_conn.assign(conn0, conn0 + nelem * nen);
+  NLS_TRY(dev_alloc(h, &h->d_conn, (size_t)(nelem * nen)));
+  NLS_TRY(dev_alloc(h, &h->d_coords, (size_t)(nnodes * dim)));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_conn, conn0, sizeof(int32_t) * nelem * nen, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_coords, coords, sizeof(double) * nnodes * dim, cudaMemcpyHostToDevice, h->stream));
+  const size_t nd = (size_t)h->ndof_local();
+  NLS_TRY(dev_alloc(h, &h->d_U, nd)); NLS_TRY(dev_alloc(h, &h->d_R, nd)); NLS_TRY(dev_alloc(h, &h->d_dU, nd));
+  NLS_TRY(dev_alloc(h, &h->d_r, nd)); NLS_TRY(dev_alloc(h, &h->d_p, nd)); NLS_TRY(dev_alloc(h, &h->d_Ap, nd));
+  NLS_TRY(dev_alloc(h, &h->d_dinv, nd)); NLS_TRY(dev_alloc(h, &h->d_b, nd)); NLS_TRY(dev_alloc(h, &h->d_tmp, nd));
+  NLS_TRY(dev_alloc(h, &h->d_con, nd));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_con, 0, nd, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_U, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_dU, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_p, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->ndir = h->ndir_user = 0; h->nneu = 0;
+  h->dir_user_dofs.clear(); h->dir_slot.clear();
+  for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
+  dev_free(&h->d_u_n);
+  h->have_mesh = true;
+  h->have_disc = false;
+  h->nneigh = 0;
+  if (dim > 1) { h->p = 1; h->nq = 2; nls_host_tabq1(dim, &h->tabq); h->have_disc = true; }
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_set_discretization(nls_handle h, int32_t p_order, int32_t nq) {
+  NLS_ENTER(h);
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_discretization: call nls_set_mesh first");
+  if (h->dim == 1) {
+    if (p_order + 1 != h->nen) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_discretization: element has nen != p+1 nodes");
+    if (nq < 1 || nq > NLS_MAX_NQ) NLS_FAIL(h, NLS_ERR_ARG, "Gauss quadrature not implemented for this n (1..5 supported)");
+    if (nls_host_tab1d(p_order, nq, &h->tab1)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_discretization: unsupported p/nq");
+  } else {
+    if (p_order != 1 || nq != 2) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "multi-D elements are Q1 with 2 Gauss points per direction");
+    nls_host_tabq1(h->dim, &h->tabq);
+  }
+  if (h->have_disc && (h->p != p_order || h->nq != nq)) { for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]); dev_free(&h->d_u_n); }
+  h->p = p_order; h->nq = nq; h->have_disc = true;
+  return alloc_state(h);
+}
+
+extern "C" int32_t nls_set_material(nls_handle h, int32_t kind, const double *params, int32_t nparams) {
+  NLS_ENTER(h);
+  if (!params) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: null params");
+  const int need[4] = {1, 2, 5, 2};
+  if (kind < 0 || kind > 3) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: unknown material kind");
+  if (nparams < need[kind] || nparams > 8) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: wrong number of parameters");
+  if (h->have_mesh) {
+    if (kind == NLS_MAT_NEOHOOKEAN && h->dim == 1) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "Neo-Hookean needs a 2-D or 3-D mesh");
+    if (kind != NLS_MAT_NEOHOOKEAN && h->dim != 1) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D materials need a 1-D mesh");
+  }
+  const double keep_area = h->mat.area;
+  std::memset(&h->mat, 0, sizeof(h->mat));
+  h->mat.area = keep_area;
+  h->mat.kind = kind;
+  for (int i = 0; i < nparams; ++i) h->mat.p[i] = params[i];
+  if (kind == NLS_MAT_ELASTOPLASTIC_1D && nparams < 6) {  // Eep default, linearelastoplasticity.jl:17
+    const double E = params[0], Hk = params[1], Ha = params[2];
+    h->mat.p[5] = E * (Hk + Ha) / (E + Hk + Ha);
+  }
+  h->have_mat = true;
+  return alloc_state(h);
+}
+
+extern "C" int32_t nls_set_area(nls_handle h, double area) {
+  NLS_ENTER(h);
+  h->mat.area = area;
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_set_dirichlet(nls_handle h, int64_t n, const int64_t *dofs0, const double *vals) {
+  NLS_ENTER(h);
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_dirichlet: call nls_set_mesh first");
+  if (n < 0 || (n > 0 && (!dofs0 || !vals))) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_dirichlet: bad arguments");
+  const int64_t nd = h->ndof_local();
+  for (int64_t k = 0; k < n; ++k)
+    if (dofs0[k] < 0 || dofs0[k] >= nd) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_dirichlet: DoF index out of range");
+  // sequential apply! semantics: for a repeated DoF the last value wins
+  h->dir_user_dofs.assign(dofs0, dofs0 + n);
+  h->dir_slot.assign(n, -1);
+  std::unordered_map<int64_t, int64_t> last;
+  last.reserve((size_t)n * 2);
+  for (int64_t k = 0; k < n; ++k) last[dofs0[k]] = k;
+  std::vector<int64_t> udofs; std::vector<double> uvals;
+  for (int64_t k = 0; k < n; ++k)
+    if (last[dofs0[k]] == k) { h->dir_slot[k] = (int64_t)udofs.size(); udofs.push_back(dofs0[k]); uvals.push_back(vals[k]); }
+  h->ndir_user = n; h->ndir = (int64_t)udofs.size();
+  NLS_TRY(dev_alloc(h, &h->d_dir_dofs, (size_t)h->ndir));
+  NLS_TRY(dev_alloc(h, &h->d_dir_vals, (size_t)h->ndir));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_con, 0, (size_t)nd, h->stream));
+  if (h->ndir > 0) {
+    NLS_CUDA(h, cudaMemcpyAsync(h->d_dir_dofs, udofs.data(), sizeof(int64_t) * h->ndir, cudaMemcpyHostToDevice, h->stream));
+    NLS_CUDA(h, cudaMemcpyAsync(h->d_dir_vals, uvals.data(), sizeof(double) * h->ndir, cudaMemcpyHostToDevice, h->stream));
+    k_set_mask<<<(unsigned)((h->ndir + 255) / 256), 256, 0, h->stream>>>(h->ndir, h->d_dir_dofs, h->d_con);
+    h->launches++;
+  }
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_set_dirichlet_values(nls_handle h, int64_t n, const double *vals) {
+  NLS_ENTER(h);
+  if (n != h->ndir_user || (n > 0 && !vals)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_dirichlet_values: length differs from the Dirichlet list");
+  std::vector<double> uvals((size_t)h->ndir);
+  for (int64_t k = 0; k < n; ++k) if (h->dir_slot[k] >= 0) uvals[h->dir_slot[k]] = vals[k];
+  if (h->ndir > 0) {
+    NLS_CUDA(h, cudaMemcpyAsync(h->d_dir_vals, uvals.data(), sizeof(double) * h->ndir, cudaMemcpyHostToDevice, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_set_neumann(nls_handle h, int64_t n, const int64_t *dofs0, const double *vals) {
+  NLS_ENTER(h);
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_neumann: call nls_set_mesh first");
+  if (n < 0 || (n > 0 && (!dofs0 || !vals))) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_neumann: bad arguments");
+  for (int64_t k = 0; k < n; ++k)
+    if (dofs0[k] < 0 || dofs0[k] >= h->ndof_local()) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_neumann: DoF index out of range");
+  h->nneu = n;
+  NLS_TRY(dev_alloc(h, &h->d_neu_dofs, (size_t)n));
+  NLS_TRY(dev_alloc(h, &h->d_neu_vals, (size_t)n));
+  if (n > 0) {
+    NLS_CUDA(h, cudaMemcpyAsync(h->d_neu_dofs, dofs0, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
+    NLS_CUDA(h, cudaMemcpyAsync(h->d_neu_vals, vals, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_set_neumann_values(nls_handle h, int64_t n, const double *vals) {
+  NLS_ENTER(h);
+  if (n != h->nneu || (n > 0 && !vals)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_neumann_values: length differs from the Neumann list");
+  if (n > 0) {
+    NLS_CUDA(h, cudaMemcpyAsync(h->d_neu_vals, vals, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_init_state(nls_handle h) {
+  NLS_ENTER(h);
+  if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D) return NLS_OK;
+  if (!h->d_state[0]) return alloc_state(h);  // allocates, then re-enters here
+  const int64_t n = h->nel * h->nq;
+  if (n == 0) return NLS_OK;
+  const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, 4096);
+  for (int i = 0; i < 9; ++i) {
+    double v = 0.0;
+    if (i == 6) v = h->mat.p[4];  // alpha_n <- alpha_0
+    if (i == 7) v = h->mat.p[3];  // kappa_n <- kappa_0
+    k_fill<<<g, 256, 0, h->stream>>>(n, h->d_state[i], v);
+    h->launches++;
+  }
+  NLS_CUDA(h, cudaMemsetAsync(h->d_u_n, 0, sizeof(double) * h->nel * h->nen, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_commit_state(nls_handle h, const double *U) {
+  NLS_ENTER(h);
+  if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D) return NLS_OK;
+  if (!h->d_state[0]) NLS_FAIL(h, NLS_ERR_STATE, "nls_commit_state: state not initialised");
+  if (U) NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(nls_launch_commit_state(h, h->d_U));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_get_state(nls_handle h, const char *name, double *out) {
+  NLS_ENTER(h);
+  static const char *names[9] = {"sig", "alp", "kap", "gam", "dsig", "sig_n", "alp_n", "kap_n", "gam_n"};
+  if (!name || !out) NLS_FAIL(h, NLS_ERR_ARG, "nls_get_state: null argument");
+  if (!h->d_state[0]) NLS_FAIL(h, NLS_ERR_STATE, "nls_get_state: material has no state");
+  for (int i = 0; i < 9; ++i)
+    if (!std::strcmp(name, names[i])) {
+      NLS_CUDA(h, cudaMemcpyAsync(out, h->d_state[i], sizeof(double) * h->nel * h->nq, cudaMemcpyDeviceToHost, h->stream));
+      NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+      return NLS_OK;
+    }
+  NLS_FAIL(h, NLS_ERR_ARG, "nls_get_state: unknown state name");
+}
+
+// ---- pattern --------------------------------------------------------------------------
+extern "C" int32_t nls_build_pattern(nls_handle h) {
+  NLS_ENTER(h);
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_build_pattern: call nls_set_mesh first");
+  free_pattern(h);
+  nls_host_block_pattern(h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_browptr, h->h_bcol);
+  h->nnzb = (int64_t)h->h_bcol.size();
+  h->nrows = h->n_owned * h->dim;
+  h->nnz = h->nnzb * h->dim * h->dim;
+  for (int64_t a = 0; a < h->n_owned; ++a)
+    if (h->h_browptr[a + 1] - h->h_browptr[a] > 65535) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "node with more than 65535 neighbours");
+  NLS_TRY(dev_alloc(h, &h->d_browptr, (size_t)(h->n_owned + 1)));
+  NLS_TRY(dev_alloc(h, &h->d_bcol, (size_t)h->nnzb));
+  NLS_TRY(dev_alloc(h, &h->d_rowptr, (size_t)(h->nrows + 1)));
+  NLS_TRY(dev_alloc(h, &h->d_colind, (size_t)h->nnz));
+  NLS_TRY(dev_alloc(h, &h->d_vals, (size_t)h->nnz));
+  NLS_TRY(dev_alloc(h, &h->d_diag, (size_t)h->nrows));
+  NLS_TRY(dev_alloc(h, &h->d_pos, (size_t)(h->nel * h->nen * h->nen)));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_browptr, h->h_browptr.data(), sizeof(int64_t) * (h->n_owned + 1), cudaMemcpyHostToDevice, h->stream));
+  if (h->nnzb) NLS_CUDA(h, cudaMemcpyAsync(h->d_bcol, h->h_bcol.data(), sizeof(int32_t) * h->nnzb, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_diag, 0, sizeof(int32_t) * h->nrows, h->stream));
+  NLS_TRY(nls_launch_expand_pattern(h));
+  NLS_TRY(nls_launch_build_pos(h));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_pattern = true;
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_pattern_size(nls_handle h, int64_t *nrows, int64_t *nnz) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_pattern_size: call nls_build_pattern first");
+  if (nrows) *nrows = h->nrows;
+  if (nnz) *nnz = h->nnz;
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_get_pattern(nls_handle h, int64_t *rowptr, int32_t *colind) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_get_pattern: call nls_build_pattern first");
+  if (rowptr) NLS_CUDA(h, cudaMemcpyAsync(rowptr, h->d_rowptr, sizeof(int64_t) * (h->nrows + 1), cudaMemcpyDeviceToHost, h->stream));
+  if (colind && h->nnz) NLS_CUDA(h, cudaMemcpyAsync(colind, h->d_colind, sizeof(int32_t) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+// ---- operators ------------------------------------------------------------------------
+static int check_ready(nls_context *h, const char *who) {
+  if (!h->have_mesh || !h->have_disc || !h->have_mat || !h->have_pattern) {
+    h->err = std::string(who) + ": model incomplete (need mesh, discretization, material and pattern)";
+    return NLS_ERR_STATE;
+  }
+  if ((h->mat.kind == NLS_MAT_NEOHOOKEAN) != (h->dim > 1)) {
+    h->err = std::string(who) + ": material kind does not match the mesh dimension";
+    return NLS_ERR_UNSUPPORTED;
+  }
+  return NLS_OK;
+}
+
+// (::Residual)(fem,U,R,ctx) and/or (::Jacobian)(fem,U,K,ctx) on the device-resident U
+static int assemble(nls_context *h, bool want_r, bool want_k) {
+  NLS_TRY(nls_launch_apply_dirichlet(h, h->d_U));              // residual.jl:13 / jacobian.jl:11
+  NLS_TRY(nls_halo_exchange(h, h->d_U));
+  if (want_r) NLS_CUDA(h, cudaMemsetAsync(h->d_R, 0, sizeof(double) * h->nrows, h->stream));   // residual.jl:14
+  if (want_k) NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));  // jacobian.jl:13
+  NLS_TRY(nls_launch_assembly(h, want_r, want_k));
+  if (want_r) NLS_TRY(nls_launch_neumann(h, h->d_R));          // residual.jl:24-25
+  return NLS_OK;
+}
+
+static int host_assemble(nls_context *h, double *U, double *R, double *vals) {
+  NLS_TRY(check_ready(h, "assemble"));
+  if (!U) NLS_FAIL(h, NLS_ERR_ARG, "assemble: null U");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(assemble(h, R != nullptr, vals != nullptr));
+  NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, sizeof(double) * h->ndof_local(), cudaMemcpyDeviceToHost, h->stream));
+  if (R) NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  if (vals) NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_residual(nls_handle h, double *U, double *R) {
+  NLS_ENTER(h);
+  if (!R) NLS_FAIL(h, NLS_ERR_ARG, "nls_residual: null R");
+  return host_assemble(h, U, R, nullptr);
+}
+extern "C" int32_t nls_jacobian(nls_handle h, double *U, double *vals) {
+  NLS_ENTER(h);
+  if (!vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_jacobian: null vals");
+  return host_assemble(h, U, nullptr, vals);
+}
+extern "C" int32_t nls_residual_jacobian(nls_handle h, double *U, double *R, double *vals) {
+  NLS_ENTER(h);
+  if (!R || !vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_residual_jacobian: null output");
+  return host_assemble(h, U, R, vals);
+}
+
+// ---- Krylov hooks -----------------------------------------------------------------------
+extern "C" int32_t nls_set_values(nls_handle h, const double *vals) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_values: call nls_build_pattern first");
+  if (!vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_values: null vals");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_vals, vals, sizeof(double) * h->nnz, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_spmv(nls_handle h, const double *x, double *y) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_spmv: call nls_build_pattern first");
+  if (!x || !y) NLS_FAIL(h, NLS_ERR_ARG, "nls_spmv: null vector");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_p, x, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(nls_halo_exchange(h, h->d_p));
+  NLS_TRY(nls_launch_spmv(h, h->d_p, h->d_Ap, false, false));
+  NLS_CUDA(h, cudaMemcpyAsync(y, h->d_Ap, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_dot(nls_handle h, int64_t n, const double *x, const double *y, double *out) {
+  NLS_ENTER(h);
+  if (!h->have_mesh || n < 0 || n > h->ndof_local() || !x || !y || !out) NLS_FAIL(h, NLS_ERR_ARG, "nls_dot: bad arguments (n must be <= local DoFs)");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_tmp, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_b, y, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  return nls_dev_dot(h, n, h->d_tmp, h->d_b, out);
+}
+
+extern "C" int32_t nls_axpy(nls_handle h, int64_t n, double a, const double *x, double *y) {
+  NLS_ENTER(h);
+  if (!h->have_mesh || n < 0 || n > h->ndof_local() || !x || !y) NLS_FAIL(h, NLS_ERR_ARG, "nls_axpy: bad arguments (n must be <= local DoFs)");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_tmp, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_b, y, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(nls_launch_axpy(h, n, a, h->d_tmp, h->d_b));
+  NLS_CUDA(h, cudaMemcpyAsync(y, h->d_b, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_linear_solve(nls_handle h, double rtol, int32_t maxits, const double *b, double *x,
+                                    int32_t *its, double *relres, int32_t *status_out) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_linear_solve: call nls_build_pattern first");
+  if (!b || !x || maxits < 0) NLS_FAIL(h, NLS_ERR_ARG, "nls_linear_solve: bad arguments");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_b, b, sizeof(double) * h->nrows, cudaMemcpyHostToDevice, h->stream));
+  int li = 0, st = 0; double rr = 0.0;
+  NLS_TRY(nls_pcg_solve(h, rtol, maxits, 0, &li, &rr, &st));
+  NLS_CUDA(h, cudaMemcpyAsync(x, h->d_dU, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (its) *its = li;
+  if (relres) *relres = rr;
+  if (status_out) *status_out = st;
+  return NLS_OK;
+}
+
+// ---- Newton ---------------------------------------------------------------------------
+static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// One linear solve of K dU = -R on the free block, dU = 0 on constrained DoFs (newton_fem.jl:158)
+static int newton_linear(nls_context *h, double lin_rtol, int lin_maxits, int *lin_its, int *status) {
+  const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((h->nrows + 255) / 256, (int64_t)h->sm_count * 8));
+  k_negate_into<<<g, 256, 0, h->stream>>>(h->nrows, h->d_R, h->d_b);
+  h->launches++;
+  double rr;
+  return nls_pcg_solve(h, lin_rtol, lin_maxits, 0, lin_its, &rr, status);
+}
+
+// solve!(solver::NewtonSolver, U0) on the device-resident U (h->d_U holds U0 on entry)
+static int newton_loop(nls_context *h, const nls_newton_opts *o, double *hist, nls_newton_result *res) {
+  NLS_TRY(check_ready(h, "nls_newton_solve"));
+  if (!o || !res || o->maxits < 0) NLS_FAIL(h, NLS_ERR_ARG, "nls_newton_solve: bad options");
+  std::memset(res, 0, sizeof(*res));
+  int rc = NLS_OK, nh = 0, its = 0, lin_total = 0;
+  NLS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+  NLS_TRY(assemble(h, true, true));                                        // :137-138
+  NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
+  double norm_r = nls_dev_masked_norm2(h, h->d_R, true, &rc);              // :140-141
+  if (rc) return rc;
+  res->ms_assembly += elapsed(h->ev2, h->ev3);
+  const double norm_r0 = norm_r > 2.220446049250313e-16 ? norm_r : 1.0;    // :143
+  int reason = NLS_REASON_NOT_YET_CONVERGED;
+  if (hist) hist[nh++] = norm_r;
+  bool finished = false;
+  while (its < o->maxits) {                                                // :145
+    if (norm_r / norm_r0 < o->rtol) { reason = NLS_REASON_CONVERGED_RELATIVE; break; }   // :146-150
+    if (norm_r < o->atol) { reason = NLS_REASON_CONVERGED_ABSOLUTE; break; }             // :151-155
+    int li = 0, st = 0;
+    NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    NLS_TRY(newton_linear(h, o->lin_rtol, o->lin_maxits, &li, &st));       // :158
+    NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
+    lin_total += li;
+    if (st != 0) { reason = NLS_REASON_DIVERGED_LINEAR_SOLVE; finished = true; }         // :159-167
+    double nd = 0.0;
+    if (!finished) {
+      nd = nls_dev_masked_norm2(h, h->d_dU, false, &rc);                   // norm(dU), :168
+      if (rc) return rc;
+    } else NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    res->ms_linear += elapsed(h->ev2, h->ev3);
+    if (finished) break;
+    if (nd > o->dtol) { reason = NLS_REASON_DIVERGED_STEP; finished = true; break; }     // :168-172
+    NLS_TRY(nls_launch_axpy(h, h->nrows, 1.0, h->d_dU, h->d_U));           // :173
+    NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    NLS_TRY(assemble(h, true, !o->type_modified));                         // :174-179
+    NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
+    norm_r = nls_dev_masked_norm2(h, h->d_R, true, &rc);                   // :180
+    if (rc) return rc;
+    res->ms_assembly += elapsed(h->ev2, h->ev3);
+    its++;                                                                 // :181
+    if (hist) hist[nh++] = norm_r;
+  }
+  if (!finished && its >= o->maxits) reason = NLS_REASON_DIVERGED_MAXITS;  // :184-187
+  NLS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  res->ms_total = elapsed(h->ev0, h->ev1);
+  res->reason = reason; res->iterations = its; res->lin_its_total = lin_total; res->nhist = nh;
+  res->norm_r = norm_r; res->norm_r0 = norm_r0;
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_newton_solve(nls_handle h, const nls_newton_opts *opts, const double *U0, double *U, double *R,
+                                    double *norm_hist, nls_newton_result *res) {
+  NLS_ENTER(h);
+  if (!U0 || !U) NLS_FAIL(h, NLS_ERR_ARG, "nls_newton_solve: null U0/U");
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_newton_solve: model incomplete");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U0, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));  // :135
+  NLS_TRY(newton_loop(h, opts, norm_hist, res));
+  NLS_TRY(nls_halo_exchange(h, h->d_U));
+  NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, sizeof(double) * h->ndof_local(), cudaMemcpyDeviceToHost, h->stream));
+  if (R) NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+// ---- device-resident variants --------------------------------------------------------------
+extern "C" int32_t nls_dev_upload_u(nls_handle h, const double *U) {
+  NLS_ENTER(h);
+  if (!h->have_mesh || !U) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_upload_u: no mesh or null U");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_dev_download_u(nls_handle h, double *U) {
+  NLS_ENTER(h);
+  if (!h->have_mesh || !U) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_download_u: no mesh or null U");
+  NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, sizeof(double) * h->ndof_local(), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_dev_download_r(nls_handle h, double *R) {
+  NLS_ENTER(h);
+  if (!h->have_pattern || !R) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_download_r: no pattern or null R");
+  NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_dev_download_vals(nls_handle h, double *vals) {
+  NLS_ENTER(h);
+  if (!h->have_pattern || !vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_download_vals: no pattern or null vals");
+  NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_dev_assemble(nls_handle h, int32_t want_residual, int32_t want_jacobian) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_dev_assemble"));
+  return assemble(h, want_residual != 0, want_jacobian != 0);
+}
+extern "C" int32_t nls_dev_spmv(nls_handle h) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_dev_spmv: call nls_build_pattern first");
+  return nls_launch_spmv(h, h->d_U, h->d_Ap, false, false);
+}
+extern "C" int32_t nls_dev_pcg_iterations(nls_handle h, int32_t niter) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_dev_pcg_iterations"));
+  if (niter < 1) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_pcg_iterations: niter must be >= 1");
+  const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((h->nrows + 255) / 256, (int64_t)h->sm_count * 8));
+  k_negate_into<<<g, 256, 0, h->stream>>>(h->nrows, h->d_R, h->d_b);
+  h->launches++;
+  int li, st; double rr;
+  return nls_pcg_solve(h, 0.0, niter, niter, &li, &rr, &st);
+}
+extern "C" int32_t nls_dev_newton_step(nls_handle h, double lin_rtol, int32_t lin_maxits, int32_t *lin_its, double *norm_r) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_dev_newton_step"));
+  int rc = NLS_OK, li = 0, st = 0;
+  NLS_TRY(assemble(h, true, true));
+  NLS_TRY(newton_linear(h, lin_rtol, lin_maxits, &li, &st));
+  NLS_TRY(nls_launch_axpy(h, h->nrows, 1.0, h->d_dU, h->d_U));
+  NLS_TRY(assemble(h, true, false));
+  const double nr = nls_dev_masked_norm2(h, h->d_R, true, &rc);
+  if (rc) return rc;
+  if (lin_its) *lin_its = li;
+  if (norm_r) *norm_r = nr;
+  return NLS_OK;
+}
+extern "C" int32_t nls_dev_newton_solve(nls_handle h, const nls_newton_opts *opts, double *norm_hist, nls_newton_result *res) {
+  NLS_ENTER(h);
+  return newton_loop(h, opts, norm_hist, res);
+}
+extern "C" int32_t nls_sync(nls_handle h) {
+  NLS_ENTER(h);
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_timer_start(nls_handle h) {
+  NLS_ENTER(h);
+  NLS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_timer_stop(nls_handle h, float *ms) {
+  NLS_ENTER(h);
+  NLS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  NLS_CUDA(h, cudaEventSynchronize(h->ev1));
+  if (ms) *ms = elapsed(h->ev0, h->ev1);
+  return NLS_OK;
+}
+extern "C" int32_t nls_flush_l2(nls_handle h) {
+  NLS_ENTER(h);
+  if (!h->d_flush) {
+    h->flush_bytes = (size_t)256 << 20;  // > 126 MB L2
+    NLS_CUDA(h, cudaMalloc(&h->d_flush, h->flush_bytes));
+  }
+  NLS_CUDA(h, cudaMemsetAsync(h->d_flush, 0x5a, h->flush_bytes, h->stream));
+  return NLS_OK;
+}
+extern "C" int64_t nls_kernel_launches(nls_handle h) { return h ? h->launches : 0; }
+
+extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) {
+  NLS_ENTER(h);
+  if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
+  if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
+  NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: unknown key");
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------
+extern "C" int32_t nls_set_halo(nls_handle h, int64_t n_owned_nodes, int32_t nneigh, const int32_t *neigh_ranks,
+                                const int64_t *send_ptr, const int32_t *send_nodes,
+                                const int64_t *recv_ptr, const int32_t *recv_nodes) {
+  NLS_ENTER(h);
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_halo: call nls_set_mesh first");
+  if (n_owned_nodes < 0 || n_owned_nodes > h->nn || nneigh < 0) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: bad sizes");
+  if (nneigh > 0 && (!neigh_ranks || !send_ptr || !recv_ptr)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: null lists");
+  free_pattern(h);
+  h->n_owned = n_owned_nodes;
+  h->nneigh = nneigh;
+  h->neigh.assign(neigh_ranks, neigh_ranks + nneigh);
+  h->send_ptr.assign(1, 0); h->recv_ptr.assign(1, 0);
+  if (nneigh > 0) { h->send_ptr.assign(send_ptr, send_ptr + nneigh + 1); h->recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1); }
+  const int64_t ns = h->send_ptr.back(), nr = h->recv_ptr.back();
+  for (int64_t k = 0; k < ns; ++k) if (send_nodes[k] < 0 || send_nodes[k] >= h->n_owned) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: send node is not an owned node");
+  for (int64_t k = 0; k < nr; ++k) if (recv_nodes[k] < h->n_owned || recv_nodes[k] >= h->nn) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: recv node is not a ghost node");
+  NLS_TRY(dev_alloc(h, &h->d_send_nodes, (size_t)ns)); NLS_TRY(dev_alloc(h, &h->d_recv_nodes, (size_t)nr));
+  NLS_TRY(dev_alloc(h, &h->d_sendbuf, (size_t)(ns * h->dim))); NLS_TRY(dev_alloc(h, &h->d_recvbuf, (size_t)(nr * h->dim)));
+  if (ns) NLS_CUDA(h, cudaMemcpyAsync(h->d_send_nodes, send_nodes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, h->stream));
+  if (nr) NLS_CUDA(h, cudaMemcpyAsync(h->d_recv_nodes, recv_nodes, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_comm_unique_id(const char *nccl_lib_path, uint8_t *id128) {
+  if (!id128) { g_noctx_error = "nls_comm_unique_id: null id"; return NLS_ERR_ARG; }
+  std::string e = g_nccl.load(nccl_lib_path);
+  if (!e.empty()) { g_noctx_error = e; return NLS_ERR_NCCL; }
+  NcclDynId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { g_noctx_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc); return NLS_ERR_NCCL; }
+  std::memcpy(id128, id.internal, NCCL_DYN_ID_BYTES);
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_comm_init(nls_handle h, const char *nccl_lib_path, int32_t rank, int32_t nranks, const uint8_t *id128) {
+  NLS_ENTER(h);
+  if (!id128 || rank < 0 || rank >= nranks) NLS_FAIL(h, NLS_ERR_ARG, "nls_comm_init: bad arguments");
+  std::string e = g_nccl.load(nccl_lib_path);
+  if (!e.empty()) NLS_FAIL(h, NLS_ERR_NCCL, e);
+  h->nccl = &g_nccl;
+  NcclDynId id;
+  std::memcpy(id.internal, id128, NCCL_DYN_ID_BYTES);
+  void *comm = nullptr;
+  int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (rc != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+  h->comm = comm; h->rank = rank; h->nranks = nranks; h->distributed = true;
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_dev_halo_exchange_u(nls_handle h) {
+  NLS_ENTER(h);
+  NLS_TRY(nls_halo_exchange(h, h->d_U));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}

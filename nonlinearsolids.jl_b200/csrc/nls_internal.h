@@ -1,0 +1,161 @@
+// nls_internal.h -- shared declarations of libnls_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/nls_b200.h"
+
+#define NLS_MAX_NEN1D 8   // 1-D Lagrange order p <= 7
+#define NLS_MAX_NQ 5      // gauss_quadrature(1..5), quadrature.jl:29-50
+
+// ---- shape/quadrature tables, passed to kernels by value (__grid_constant__) ----
+struct Tab1D {            // dN_i/dxi at each Gauss point, shapefunctions.jl:64-81
+  int m, nq;
+  double w[NLS_MAX_NQ];
+  double dN[NLS_MAX_NQ][NLS_MAX_NEN1D];
+};
+struct TabQ1 {            // tensor-product Q1: [qp][node][ref dir], x fastest
+  int dim, nen, nqp;
+  double w[8];
+  double dN[8][8][3];
+};
+struct MatParams {
+  int kind;
+  double p[8];
+  double area;
+};
+
+// ---- host-side tabulation with the reference formulas (host_tables.cpp) ----
+void nls_host_lagrange_nodes(int p, int kind, double *nodes);
+void nls_host_lagrange_weights(int m, const double *nodes, double *w);
+void nls_host_shape_N(int m, const double *x, const double *w, double xi, double *N);
+void nls_host_shape_dN(int m, const double *x, const double *w, double xi, double *dN);
+int nls_host_gauss(int nq, double *x, double *w);
+int nls_host_tab1d(int p, int nq, Tab1D *t);
+int nls_host_tabq1(int dim, TabQ1 *t);
+
+// node-level sparsity pattern for the owned nodes (block rows); scalar CSR is its
+// dim x dim expansion. bcol ascending within a row.
+void nls_host_block_pattern(int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
+                            std::vector<int64_t> &browptr, std::vector<int32_t> &bcol);
+
+// ---- device control block of the PCG loop (lives in device memory) ----
+struct PcgCtl {
+  double rz, rz_new, pAp, rr, bb;   // reductions (global, after allreduce if distributed)
+  double alpha, beta;
+  double tol2;                      // lin_rtol^2
+  int iters;
+  int done;                         // 0 running, 1 converged, 2 maxits(not set on device), 3 breakdown
+  int maxits;
+  int pad;
+  double red[4];                    // scratch for allreduce: [0]=pAp partial, [1]=rz partial, [2]=rr partial
+};
+
+struct NcclApi;                     // nccl_dyn.h
+
+struct nls_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+
+  // mesh
+  int dim = 0, nen = 0;
+  int64_t nn = 0, nel = 0, n_owned = 0;
+  std::vector<int32_t> h_conn;
+  int32_t *d_conn = nullptr;
+  double *d_coords = nullptr;
+  bool have_mesh = false;
+
+  // discretisation / material
+  int p = 1, nq = 2;
+  bool have_disc = false;
+  Tab1D tab1{};
+  TabQ1 tabq{};
+  MatParams mat{};
+  bool have_mat = false;
+
+  // boundaries (deduplicated, last write wins like sequential apply!)
+  int64_t ndir = 0, ndir_user = 0;
+  std::vector<int64_t> dir_user_dofs;   // as given (may hold duplicates)
+  std::vector<int64_t> dir_slot;        // user index -> unique slot or -1 if overridden
+  int64_t *d_dir_dofs = nullptr;
+  double *d_dir_vals = nullptr;
+  uint8_t *d_con = nullptr;             // constrained mask, ndof_local
+  int64_t nneu = 0;
+  int64_t *d_neu_dofs = nullptr;
+  double *d_neu_vals = nullptr;
+
+  // pattern
+  bool have_pattern = false;
+  int64_t nrows = 0, nnz = 0, nnzb = 0;
+  std::vector<int64_t> h_browptr;
+  std::vector<int32_t> h_bcol;
+  int64_t *d_browptr = nullptr;
+  int32_t *d_bcol = nullptr;
+  int64_t *d_rowptr = nullptr;
+  int32_t *d_colind = nullptr;
+  double *d_vals = nullptr;
+  uint16_t *d_pos = nullptr;            // [nel][nen][nen] position of node b in block row of node a
+  int32_t *d_diag = nullptr;            // [nrows] offset of the diagonal entry within its row
+
+  // vectors (ndof_local unless noted)
+  double *d_U = nullptr, *d_R = nullptr, *d_dU = nullptr;
+  double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr, *d_b = nullptr;
+  double *d_tmp = nullptr;
+  double *d_partial = nullptr;          // block partial sums
+  PcgCtl *d_ctl = nullptr;
+  PcgCtl *h_ctl = nullptr;              // pinned mirror
+  double *d_scal = nullptr;             // small scalar scratch (8 doubles)
+  double *h_scal = nullptr;             // pinned
+
+  // plastic state [nel][nq]
+  double *d_state[9] = {nullptr};       // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
+  double *d_u_n = nullptr;              // [nel][nen]
+
+  // L2 flush scratch
+  void *d_flush = nullptr;
+  size_t flush_bytes = 0;
+
+  // options
+  int opt_assembly = 0;
+
+  // distributed
+  bool distributed = false;
+  int rank = 0, nranks = 1;
+  int nneigh = 0;
+  std::vector<int> neigh;
+  std::vector<int64_t> send_ptr, recv_ptr;   // in nodes
+  int32_t *d_send_nodes = nullptr, *d_recv_nodes = nullptr;
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  NcclApi *nccl = nullptr;
+  void *comm = nullptr;
+
+  int64_t ndof_local() const { return nn * (int64_t)dim; }
+};
+
+// error helpers
+#define NLS_FAIL(h, code, msg) do { (h)->err = (msg); return (code); } while (0)
+#define NLS_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+  (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return NLS_ERR_CUDA; } } while (0)
+
+// ---- kernel launchers (kernels_assembly.cu / kernels_krylov.cu) ----
+int nls_launch_assembly(nls_context *h, bool want_r, bool want_k);
+int nls_launch_apply_dirichlet(nls_context *h, double *U);
+int nls_launch_neumann(nls_context *h, double *R);
+int nls_launch_build_pos(nls_context *h);
+int nls_launch_expand_pattern(nls_context *h);
+int nls_launch_commit_state(nls_context *h, const double *dU);
+
+int nls_launch_spmv(nls_context *h, const double *x, double *y, bool masked, bool with_dot);
+int nls_launch_extract_dinv(nls_context *h);
+double nls_dev_masked_norm2(nls_context *h, const double *v, bool masked, int *rc);  // sqrt(sum v_i^2) over owned (free) DoFs
+int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, double *out);
+int nls_launch_axpy(nls_context *h, int64_t n, double a, const double *x, double *y);
+int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int *its, double *relres, int *status);
+
+int nls_halo_exchange(nls_context *h, double *v);
+int nls_allreduce_sum(nls_context *h, double *dptr, int count);

@@ -1,0 +1,61 @@
+"""Host-side mirror of src/gallery/residual.jl and jacobian.jl: the functors NewtonSolver calls.
+
+Calling them runs the element loop on the GPU through the C ABI with host buffers, with the
+reference's in/out contract: U comes back with its Dirichlet entries overwritten.
+"""
+import numpy as np
+
+from ._lib import dptr
+
+
+class CSRMatrix:
+    """Jacobian storage: CSR values over the model's precomputed pattern (replaces Matrix{Float64})."""
+
+    def __init__(self, fem):
+        self.rowptr, self.colind = fem.pattern()
+        self.vals = np.zeros(len(self.colind))
+        self.shape = (len(self.rowptr) - 1, fem.ndof)
+
+    def toarray(self):
+        A = np.zeros(self.shape)
+        for i in range(self.shape[0]):
+            s, e = self.rowptr[i], self.rowptr[i + 1]
+            A[i, self.colind[s:e]] = self.vals[s:e]
+        return A
+
+
+class Residual:
+    """Residual(material, externalforces=[]) (residual.jl:5-9). R = F_int(U) - F_ext."""
+
+    def __init__(self, material, externalforces=()):
+        if len(externalforces):
+            raise NotImplementedError("external force functors are not on the device path yet (SURVEY 8f-1)")
+        self.material = material
+        self.externalforces = list(externalforces)
+
+    def __call__(self, fem, U, R, ctx=None):
+        if not (isinstance(U, np.ndarray) and U.dtype == np.float64 and U.flags.c_contiguous):
+            raise TypeError("U must be a contiguous float64 array (it is updated in place)")
+        fem.handle(self.material).call("nls_residual", dptr(U), dptr(R))
+
+
+class Jacobian:
+    """Jacobian(material, dexternalforces=[]) (jacobian.jl:3-7). K = dF_int/dU in CSR."""
+
+    def __init__(self, material, dexternalforces=()):
+        if len(dexternalforces):
+            raise NotImplementedError("external force tangents are not on the device path yet")
+        self.material = material
+        self.dexternalforces = list(dexternalforces)
+
+    def __call__(self, fem, U, K, ctx=None):
+        if not (isinstance(U, np.ndarray) and U.dtype == np.float64 and U.flags.c_contiguous):
+            raise TypeError("U must be a contiguous float64 array (it is updated in place)")
+        vals = K.vals if isinstance(K, CSRMatrix) else K
+        fem.handle(self.material).call("nls_jacobian", dptr(U), dptr(vals))
+
+
+def residual_jacobian(material, fem, U, R, K):
+    """Both operators from one element pass (same results as Residual then Jacobian)."""
+    vals = K.vals if isinstance(K, CSRMatrix) else K
+    fem.handle(material).call("nls_residual_jacobian", dptr(U), dptr(R), dptr(vals))
