@@ -90,6 +90,11 @@ int32_t nls_shape_eval(int32_t m, const double *nodes, const double *weights, do
 /* gauss_quadrature(order) (src/fem/quadrature.jl:29-50), order 1..5 */
 int32_t nls_gauss_quadrature(int32_t nq, double *points, double *weights);
 
+/* The CSR pattern builder on its own (what nls_build_pattern computes on the host): rows of the
+ * first n_owned nodes, columns ascending. Two-pass: colind == NULL returns only rowptr / nnz. */
+int32_t nls_pattern_host(int32_t dim, int32_t nen, int64_t nelem, const int32_t *conn0, int64_t nnodes,
+                         int64_t n_owned_nodes, int64_t *rowptr, int32_t *colind, int64_t *nnz);
+
 /* ---- model description ---------------------------------------------------- */
 /* Mesh / Element (src/fem/element.jl:6-12,73-83): flattened connectivity + coordinates.
  * nen = p+1 (1-D), 4 (2-D Q1, tensor order x-fastest), 8 (3-D Q1). */

@@ -5,7 +5,7 @@ package is the host-side mirror of the reference's Julia API for that path -- me
 materials, Residual/Jacobian functors, NewtonSolver, PseudoTimeStepper -- calling the ABI
 through ctypes exactly as the Julia `ccall` shim in julia/NonlinearSolidsB200.jl does.
 """
-from . import _lib
+from . import _lib, distributed
 from ._lib import Handle, NLSError, lib
 from .fem import (Dirichlet, Element, ElementBoundary, FEMModel, Lagrange, Mesh, N, Neumann, Quadrature,
                   TimeDependent, dN, gauss_quadrature, getstate, integrate, interpolate, lagrange)

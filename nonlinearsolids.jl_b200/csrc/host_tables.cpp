@@ -247,3 +247,25 @@ extern "C" int32_t nls_gauss_quadrature(int32_t nq, double *points, double *weig
   if (!points || !weights) return NLS_ERR_ARG;
   return nls_host_gauss(nq, points, weights) ? NLS_ERR_ARG : NLS_OK;
 }
+extern "C" int32_t nls_pattern_host(int32_t dim, int32_t nen, int64_t nelem, const int32_t *conn0, int64_t nnodes,
+                                    int64_t n_owned_nodes, int64_t *rowptr, int32_t *colind, int64_t *nnz) {
+  if (dim < 1 || dim > 3 || nen < 1 || nelem < 0 || nnodes < 0 || n_owned_nodes < 0 || n_owned_nodes > nnodes || !rowptr || !nnz ||
+      (nelem > 0 && !conn0)) return NLS_ERR_ARG;
+  for (int64_t k = 0; k < nelem * nen; ++k) if (conn0[k] < 0 || conn0[k] >= nnodes) return NLS_ERR_ARG;
+  std::vector<int64_t> browptr; std::vector<int32_t> bcol;
+  nls_host_block_pattern(nen, nelem, conn0, nnodes, n_owned_nodes, browptr, bcol);
+  int64_t pos = 0;
+  for (int64_t a = 0; a < n_owned_nodes; ++a) {
+    const int64_t b0 = browptr[a], deg = browptr[a + 1] - b0;
+    for (int i = 0; i < dim; ++i) {
+      rowptr[a * dim + i] = pos;
+      if (colind)
+        for (int64_t j = 0; j < deg; ++j)
+          for (int k = 0; k < dim; ++k) colind[pos + j * dim + k] = bcol[b0 + j] * dim + k;
+      pos += deg * dim;
+    }
+  }
+  rowptr[n_owned_nodes * dim] = pos;
+  *nnz = pos;
+  return NLS_OK;
+}

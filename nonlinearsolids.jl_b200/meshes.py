@@ -12,34 +12,44 @@ def bar_mesh(nel, p=1, length=1.0):
     return Mesh(1, conn, coords=coords)
 
 
+def _shape(n, dim):
+    """(n, dim) -> per-axis node counts (x, y[, z]); a tuple is taken as is (slowest axis last)."""
+    return tuple(int(v) for v in n) if np.ndim(n) else (int(n),) * dim
+
+
 def _grid_conn(n, dim, k0=0, k1=None):
-    """Q1 connectivity of an n^dim-node grid (x fastest), element layers k0..k1 of the slowest axis."""
-    k1 = (n - 1) if k1 is None else k1
+    """Q1 connectivity of a structured grid (x fastest), element layers k0..k1 of the slowest axis."""
+    sh = _shape(n, dim)
+    k1 = (sh[-1] - 1) if k1 is None else k1
+    nx = sh[0]
     if dim == 2:
-        ei, ej = np.meshgrid(np.arange(n - 1), np.arange(k0, k1), indexing="xy")
-        base = (ei + n * ej).ravel().astype(np.int64)
-        offs = np.array([0, 1, n, n + 1], dtype=np.int64)
+        ei, ej = np.meshgrid(np.arange(nx - 1), np.arange(k0, k1), indexing="xy")
+        base = (ei + nx * ej).ravel().astype(np.int64)
+        offs = np.array([0, 1, nx, nx + 1], dtype=np.int64)
     else:
-        ek, ej, ei = np.meshgrid(np.arange(k0, k1), np.arange(n - 1), np.arange(n - 1), indexing="ij")
-        base = (ei + n * (ej + n * ek)).ravel().astype(np.int64)
-        offs = np.array([0, 1, n, n + 1, n * n, n * n + 1, n * n + n, n * n + n + 1], dtype=np.int64)
+        ny = sh[1]
+        ek, ej, ei = np.meshgrid(np.arange(k0, k1), np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+        base = (ei + nx * (ej + ny * ek)).ravel().astype(np.int64)
+        pl = nx * ny
+        offs = np.array([0, 1, nx, nx + 1, pl, pl + 1, pl + nx, pl + nx + 1], dtype=np.int64)
     return base[:, None] + offs[None, :]
 
 
 def grid_coords(n, dim, k0=0, k1=None):
-    """Coordinates i/(n-1) of node planes k0..k1 (exclusive) of the slowest axis."""
-    k1 = n if k1 is None else k1
-    x = np.arange(n) / (n - 1)
-    s = np.arange(k0, k1) / (n - 1)
+    """Coordinates i/(nx-1) (exactly) of node planes k0..k1 (exclusive) of the slowest axis."""
+    sh = _shape(n, dim)
+    k1 = sh[-1] if k1 is None else k1
+    ax = [np.arange(m) / (sh[0] - 1) for m in sh[:-1]] + [np.arange(k0, k1) / (sh[0] - 1)]
     if dim == 2:
-        X, Y = np.meshgrid(x, s, indexing="xy")
+        X, Y = np.meshgrid(ax[0], ax[1], indexing="xy")
         return np.stack([X.ravel(), Y.ravel()], axis=1)
-    Z, Y, X = np.meshgrid(s, x, x, indexing="ij")
+    Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
     return np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
 
 
 def grid_mesh(n, dim):
-    """Unit square / cube, n nodes per side, Q1 elements, lexicographic numbering (x fastest)."""
+    """Structured Q1 mesh, lexicographic numbering (x fastest). n: nodes per side, or a tuple of
+    per-axis node counts (slowest axis last); n-per-side gives the unit square / cube."""
     return Mesh(dim, _grid_conn(n, dim).astype(np.int32), coords=grid_coords(n, dim))
 
 
@@ -58,12 +68,12 @@ def smooth_field(coords, amp=0.01):
 
 
 def face_nodes(n, dim, axis, side):
-    """Node ids on the face `axis` = 0 (side 0) or 1 (side 1) of the unit grid."""
-    idx = np.arange(n ** dim).reshape((n,) * dim)   # [.., y, x]: axis d is array axis dim-1-d
+    """Node ids on the face `axis` = const (side 0: low, 1: high) of the structured grid."""
+    sh = _shape(n, dim)
+    idx = np.arange(int(np.prod(sh))).reshape(sh[::-1])   # [.., y, x]: axis d is array axis dim-1-d
     sl = [slice(None)] * dim
-    sl[dim - 1 - axis] = 0 if side == 0 else n - 1
-    nodes = np.sort(idx[tuple(sl)].ravel())
-    return nodes
+    sl[dim - 1 - axis] = 0 if side == 0 else sh[axis] - 1
+    return np.sort(idx[tuple(sl)].ravel())
 
 
 def slab_planes(n, nranks):
@@ -72,16 +82,17 @@ def slab_planes(n, nranks):
 
 
 def slab_local_mesh(n, dim, nranks, rank):
-    """Closed-form local slab of the unit grid for `rank`: local mesh (owned nodes first, then the
-    ghost planes below/above), halo lists, and the local->global node map. Matches nls_partition
-    applied to the global mesh (tests check this bit-exactly on small grids)."""
-    cuts = slab_planes(n, nranks)
+    """Closed-form local slab of a structured grid for `rank`: local mesh (owned nodes first, then
+    the ghost planes below/above), halo lists, and the local->global node map. Matches
+    nls_partition applied to the global mesh (tests check this bit-exactly on small grids)."""
+    sh = _shape(n, dim)
+    ns = sh[-1]
+    cuts = slab_planes(ns, nranks)
     p0, p1 = cuts[rank], cuts[rank + 1]
-    plane = n ** (dim - 1)
-    has_lo, has_hi = p0 > 0 and p1 > p0, p1 < n and p1 > p0
+    plane = int(np.prod(sh[:-1]))
+    has_lo, has_hi = p0 > 0 and p1 > p0, p1 < ns and p1 > p0
     g0, g1 = p0 - (1 if has_lo else 0), p1 + (1 if has_hi else 0)   # node planes present locally
     n_owned = (p1 - p0) * plane
-    # global node ids present, in local order: owned, then ghosts ascending (low plane, high plane)
     owned = np.arange(p0 * plane, p1 * plane, dtype=np.int64)
     ghosts = []
     if has_lo:
@@ -89,10 +100,8 @@ def slab_local_mesh(n, dim, nranks, rank):
     if has_hi:
         ghosts.append(np.arange(p1 * plane, (p1 + 1) * plane, dtype=np.int64))
     l2g = np.concatenate([owned] + ghosts) if ghosts else owned
-    # elements touching an owned node: layers g0..g1-1
-    conn_g = _grid_conn(n, dim, g0, g1 - 1)
-    g2l = {}
-    # vectorised global->local: owned block, low ghost block, high ghost block
+    conn_g = _grid_conn(sh, dim, g0, g1 - 1)          # elements touching an owned node
+
     def to_local(g):
         out = np.empty_like(g)
         m_own = (g >= p0 * plane) & (g < p1 * plane)
@@ -103,7 +112,7 @@ def slab_local_mesh(n, dim, nranks, rank):
         out[m_hi] = n_owned + (plane if has_lo else 0) + (g[m_hi] - p1 * plane)
         return out
     conn_l = to_local(conn_g).astype(np.int32)
-    coords = grid_coords(n, dim)[l2g] if n ** dim <= 2_000_000 else _coords_of(l2g, n, dim)
+    coords = _coords_of(l2g, sh, dim)
     neigh, send_ptr, send_nodes, recv_ptr, recv_nodes = [], [0], [], [0], []
     if has_lo:   # neighbour rank-1: send my lowest owned plane, receive its highest
         neigh.append(rank - 1)
@@ -122,10 +131,11 @@ def slab_local_mesh(n, dim, nranks, rank):
                 recv_nodes=cat(recv_nodes), elem_layers=(g0, g1 - 1), node_off=[c * plane for c in cuts])
 
 
-def _coords_of(gids, n, dim):
+def _coords_of(gids, sh, dim):
+    """Coordinates of global node ids on a structured grid with spacing 1/(nx-1)."""
     g = np.asarray(gids, dtype=np.int64)
     out = np.zeros((len(g), dim))
     for d in range(dim):
-        out[:, d] = (g % n) / (n - 1)
-        g = g // n
+        out[:, d] = (g % sh[d]) / (sh[0] - 1)
+        g = g // sh[d]
     return out

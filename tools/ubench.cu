@@ -28,7 +28,7 @@ __global__ void k_scatter(double *a, size_t n_groups, int run, size_t total_ops,
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total_ops; t += (size_t)gridDim.x * blockDim.x) {
     size_t g = t / run; int r = (int)(t % run);
     size_t gg = contiguous ? g : ((g * 2654435761ull) & mask);
-    if (!contiguous && gg >= n_groups) gg -= n_groups / 2;
+    if (!contiguous) gg = ((g * 2654435761ull) & mask) % n_groups;
     double *p = a + gg * run + r;
     if (MODE == 0) atomicAdd(p, 1.0);
     else if (MODE == 1) *p += 1.0;
