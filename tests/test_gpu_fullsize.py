@@ -121,9 +121,9 @@ from helpers import node_dofs, rel_err
 rank, world, lr = nls.distributed.env_rank()
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-uid = nls.distributed.broadcast_unique_id(dist, rank, device="cuda")
 dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
 for dim, shape, comp in [(2, (9, 14), -0.02), (3, (5, 4, 9), -0.05)]:
+    uid = nls.distributed.broadcast_unique_id(dist, rank, device="cuda")   # one NCCL id per communicator
     mat = nls.NeoHookean(E=1.0, nu=0.3)
     fem, part = nls.distributed.slab_model(nls.FEMModel, shape, dim, world, rank, lr, uid)
     gm = nls.grid_mesh(shape, dim)
