@@ -158,6 +158,8 @@ def run_ours(args):
     fem, mat, mesh, n_owned = build_local_model(nls, world, rank, local_rank, uid)
     H = fem.handle(mat)
     L = nls.lib()
+    if args.assembly is not None:
+        H.call("nls_set_option", b"assembly", args.assembly)
     nrows, nnz = C.c_int64(0), C.c_int64(0)
     H.call("nls_pattern_size", C.byref(nrows), C.byref(nnz))
     nrows, nnz = nrows.value, nnz.value
@@ -202,13 +204,14 @@ def run_ours(args):
         pin = lambda n: np.empty(n)
     Uh, Rh, Vh = pin(fem.ndof), pin(nrows), pin(nnz)
     Uh[:] = U0
-    for _ in range(max(1, args.warmup // 2)):
+    e2e_steps = 0 if args.skip_e2e else args.steps
+    for _ in range(0 if args.skip_e2e else max(1, args.warmup // 2)):
         H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))
-    e2e_s = allmax((time.perf_counter() - t0) / args.steps)
+    e2e_s = allmax((time.perf_counter() - t0) / max(1, e2e_steps)) or 1e-30
     barrier()
 
     # ---- Newton step (assembly + PCG + update + norm), device-resident ----
@@ -330,6 +333,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lin-rtol", dest="lin_rtol", type=float, default=1e-8)
     ap.add_argument("--skip-newton", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--assembly", type=int, default=None, help="0 atomic scatter, 1 gather/row-owner (default)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-rows", dest="cpu_rows", type=int, default=N_SIDE)
     a = ap.parse_args()

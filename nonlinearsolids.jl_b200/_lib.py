@@ -46,6 +46,7 @@ PROTOTYPES = {
     "nls_shape_eval": (C.c_int32, [C.c_int32, _dp, _dp, C.c_double, _dp, _dp]),
     "nls_gauss_quadrature": (C.c_int32, [C.c_int32, _dp, _dp]),
     "nls_pattern_host": (C.c_int32, [C.c_int32, C.c_int32, C.c_int64, _ip, C.c_int64, C.c_int64, _lp, _ip, _lp]),
+    "nls_plan_stats": (C.c_int32, [C.c_int32, C.c_int32, C.c_int64, _ip, C.c_int64, C.c_int64, _dp, C.c_int32, _lp]),
     "nls_set_mesh": (C.c_int32, [_H, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _ip, _dp]),
     "nls_set_discretization": (C.c_int32, [_H, C.c_int32, C.c_int32]),
     "nls_set_material": (C.c_int32, [_H, C.c_int32, _dp, C.c_int32]),

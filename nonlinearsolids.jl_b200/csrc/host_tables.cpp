@@ -269,3 +269,126 @@ extern "C" int32_t nls_pattern_host(int32_t dim, int32_t nen, int64_t nelem, con
   *nnz = pos;
   return NLS_OK;
 }
+
+// ---- cluster plan for the gather (row-owner) assembly ----------------------------------------
+// Owned nodes are grouped into spatially compact clusters of <= nc nodes (Morton order of the
+// quantised coordinates; works for any mesh, gives 8x8 tiles on a structured 2-D grid). A CTA
+// computes every element touching its cluster once into shared memory, then each cluster node
+// gathers its rows from there: no atomics, no zero-fill, rows written once, contributions summed
+// in ascending element order (the order of the reference's serial element loop, defaults.jl:77-81).
+static inline uint64_t spread_bits(uint64_t v, int dim) {
+  uint64_t r = 0;
+  for (int b = 0; b < 21; ++b) r |= ((v >> b) & 1ull) << (b * dim);
+  return r;
+}
+
+void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
+                           const double *coords, int nc, const std::vector<int64_t> *browptr,
+                           const std::vector<int32_t> *bcol, AsmPlan &plan) {
+  plan = AsmPlan();
+  plan.nc = nc;
+  if (n_owned == 0) { plan.eptr.assign(1, 0); plan.iptr.assign(1, 0); return; }
+  // Morton keys of the owned nodes. Coordinates are binned on a grid with about one node per
+  // bin (bins per axis = nodes^(1/dim) scaled by the aspect ratio), so on a structured mesh the
+  // bin index is the grid index and a Morton tile (key >> tile_bits) is an 8x8 (4x4x4) node tile.
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int64_t a = 0; a < n_owned; ++a)
+    for (int d = 0; d < dim; ++d) { lo[d] = std::min(lo[d], coords[a * dim + d]); hi[d] = std::max(hi[d], coords[a * dim + d]); }
+  double vol = 1.0;
+  for (int d = 0; d < dim; ++d) vol *= std::max(hi[d] - lo[d], 1e-300);
+  const double hbin = std::pow(vol / (double)n_owned, 1.0 / dim);   // ~ node spacing
+  int tile_bits = 0;
+  while ((1 << tile_bits) < nc) ++tile_bits;                        // nc = 64 -> 6 bits: 8x8 or 4x4x4
+  std::vector<std::pair<uint64_t, int32_t>> keyed((size_t)n_owned);
+  for (int64_t a = 0; a < n_owned; ++a) {
+    uint64_t key = 0;
+    for (int d = 0; d < dim; ++d) {
+      double b = std::floor((coords[a * dim + d] - lo[d]) / hbin + 0.5);
+      if (b < 0) b = 0;
+      if (b > 2097151.0) b = 2097151.0;
+      key |= spread_bits((uint64_t)b, dim) << d;
+    }
+    keyed[a] = {key, (int32_t)a};
+  }
+  std::sort(keyed.begin(), keyed.end());
+  // clusters: split the Morton order at tile boundaries, and every nc nodes inside a tile
+  std::vector<int64_t> cstart;
+  for (int64_t s = 0, in_tile = 0; s < n_owned; ++s) {
+    const bool new_tile = (s == 0) || ((keyed[s].first >> tile_bits) != (keyed[s - 1].first >> tile_bits));
+    if (new_tile || in_tile == nc) { cstart.push_back(s); in_tile = 0; }
+    ++in_tile;
+  }
+  cstart.push_back(n_owned);
+  // node -> incident elements
+  std::vector<int64_t> nptr(nn + 1, 0);
+  for (int64_t k = 0; k < nel * nen; ++k) nptr[conn[k] + 1]++;
+  for (int64_t i = 0; i < nn; ++i) nptr[i + 1] += nptr[i];
+  std::vector<int32_t> nidx(nptr[nn]);
+  {
+    std::vector<int64_t> cur(nptr.begin(), nptr.end() - 1);
+    for (int64_t e = 0; e < nel; ++e)
+      for (int a = 0; a < nen; ++a) nidx[cur[conn[e * nen + a]]++] = (int32_t)e;   // ascending e per node
+  }
+  const int64_t ncl = (int64_t)cstart.size() - 1;
+  plan.ncl = ncl;
+  plan.nodes.assign((size_t)(ncl * nc), -1);
+  plan.eptr.assign((size_t)ncl + 1, 0);
+  plan.iptr.assign((size_t)ncl + 1, 0);
+  std::vector<int32_t> el;
+  std::vector<uint32_t> items;
+  for (int64_t c = 0; c < ncl; ++c) {
+    el.clear(); items.clear();
+    const int64_t n0 = cstart[c], n1 = cstart[c + 1];
+    for (int64_t s = n0; s < n1; ++s) {
+      const int32_t a = keyed[s].second;
+      plan.nodes[c * nc + (s - n0)] = a;
+      el.insert(el.end(), nidx.begin() + nptr[a], nidx.begin() + nptr[a + 1]);
+    }
+    std::sort(el.begin(), el.end());
+    el.erase(std::unique(el.begin(), el.end()), el.end());
+    plan.max_elems = std::max<int>(plan.max_elems, (int)el.size());
+    for (int t = 0; t < (int)(n1 - n0); ++t) {
+      const int32_t a = plan.nodes[c * nc + t];
+      plan.max_adj = std::max<int>(plan.max_adj, (int)(nptr[a + 1] - nptr[a]));
+      for (int64_t k = nptr[a]; k < nptr[a + 1]; ++k) {   // ascending element id = rank order
+        const int32_t e = nidx[k];
+        const uint32_t slot = (uint32_t)(std::lower_bound(el.begin(), el.end(), e) - el.begin());
+        uint32_t al = 0;
+        while (conn[(int64_t)e * nen + al] != a) ++al;
+        const uint32_t rank = (uint32_t)(k - nptr[a]);
+        items.push_back(slot | (al << 12) | ((uint32_t)t << 16) | (rank << 24));
+      }
+    }
+    // lanes of one element adjacent (broadcast reads), elements ascending
+    std::sort(items.begin(), items.end(), [](uint32_t x, uint32_t y) {
+      return ((x & 0xfff) * 8 + ((x >> 12) & 7)) < ((y & 0xfff) * 8 + ((y >> 12) & 7)); });
+    plan.max_items = std::max<int>(plan.max_items, (int)items.size());
+    for (uint32_t it : items) {          // CSR block positions, resolved on the host once
+      const int32_t e = el[it & 0xfff];
+      const int32_t a = conn[(int64_t)e * nen + ((it >> 12) & 7)];
+      for (int b = 0; b < nen; ++b) {
+        uint16_t pos = 0;
+        if (browptr) {
+          const int32_t *lo_ = bcol->data() + (*browptr)[a], *hi_ = bcol->data() + (*browptr)[a + 1];
+          pos = (uint16_t)(std::lower_bound(lo_, hi_, conn[(int64_t)e * nen + b]) - lo_);
+        }
+        plan.ipos.push_back(pos);
+      }
+    }
+    for (int32_t e : el) plan.conn.insert(plan.conn.end(), conn + (int64_t)e * nen, conn + (int64_t)(e + 1) * nen);
+    plan.items.insert(plan.items.end(), items.begin(), items.end());
+    plan.iptr[c + 1] = (int32_t)plan.items.size();
+    plan.elems.insert(plan.elems.end(), el.begin(), el.end());
+    plan.eptr[c + 1] = (int32_t)plan.elems.size();
+  }
+}
+
+extern "C" int32_t nls_plan_stats(int32_t dim, int32_t nen, int64_t nelem, const int32_t *conn0, int64_t nnodes,
+                                  int64_t n_owned_nodes, const double *coords, int32_t nc, int64_t *out4) {
+  if (dim < 1 || dim > 3 || nen < 1 || nelem < 0 || nnodes < 1 || n_owned_nodes < 0 || n_owned_nodes > nnodes || !coords ||
+      !out4 || nc < 1 || (nelem > 0 && !conn0)) return NLS_ERR_ARG;
+  AsmPlan plan;
+  nls_host_cluster_plan(dim, nen, nelem, conn0, nnodes, n_owned_nodes, coords, nc, nullptr, nullptr, plan);
+  out4[0] = plan.ncl; out4[1] = plan.max_elems; out4[2] = (int64_t)plan.elems.size(); out4[3] = (int64_t)plan.items.size();
+  return NLS_OK;
+}

@@ -12,21 +12,7 @@
 // All arithmetic is FP64. Scatter is FP64 atomics (RED.E.ADD.F64) into R and the CSR
 // values; element -> CSR slot comes from a precomputed per-element position map.
 #include "nls_internal.h"
-
-struct AsmArgs {
-  int64_t nel, n_owned;
-  const int32_t *conn;
-  const double *coords;
-  const double *U;
-  double *R;
-  double *vals;
-  const int64_t *browptr;
-  const uint16_t *pos;
-  double *st[9];   // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
-  const double *u_n;
-};
-
-__device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
+#include "asm_common.cuh"
 
 // ------------------------------------------------------------------------------------
 // 1-D bar, order p = M-1 Lagrange on Chebyshev-2 nodes, nq Gauss points.
@@ -122,46 +108,15 @@ k_asm_1d(const AsmArgs A, const __grid_constant__ Tab1D T, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------
-// Small dense helpers
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ double inv2(const double *M, double *Mi) {
-  const double det = M[0] * M[3] - M[1] * M[2];
-  const double id = 1.0 / det;
-  Mi[0] = M[3] * id; Mi[1] = -M[1] * id; Mi[2] = -M[2] * id; Mi[3] = M[0] * id;
-  return det;
-}
-__device__ __forceinline__ double inv3(const double *M, double *Mi) {
-  const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
-  const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
-  const double id = 1.0 / det;
-  Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
-  Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
-  Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;
-  return det;
-}
-
-// ------------------------------------------------------------------------------------
 // 2-D plane-strain Q1 compressible Neo-Hookean. One thread per element.
 //   F = I + sum_a u_a (x) dN_a/dX,  P = mu (F - F^-T) + lam lnJ F^-T
 //   K_{ai,bk} = w detJ [ mu d_ik (G_a.G_b) + lam g_ai g_bk + (mu - lam lnJ) g_ak g_bi ],
 //   G_a = dN_a/dX,  g_a = F^-T G_a  (spatial form of the tangent of SURVEY.md 8c).
 // ------------------------------------------------------------------------------------
+// Element integrals of one quad: fe[8], Ke[8][8] (row-major DoF order a*2+i).
 template <bool DO_R, bool DO_K>
-__global__ void __launch_bounds__(128)
-k_asm_q1_2d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= A.nel) return;
-  const int4 c4 = reinterpret_cast<const int4 *>(A.conn)[e];
-  const int nd[4] = {c4.x, c4.y, c4.z, c4.w};
-  double X[4][2], u[4][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const double2 x = reinterpret_cast<const double2 *>(A.coords)[nd[a]];
-    const double2 v = reinterpret_cast<const double2 *>(A.U)[nd[a]];
-    X[a][0] = x.x; X[a][1] = x.y; u[a][0] = v.x; u[a][1] = v.y;
-  }
-  const double mu = mp.p[0], lam = mp.p[1];
-  double fe[8], Ke[8][8];
+__device__ __forceinline__ void q1_2d_element(const double (&X)[4][2], const double (&u)[4][2], const TabQ1 &T,
+                                              const double mu, const double lam, double (&fe)[8], double (&Ke)[8][8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     fe[i] = 0.0;
@@ -210,12 +165,13 @@ k_asm_q1_2d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_const
 #pragma unroll
         for (int i = 0; i < 2; ++i) g[a][i] = G[a][0] * Fi[i] + G[a][1] * Fi[2 + i];
       const double c1 = wd * mu, c2 = wd * lam, c3 = wd * (mu - lam * lnJ);
+      // K is symmetric: K[(b,k),(a,i)] = K[(a,i),(b,k)]; accumulate blocks b >= a only
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const double c2g[2] = {c2 * g[a][0], c2 * g[a][1]};
         const double c3g[2] = {c3 * g[a][0], c3 * g[a][1]};
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = a; b < 4; ++b) {
           const double dab = c1 * (G[a][0] * G[b][0] + G[a][1] * G[b][1]);
 #pragma unroll
           for (int i = 0; i < 2; ++i)
@@ -226,6 +182,31 @@ k_asm_q1_2d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_const
       }
     }
   }
+  if (DO_K) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < r; ++c)
+        if ((c >> 1) < (r >> 1)) Ke[r][c] = Ke[c][r];   // mirror the strictly-lower blocks
+  }
+}
+
+template <bool DO_R, bool DO_K>
+__global__ void __launch_bounds__(128)
+k_asm_q1_2d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= A.nel) return;
+  const int4 c4 = reinterpret_cast<const int4 *>(A.conn)[e];
+  const int nd[4] = {c4.x, c4.y, c4.z, c4.w};
+  double X[4][2], u[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double2 x = reinterpret_cast<const double2 *>(A.coords)[nd[a]];
+    const double2 v = reinterpret_cast<const double2 *>(A.U)[nd[a]];
+    X[a][0] = x.x; X[a][1] = x.y; u[a][0] = v.x; u[a][1] = v.y;
+  }
+  double fe[8], Ke[8][8];
+  q1_2d_element<DO_R, DO_K>(X, u, T, mp.p[0], mp.p[1], fe, Ke);
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     if (nd[a] >= A.n_owned) continue;
@@ -507,6 +488,7 @@ int nls_launch_assembly(nls_context *h, bool want_r, bool want_k) {
       default: NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D elements support p = 1..7");
     }
   }
+  if (nls_assembly_overwrites(h)) return nls_launch_gather_2d(h, want_r, want_k);
   if (h->dim == 2) {
     const unsigned g = nblk(h->nel, 128);
     if (want_r && want_k) k_asm_q1_2d<true, true><<<g, 128, 0, h->stream>>>(a, h->tabq, h->mat);

@@ -44,6 +44,8 @@ __global__ void k_negate_into(int64_t n, const double *x, double *y) {
 static void free_pattern(nls_context *h) {
   dev_free(&h->d_browptr); dev_free(&h->d_bcol); dev_free(&h->d_rowptr); dev_free(&h->d_colind);
   dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
+  dev_free(&h->d_cl_nodes); dev_free(&h->d_cl_eptr); dev_free(&h->d_cl_elems); dev_free(&h->d_cl_iptr); dev_free(&h->d_cl_items); dev_free(&h->d_cl_conn); dev_free(&h->d_cl_ipos);
+  h->have_plan = false;
   h->h_browptr.clear(); h->h_bcol.clear();
   h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
 }
@@ -133,6 +135,7 @@ extern "C" int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64
   free_pattern(h);
   h->dim = dim; h->nen = nen; h->nn = nnodes; h->nel = nelem; h->n_owned = nnodes;
   h->h_conn.assign(conn0, conn0 + nelem * nen);
+  h->h_coords.assign(coords, coords + nnodes * dim);
   NLS_TRY(dev_alloc(h, &h->d_conn, (size_t)(nelem * nen)));
   NLS_TRY(dev_alloc(h, &h->d_coords, (size_t)(nnodes * dim)));
   NLS_CUDA(h, cudaMemcpyAsync(h->d_conn, conn0, sizeof(int32_t) * nelem * nen, cudaMemcpyHostToDevice, h->stream));
@@ -339,6 +342,32 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
   NLS_CUDA(h, cudaMemsetAsync(h->d_diag, 0, sizeof(int32_t) * h->nrows, h->stream));
   NLS_TRY(nls_launch_expand_pattern(h));
   NLS_TRY(nls_launch_build_pos(h));
+  // plan of the gather (row-owner) assembly: 2-D only for now; falls back to the atomic scatter
+  // when a cluster would not fit in shared memory
+  if (h->dim == 2 && h->n_owned > 0 && h->nel > 0) {
+    int maxdeg = 0;
+    for (int64_t a = 0; a < h->n_owned; ++a) maxdeg = std::max<int>(maxdeg, (int)(h->h_browptr[a + 1] - h->h_browptr[a]));
+    AsmPlan plan;
+    nls_host_cluster_plan(h->dim, h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_coords.data(), nls_gather_nc(),
+                          &h->h_browptr, &h->h_bcol, plan);
+    if (nls_gather_smem(plan.max_elems, maxdeg) <= (size_t)110 * 1024 && plan.max_elems < 4096 && plan.max_adj < 256 &&
+        plan.max_items <= nls_gather_max_items()) {
+      h->plan_nc = plan.nc; h->plan_ncl = plan.ncl; h->plan_max_elems = plan.max_elems; h->plan_maxdeg = maxdeg; h->plan_max_adj = plan.max_adj;
+      NLS_TRY(dev_alloc(h, &h->d_cl_nodes, plan.nodes.size())); NLS_TRY(dev_alloc(h, &h->d_cl_eptr, plan.eptr.size()));
+      NLS_TRY(dev_alloc(h, &h->d_cl_elems, plan.elems.size())); NLS_TRY(dev_alloc(h, &h->d_cl_iptr, plan.iptr.size()));
+      NLS_TRY(dev_alloc(h, &h->d_cl_items, plan.items.size()));
+      NLS_TRY(dev_alloc(h, &h->d_cl_conn, plan.conn.size())); NLS_TRY(dev_alloc(h, &h->d_cl_ipos, plan.ipos.size()));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_conn, plan.conn.data(), sizeof(int32_t) * plan.conn.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_ipos, plan.ipos.data(), sizeof(uint16_t) * plan.ipos.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_nodes, plan.nodes.data(), sizeof(int32_t) * plan.nodes.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_eptr, plan.eptr.data(), sizeof(int32_t) * plan.eptr.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_elems, plan.elems.data(), sizeof(int32_t) * plan.elems.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_iptr, plan.iptr.data(), sizeof(int32_t) * plan.iptr.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_items, plan.items.data(), sizeof(uint32_t) * plan.items.size(), cudaMemcpyHostToDevice, h->stream));
+      NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+      h->have_plan = true;
+    }
+  }
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_pattern = true;
   return NLS_OK;
@@ -378,8 +407,10 @@ static int check_ready(nls_context *h, const char *who) {
 static int assemble(nls_context *h, bool want_r, bool want_k) {
   NLS_TRY(nls_launch_apply_dirichlet(h, h->d_U));              // residual.jl:13 / jacobian.jl:11
   NLS_TRY(nls_halo_exchange(h, h->d_U));
-  if (want_r) NLS_CUDA(h, cudaMemsetAsync(h->d_R, 0, sizeof(double) * h->nrows, h->stream));   // residual.jl:14
-  if (want_k) NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));  // jacobian.jl:13
+  if (!nls_assembly_overwrites(h)) {   // the gather kernel writes every row itself
+    if (want_r) NLS_CUDA(h, cudaMemsetAsync(h->d_R, 0, sizeof(double) * h->nrows, h->stream));   // residual.jl:14
+    if (want_k) NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));  // jacobian.jl:13
+  }
   NLS_TRY(nls_launch_assembly(h, want_r, want_k));
   if (want_r) NLS_TRY(nls_launch_neumann(h, h->d_R));          // residual.jl:24-25
   return NLS_OK;

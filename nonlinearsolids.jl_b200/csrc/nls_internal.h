@@ -40,6 +40,26 @@ int nls_host_tabq1(int dim, TabQ1 *t);
 void nls_host_block_pattern(int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
                             std::vector<int64_t> &browptr, std::vector<int32_t> &bcol);
 
+// cluster plan of the gather (row-owner) assembly, built on the host (host_tables.cpp)
+struct AsmPlan {
+  int nc = 0;                     // nodes per cluster
+  int64_t ncl = 0;                // clusters
+  int max_elems = 0;              // largest element count of a cluster
+  int max_adj = 0;                // largest number of elements around a node
+  int max_items = 0;              // largest number of (element, node) items of a cluster
+  std::vector<int32_t> conn;      // [elems.size()][nen] connectivity rows of the cluster elements
+  std::vector<uint16_t> ipos;     // [items.size()][nen] block positions of the element's nodes in the row of node a
+  std::vector<int32_t> nodes;     // [ncl*nc] owned node id or -1
+  std::vector<int32_t> eptr;      // [ncl+1] into elems
+  std::vector<int32_t> elems;     // element ids, ascending per cluster
+  std::vector<int32_t> iptr;      // [ncl+1] into items
+  std::vector<uint32_t> items;    // (element slot, local node a) pairs whose node is in the cluster:
+                                  // slot | a << 12 | node_local << 16 | rank << 24, sorted by (slot, a)
+};
+void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
+                           const double *coords, int nc, const std::vector<int64_t> *browptr,
+                           const std::vector<int32_t> *bcol, AsmPlan &plan);
+
 // ---- device control block of the PCG loop (lives in device memory) ----
 struct PcgCtl {
   double rz, rz_new, pAp, rr, bb;   // reductions (global, after allreduce if distributed)
@@ -102,6 +122,16 @@ struct nls_context {
   uint16_t *d_pos = nullptr;            // [nel][nen][nen] position of node b in block row of node a
   int32_t *d_diag = nullptr;            // [nrows] offset of the diagonal entry within its row
 
+  // gather-assembly plan (device copies)
+  bool have_plan = false;
+  int plan_nc = 0, plan_max_elems = 0, plan_maxdeg = 0, plan_max_adj = 0;
+  int64_t plan_ncl = 0;
+  int32_t *d_cl_nodes = nullptr, *d_cl_eptr = nullptr, *d_cl_elems = nullptr, *d_cl_iptr = nullptr;
+  uint32_t *d_cl_items = nullptr;
+  int32_t *d_cl_conn = nullptr;
+  uint16_t *d_cl_ipos = nullptr;
+  std::vector<double> h_coords;
+
   // vectors (ndof_local unless noted)
   double *d_U = nullptr, *d_R = nullptr, *d_dU = nullptr;
   double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr, *d_b = nullptr;
@@ -121,7 +151,7 @@ struct nls_context {
   size_t flush_bytes = 0;
 
   // options
-  int opt_assembly = 0;
+  int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: gather (row-owner) kernel where available
 
   // distributed
   bool distributed = false;
@@ -144,6 +174,11 @@ struct nls_context {
 
 // ---- kernel launchers (kernels_assembly.cu / kernels_krylov.cu) ----
 int nls_launch_assembly(nls_context *h, bool want_r, bool want_k);
+bool nls_assembly_overwrites(const nls_context *h);
+int nls_gather_nc(void);
+int nls_gather_max_items(void);
+size_t nls_gather_smem(int max_elems, int maxdeg);
+int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k);
 int nls_launch_apply_dirichlet(nls_context *h, double *U);
 int nls_launch_neumann(nls_context *h, double *R);
 int nls_launch_build_pos(nls_context *h);

@@ -195,8 +195,8 @@ def test_q1_newton(nls, orc, dim, n, compress):
 def test_krylov_hooks(nls, orc):
     """SpMV, dot, axpy and the PCG solve against the oracle on the same CSR values."""
     mat = nls.NeoHookean(E=1.0, nu=0.3)
-    fem, om = grid_problem(nls, orc, 8, 3, mat)
-    U = nls.smooth_field(fem.mesh.coords)
+    fem, om = grid_problem(nls, orc, 8, 3, mat, compress=-0.01)     # mild state: the tangent stays SPD
+    U = nls.smooth_field(fem.mesh.coords, amp=0.002)
     vals = om.jacobian_csr(U)
     H = fem.handle(mat)
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
@@ -259,3 +259,42 @@ def test_empty_and_duplicate_boundaries(nls, orc):
     Ud = U.copy(); nls.Residual(mat)(fem, Ud, R)
     Uo, Ro = om.residual(U)
     assert Ud[0] == 3.0 and np.array_equal(Ud, Uo) and rel_err(R, Ro) <= RTOL
+
+
+@pytest.mark.parametrize("n,kind", [(24, "affine"), (37, "distorted"), (66, "shuffled")])
+def test_gather_vs_atomic_assembly_2d(nls, orc, n, kind):
+    """The two 2-D assembly kernels (gather/row-owner = default, atomic scatter = option 0) agree with
+    each other and with the oracle, also on an unstructured numbering; the gather kernel is
+    bit-reproducible run to run."""
+    mat = nls.NeoHookean(E=1.0, nu=0.3)
+    mesh = nls.grid_mesh(n, 2)
+    if kind == "distorted":
+        mesh.coords[:] = distorted(mesh)
+    if kind == "shuffled":
+        rng = np.random.default_rng(5)
+        perm = rng.permutation(mesh.nn)
+        conn = perm[mesh.conn][rng.permutation(mesh.nel)].astype(np.int32)
+        coords = np.zeros_like(mesh.coords); coords[perm] = mesh.coords
+        mesh = nls.Mesh(2, conn, coords=coords)
+    fem = nls.FEMModel(mesh)
+    fem.addboundary(nls.Dirichlet([0, 1, 7], [0.0, 0.001, -0.002]))
+    fem.addboundary(nls.Neumann([5, 9], [0.25, -0.5]))
+    om = orc.OracleModel(2, mesh.conn, mesh.coords, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mat.mu, mat.lam))
+    om.set_dirichlet([0, 1, 7], [0.0, 0.001, -0.002]); om.set_neumann([5, 9], [0.25, -0.5])
+    U = nls.smooth_field(mesh.coords, amp=0.2 / (n - 1))    # well below the element size: no inversion at the BC nodes
+    H = fem.handle(mat)
+    out = {}
+    for opt in (1, 0, 1):
+        H.call("nls_set_option", b"assembly", opt)
+        R, K = np.full(fem.ndof, np.nan), nls.CSRMatrix(fem)
+        K.vals[:] = np.nan
+        nls.residual_jacobian(mat, fem, U.copy(), R, K)
+        if opt == 1 and 1 in out:
+            assert np.array_equal(out[1][0], R) and np.array_equal(out[1][1], K.vals)   # deterministic
+        out[opt] = (R, K.vals.copy())
+        R1, K1 = np.zeros(fem.ndof), nls.CSRMatrix(fem)
+        nls.Residual(mat)(fem, U.copy(), R1); nls.Jacobian(mat)(fem, U.copy(), K1)
+        assert rel_err(R1, R) <= 1e-13 and rel_err(K1.vals, K.vals) <= 1e-13
+    _, Ro = om.residual(U); Ko = om.jacobian_csr(U)
+    for opt in (0, 1):
+        assert rel_err(out[opt][0], Ro) <= RTOL and rel_err(out[opt][1], Ko) <= RTOL, opt
