@@ -1,0 +1,213 @@
+# NonlinearSolidsB200.jl -- thin `ccall` shim that plugs libnls_b200.so (include/nls_b200.h) into
+# NonlinearSolids.jl's own dispatch points, so an existing script keeps its meshes, materials,
+# boundaries, timesteppers and postprocessing and only swaps the solver type:
+#
+#     solver = B200NewtonSolver(fem; rtol=1e-10, atol=1e-14, maxits=25)     # was NewtonSolver(fem; ...)
+#     set_residual_fn!(solver, Residual(mat)); set_jacobian_fn!(solver, Jacobian(mat))
+#     ts = PseudoTimeStepper(solver; Δt=0.1, maxtime=1.0); solve!(ts)
+#
+# NOTE: Julia is not installed in the build image, so this file is written against the C header
+# but has never been executed; the identical ABI is exercised from Python (ctypes) by tests/.
+# Reference seams it binds (paths in the NonlinearSolids.jl tree):
+#   AbstractNonlinearSolver verbs used by timesteppers   src/nonlinearsolvers/newton_fem.jl:74-125
+#   solve!(::NewtonSolver, U0)                           src/nonlinearsolvers/newton_fem.jl:132-190
+#   compute_internalforce / compute_dinternalforce       src/materials/defaults.jl:29-46, 68-82
+#   updateboundaries! / TimeDependent update!            src/fem/fem.jl:68-72, src/fem/boundary.jl:86-92
+#   save_state! on poststep!                             src/timesteppers/types.jl:74-78
+module NonlinearSolidsB200
+
+using NonlinearSolids
+import NonlinearSolids: solve!, solution, residual, iterations, model, numdof, is_converged,
+    set_residual_fn!, set_jacobian_fn!, set_ctx!, compute_internalforce, compute_dinternalforce, save_state!
+
+export B200NewtonSolver, B200Model, NeoHookean
+
+const libnls = get(ENV, "NLS_B200_LIB", "libnls_b200.so")
+
+struct NLSError <: Exception
+    status::Int32
+    msg::String
+end
+
+function check(h::Ptr{Cvoid}, rc::Int32)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:nls_last_error, libnls), Cstring, (Ptr{Cvoid},), h))
+    rc == 1 ? throw(ArgumentError(msg)) : throw(NLSError(rc, msg))   # NLS_ERR_ARG -> ArgumentError
+end
+
+"""Compressible Neo-Hookean (builder-defined T2 material; params mu, lambda)."""
+Base.@kwdef struct NeoHookean <: NonlinearSolids.AbstractMaterial
+    μ::Float64
+    λ::Float64
+    ρ::Float64 = 1.0
+end
+
+matkind(::LinearElasticity1D) = Int32(0)
+matkind(::ExponentialMaterial) = Int32(1)
+matkind(::LinearElastoPlasticity1D) = Int32(2)
+matkind(::NeoHookean) = Int32(3)
+matparams(m::LinearElasticity1D) = [m.E]
+matparams(m::ExponentialMaterial) = [m.σ_sat, m.b]
+matparams(m::LinearElastoPlasticity1D) = [m.E, m.Hκ, m.Hα, m.κ₀, m.α₀, m.Eep]
+matparams(m::NeoHookean) = [m.μ, m.λ]
+
+"""Device-resident mirror of a FEMModel (one GPU). Indices are converted 1-based -> 0-based once."""
+mutable struct B200Model
+    fem::FEMModel
+    h::Ptr{Cvoid}
+    dim::Int
+    material::Any
+    function B200Model(fem::FEMModel; device::Integer=0, dim::Integer=NonlinearSolids.dim(fem))
+        href = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:nls_create, libnls), Int32, (Int32, Ref{Ptr{Cvoid}}), device, href)
+        rc == 0 || throw(NLSError(rc, unsafe_string(ccall((:nls_last_error, libnls), Cstring, (Ptr{Cvoid},), C_NULL))))
+        m = new(fem, href[], dim, nothing)
+        finalizer(x -> ccall((:nls_destroy, libnls), Int32, (Ptr{Cvoid},), x.h), m)
+        els = elements(fem.mesh)
+        nen = length(nodes(els[1]))
+        conn = Matrix{Int32}(undef, nen, length(els))                 # column-major = [nel][nen] row-major in C
+        for (e, el) in enumerate(els)
+            conn[:, e] .= Int32.(nodes(el) .- 1)
+        end
+        xy = Float64.(permutedims(reshape(collect(coords(fem.mesh)), :, dim)))   # [nn][dim] row-major
+        check(m.h, ccall((:nls_set_mesh, libnls), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Int32, Ptr{Int32}, Ptr{Float64}),
+                         m.h, dim, length(nodes(fem.mesh)), length(els), nen, conn, xy))
+        check(m.h, ccall((:nls_set_discretization, libnls), Int32, (Ptr{Cvoid}, Int32, Int32),
+                         m.h, order(fem.P), order(fem.Q)))
+        check(m.h, ccall((:nls_build_pattern, libnls), Int32, (Ptr{Cvoid},), m.h))
+        m
+    end
+end
+
+function sync_material!(m::B200Model, mat)
+    m.material === mat && return
+    p = matparams(mat)
+    check(m.h, ccall((:nls_set_material, libnls), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32), m.h, matkind(mat), p, length(p)))
+    check(m.h, ccall((:nls_set_area, libnls), Int32, (Ptr{Cvoid}, Float64), m.h, Float64(get(m.fem.data, :A, 3e-4))))
+    m.material = mat
+end
+
+"""Push the current boundary lists/values (after updateboundaries!) to the device."""
+function sync_boundaries!(m::B200Model)
+    dn, dv, nn, nv = Int64[], Float64[], Int64[], Float64[]
+    for bc in m.fem.boundaries
+        if isdirichlet(bc)
+            append!(dn, nodes(bc) .- 1); append!(dv, values(bc))
+        else
+            append!(nn, nodes(bc) .- 1); append!(nv, values(bc))
+        end
+    end
+    check(m.h, ccall((:nls_set_dirichlet, libnls), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}), m.h, length(dn), dn, dv))
+    check(m.h, ccall((:nls_set_neumann, libnls), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}), m.h, length(nn), nn, nv))
+end
+
+# ---- dispatch point (2): material-level global loops on a device model -------------------------
+"""compute_internalforce(material, ::B200Model, U, Fint, ctx; mode): F_int via the element kernel.
+`mode=:add` adds to Fint like the reference (defaults.jl:29-46)."""
+function compute_internalforce(material, m::B200Model, U::Vector{Float64}, Fint::Vector{Float64}, ctx; mode=:add)
+    mode in (:add, :set) || throw(ArgumentError("Invalid mode: $mode"))
+    sync_material!(m, material)
+    tmp = similar(Fint)
+    check(m.h, ccall((:nls_residual, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, U, tmp))
+    mode == :set ? (Fint .= tmp) : (Fint .+= tmp)
+end
+
+"""compute_dinternalforce(material, ::B200Model, U, vals, ctx; mode): CSR values of dF_int/dU."""
+function compute_dinternalforce(material, m::B200Model, U::Vector{Float64}, vals::Vector{Float64}, ctx; mode=:add)
+    mode in (:add, :set) || throw(ArgumentError("Invalid mode: $mode"))
+    sync_material!(m, material)
+    tmp = similar(vals)
+    check(m.h, ccall((:nls_jacobian, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, U, tmp))
+    mode == :set ? (vals .= tmp) : (vals .+= tmp)
+end
+
+# ---- dispatch point (3): the solver verbs the timesteppers consume ------------------------------
+struct NewtonOpts
+    type_modified::Int32; atol::Float64; rtol::Float64; dtol::Float64; maxits::Int32; lin_rtol::Float64; lin_maxits::Int32
+end
+mutable struct NewtonResult
+    reason::Int32; iterations::Int32; lin_its_total::Int32; nhist::Int32
+    norm_r::Float64; norm_r0::Float64; ms_assembly::Float64; ms_linear::Float64; ms_total::Float64
+    NewtonResult() = new(0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0)
+end
+
+const REASONS = (REASON_NOT_YET_CONVERGED, REASON_CONVERGED_RELATIVE, REASON_CONVERGED_ABSOLUTE,
+                 REASON_DIVERGED_MAXITS, REASON_DIVERGED_STEP, REASON_DIVERGED_LINEAR_SOLVE)
+
+"""Sibling of NewtonSolver (its `K::Matrix{Float64}` field is dense, newton_fem.jl:41, so it cannot be reused at
+scale). Same keyword fields plus the Krylov controls that replace `\\`."""
+Base.@kwdef mutable struct B200NewtonSolver <: AbstractNonlinearSolver
+    type::Symbol = :standard
+    atol::Float64 = 1e-16
+    rtol::Float64 = 1e-16
+    dtol::Float64 = 1e6
+    maxits::Int = 100
+    lin_rtol::Float64 = 1e-12
+    lin_maxits::Int = 100_000
+    ctx::Any = nothing
+    fem::FEMModel
+    dev::B200Model
+    residual_fn!::Function = (a...) -> nothing
+    jacobian_fn!::Function = (a...) -> nothing
+    monitor_residual_norm::Bool = false
+    monitor_converged_reason::Bool = false
+    allow_maxits::Bool = false
+    U::Vector{Float64}
+    δU::Vector{Float64}
+    R::Vector{Float64}
+    norm_history::Vector{Float64} = Float64[]
+    converged_reason::NonlinearSolids.AbstractConvergedReason = REASON_NOT_YET_CONVERGED
+    iterations::Int = 0
+    lin_iterations::Int = 0
+end
+
+function B200NewtonSolver(fem::FEMModel; device=0, kwargs...)
+    n = numdof(fem)
+    B200NewtonSolver(; fem=fem, dev=B200Model(fem; device=device), U=zeros(n), δU=zeros(n), R=zeros(n), kwargs...)
+end
+
+solution(s::B200NewtonSolver) = s.U
+residual(s::B200NewtonSolver) = s.R
+iterations(s::B200NewtonSolver) = s.iterations
+model(s::B200NewtonSolver) = s.fem
+numdof(s::B200NewtonSolver) = numdof(s.fem)
+set_ctx!(s::B200NewtonSolver, ctx) = s.ctx = ctx
+set_residual_fn!(s::B200NewtonSolver, f::Function) = s.residual_fn! = f
+set_jacobian_fn!(s::B200NewtonSolver, f::Function) = s.jacobian_fn! = f
+is_converged(s::B200NewtonSolver; allow_maxits=s.allow_maxits) = is_converged(s.converged_reason, allow_maxits=allow_maxits)
+
+"""solve!(solver, U0): the whole loop of newton_fem.jl:132-190 runs on the GPU (nls_newton_solve)."""
+function solve!(s::B200NewtonSolver, U0::AbstractVector=zeros(numdof(s.fem)))
+    s.residual_fn! isa Residual && s.jacobian_fn! isa Jacobian ||
+        error("B200NewtonSolver needs the gallery Residual/Jacobian functors (their material selects the device law)")
+    isempty(s.residual_fn!.externalforces) || error("external force functors are not on the device path yet")
+    sync_material!(s.dev, s.residual_fn!.material)
+    sync_boundaries!(s.dev)                     # TimeDependent values were updated by step!(ts, Δt)
+    opts = NewtonOpts(s.type == :modified, s.atol, s.rtol, s.dtol, s.maxits, s.lin_rtol, s.lin_maxits)
+    res = NewtonResult()
+    hist = zeros(s.maxits + 2)
+    u0 = Vector{Float64}(U0)
+    check(s.dev.h, ccall((:nls_newton_solve, libnls), Int32,
+        (Ptr{Cvoid}, Ref{NewtonOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{NewtonResult}),
+        s.dev.h, opts, u0, s.U, s.R, hist, res))
+    s.converged_reason = REASONS[res.reason + 1]
+    s.iterations = res.iterations
+    s.lin_iterations = res.lin_its_total
+    s.norm_history = hist[1:res.nhist]
+    return
+end
+
+# stateful materials: commit the trial state of a converged step. poststep! (types.jl:74-78) calls
+# save_state!(material(ts), model(ts), u, ts) with the host FEMModel; this method is more specific in
+# its last argument than the reference's (ctx::Any), so it is picked for timestepper-driven runs and
+# forwards to the device when the timestepper's solver is a B200NewtonSolver.
+function save_state!(mat::LinearElastoPlasticity1D, fem::FEMModel, U, ts::AbstractTimeStepper)
+    s = NonlinearSolids.solver(ts)
+    if s isa B200NewtonSolver
+        check(s.dev.h, ccall((:nls_commit_state, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}), s.dev.h, Vector{Float64}(U)))
+    else
+        invoke(save_state!, Tuple{LinearElastoPlasticity1D,FEMModel,Any,Any}, mat, fem, U, ts)
+    end
+end
+
+end # module
