@@ -171,7 +171,8 @@ int32_t nls_timer_start(nls_handle h);       /* CUDA event on the library's stre
 int32_t nls_timer_stop(nls_handle h, float *ms);
 int32_t nls_flush_l2(nls_handle h);          /* overwrite a >L2-sized scratch buffer */
 int64_t nls_kernel_launches(nls_handle h);   /* kernels launched by this handle so far */
-/* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomics, 1 row-owner (where available) */
+/* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 gather/row-owner (2-D);
+ * "spmv" -> 0 scalar CSR, 1 block-aware; "spmv_lanes" -> lanes per node (0 = default) */
 int32_t nls_set_option(nls_handle h, const char *key, int32_t value);
 
 /* ---- multi-GPU: one process per GPU, element-partitioned slabs ---------------- */

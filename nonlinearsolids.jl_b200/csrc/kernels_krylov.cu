@@ -120,6 +120,72 @@ k_spmv(int64_t nrows, const int64_t *__restrict__ rowptr, const int32_t *__restr
   if (DOT) grid_reduce<1>(dot, rs.partial, rs.counter, &ctl->red[0]);
 }
 
+// ------------------------------------------------------------------------------------
+// Block-aware SpMV on the same CSR values: the scalar pattern is the dim x dim expansion of the
+// node-level pattern (browptr/bcol), so the dim rows of a node share one column list. T lanes
+// per node walk its blocks: one int32 block column per dim*dim values instead of dim*dim int32
+// scalar columns (index traffic 4/dim^2 B per nonzero instead of 4 B), x gathered as a dim-vector.
+// ------------------------------------------------------------------------------------
+template <int DIM, int T, bool DOT>
+__global__ void __launch_bounds__(256)
+k_bspmv(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
+        const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+        const uint8_t *__restrict__ con, PcgCtl *ctl, RedScratch rs) {
+  if (DOT) {
+    if (ctl->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->rz = ctl->red[1];
+  }
+  const int lane = threadIdx.x % T;
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x / T;
+  double dot[1] = {0.0};
+  for (int64_t base = 0; base < n_owned; base += stride) {
+    const int64_t node = base + gid;
+    const bool valid = node < n_owned;
+    double acc[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) acc[i] = 0.0;
+    if (valid) {
+      const int64_t b0 = browptr[node];
+      const int deg = (int)(browptr[node + 1] - b0);
+      const double *v0 = vals + (int64_t)DIM * DIM * b0;
+      for (int j = lane; j < deg; j += T) {
+        const int c = bcol[b0 + j];
+        if (DIM == 2) {
+          const double2 xv = reinterpret_cast<const double2 *>(x)[c];
+          const double2 a0 = *reinterpret_cast<const double2 *>(v0 + 2 * j);
+          const double2 a1 = *reinterpret_cast<const double2 *>(v0 + 2 * deg + 2 * j);
+          acc[0] = fma(a0.x, xv.x, fma(a0.y, xv.y, acc[0]));
+          acc[1] = fma(a1.x, xv.x, fma(a1.y, xv.y, acc[1]));
+        } else {
+          double xv[DIM];
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) xv[k] = x[(int64_t)DIM * c + k];
+#pragma unroll
+          for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) acc[i] = fma(v0[(int64_t)i * DIM * deg + DIM * j + k], xv[k], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (valid && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) {
+        const int64_t row = DIM * node + i;
+        double sv = acc[i];
+        if (con && con[row]) sv = 0.0;
+        y[row] = sv;
+        if (DOT) dot[0] += x[row] * sv;
+      }
+    }
+  }
+  if (DOT) grid_reduce<1>(dot, rs.partial, rs.counter, &ctl->red[0]);
+}
+
 // diagonal -> Jacobi preconditioner; constrained rows get 0 (their residual is 0 anyway)
 __global__ void k_extract_dinv(int64_t nrows, const int64_t *rowptr, const int32_t *diag, const double *vals,
                                const uint8_t *con, double *dinv) {
@@ -254,9 +320,33 @@ static int spmv_t(nls_context *h, const double *x, double *y, const uint8_t *con
   return NLS_OK;
 }
 
+template <int DIM, int T>
+static int bspmv_t(nls_context *h, const double *x, double *y, const uint8_t *con, bool dot) {
+  int64_t g = (h->n_owned * T + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g > RED_BLOCKS_MAX) g = RED_BLOCKS_MAX;
+  if (g < 1) g = 1;
+  if (dot) k_bspmv<DIM, T, true><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, h->d_vals, x, y, con, h->d_ctl, red_of(h));
+  else     k_bspmv<DIM, T, false><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, h->d_vals, x, y, con, h->d_ctl, red_of(h));
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
 int nls_launch_spmv(nls_context *h, const double *x, double *y, bool masked, bool with_dot) {
   if (h->nrows == 0) return NLS_OK;
   const uint8_t *con = masked ? h->d_con : nullptr;
+  if (h->opt_spmv == 1 && h->dim >= 2) {   // block-aware traversal of the same CSR values
+    const int t = h->opt_spmv_lanes;
+    if (h->dim == 2) {
+      if (t == 2) return bspmv_t<2, 2>(h, x, y, con, with_dot);
+      if (t == 8) return bspmv_t<2, 8>(h, x, y, con, with_dot);
+      return bspmv_t<2, 4>(h, x, y, con, with_dot);
+    }
+    if (t == 8) return bspmv_t<3, 8>(h, x, y, con, with_dot);
+    if (t == 16) return bspmv_t<3, 16>(h, x, y, con, with_dot);
+    return bspmv_t<3, 4>(h, x, y, con, with_dot);   // measured best at C3 (profiles/r1d_spmv_variants.txt)
+  }
   const double avg = (double)h->nnz / (double)h->nrows;
   if (avg <= 3.0) return spmv_t<1>(h, x, y, con, with_dot);
   if (avg <= 6.0) return spmv_t<2>(h, x, y, con, with_dot);

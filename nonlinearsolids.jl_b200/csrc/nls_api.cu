@@ -679,6 +679,8 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   NLS_ENTER(h);
   if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
+  if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
+  if (!std::strcmp(key, "spmv_lanes")) { h->opt_spmv_lanes = value; return NLS_OK; }
   NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: unknown key");
 }
 

@@ -151,6 +151,8 @@ struct nls_context {
   size_t flush_bytes = 0;
 
   // options
+  int opt_spmv = 1;        // 0: scalar CSR SpMV; 1: block-aware traversal (dim >= 2)
+  int opt_spmv_lanes = 0;  // lanes per node for the block-aware SpMV (0 = default)
   int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: gather (row-owner) kernel where available
 
   // distributed
