@@ -160,6 +160,8 @@ def run_ours(args):
     L = nls.lib()
     if args.assembly is not None:
         H.call("nls_set_option", b"assembly", args.assembly)
+    if args.gather_ctas:
+        H.call("nls_set_option", b"gather_ctas", args.gather_ctas)
     nrows, nnz = C.c_int64(0), C.c_int64(0)
     H.call("nls_pattern_size", C.byref(nrows), C.byref(nnz))
     nrows, nnz = nrows.value, nnz.value
@@ -334,6 +336,7 @@ if __name__ == "__main__":
     ap.add_argument("--lin-rtol", dest="lin_rtol", type=float, default=1e-8)
     ap.add_argument("--skip-newton", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--gather-ctas", dest="gather_ctas", type=int, default=0)
     ap.add_argument("--assembly", type=int, default=None, help="0 atomic scatter, 1 gather/row-owner (default)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-rows", dest="cpu_rows", type=int, default=N_SIDE)

@@ -96,7 +96,7 @@ int32_t nls_pattern_host(int32_t dim, int32_t nen, int64_t nelem, const int32_t 
                          int64_t n_owned_nodes, int64_t *rowptr, int32_t *colind, int64_t *nnz);
 
 /* Statistics of the cluster plan the gather (row-owner) assembly would use for this mesh:
- * out4 = {clusters, max elements per cluster, sum of elements over clusters, (node,element) pairs}.
+ * out4 = {clusters, max elements per cluster, sum of elements over clusters, max elements around a node}.
  * sum/nelem is the redundancy factor of the element computation. */
 int32_t nls_plan_stats(int32_t dim, int32_t nen, int64_t nelem, const int32_t *conn0, int64_t nnodes,
                        int64_t n_owned_nodes, const double *coords, int32_t nc, int64_t *out4);

@@ -283,11 +283,10 @@ static inline uint64_t spread_bits(uint64_t v, int dim) {
 }
 
 void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
-                           const double *coords, int nc, const std::vector<int64_t> *browptr,
-                           const std::vector<int32_t> *bcol, AsmPlan &plan) {
+                           const double *coords, int nc, AsmPlan &plan) {
   plan = AsmPlan();
   plan.nc = nc;
-  if (n_owned == 0) { plan.eptr.assign(1, 0); plan.iptr.assign(1, 0); return; }
+  if (n_owned == 0) { plan.eptr.assign(1, 0); return; }
   // Morton keys of the owned nodes. Coordinates are binned on a grid with about one node per
   // bin (bins per axis = nodes^(1/dim) scaled by the aspect ratio), so on a structured mesh the
   // bin index is the grid index and a Morton tile (key >> tile_bits) is an 8x8 (4x4x4) node tile.
@@ -333,51 +332,19 @@ void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, i
   plan.ncl = ncl;
   plan.nodes.assign((size_t)(ncl * nc), -1);
   plan.eptr.assign((size_t)ncl + 1, 0);
-  plan.iptr.assign((size_t)ncl + 1, 0);
   std::vector<int32_t> el;
-  std::vector<uint32_t> items;
   for (int64_t c = 0; c < ncl; ++c) {
-    el.clear(); items.clear();
+    el.clear();
     const int64_t n0 = cstart[c], n1 = cstart[c + 1];
     for (int64_t s = n0; s < n1; ++s) {
       const int32_t a = keyed[s].second;
       plan.nodes[c * nc + (s - n0)] = a;
+      plan.max_adj = std::max<int>(plan.max_adj, (int)(nptr[a + 1] - nptr[a]));
       el.insert(el.end(), nidx.begin() + nptr[a], nidx.begin() + nptr[a + 1]);
     }
     std::sort(el.begin(), el.end());
     el.erase(std::unique(el.begin(), el.end()), el.end());
     plan.max_elems = std::max<int>(plan.max_elems, (int)el.size());
-    for (int t = 0; t < (int)(n1 - n0); ++t) {
-      const int32_t a = plan.nodes[c * nc + t];
-      plan.max_adj = std::max<int>(plan.max_adj, (int)(nptr[a + 1] - nptr[a]));
-      for (int64_t k = nptr[a]; k < nptr[a + 1]; ++k) {   // ascending element id = rank order
-        const int32_t e = nidx[k];
-        const uint32_t slot = (uint32_t)(std::lower_bound(el.begin(), el.end(), e) - el.begin());
-        uint32_t al = 0;
-        while (conn[(int64_t)e * nen + al] != a) ++al;
-        const uint32_t rank = (uint32_t)(k - nptr[a]);
-        items.push_back(slot | (al << 12) | ((uint32_t)t << 16) | (rank << 24));
-      }
-    }
-    // lanes of one element adjacent (broadcast reads), elements ascending
-    std::sort(items.begin(), items.end(), [](uint32_t x, uint32_t y) {
-      return ((x & 0xfff) * 8 + ((x >> 12) & 7)) < ((y & 0xfff) * 8 + ((y >> 12) & 7)); });
-    plan.max_items = std::max<int>(plan.max_items, (int)items.size());
-    for (uint32_t it : items) {          // CSR block positions, resolved on the host once
-      const int32_t e = el[it & 0xfff];
-      const int32_t a = conn[(int64_t)e * nen + ((it >> 12) & 7)];
-      for (int b = 0; b < nen; ++b) {
-        uint16_t pos = 0;
-        if (browptr) {
-          const int32_t *lo_ = bcol->data() + (*browptr)[a], *hi_ = bcol->data() + (*browptr)[a + 1];
-          pos = (uint16_t)(std::lower_bound(lo_, hi_, conn[(int64_t)e * nen + b]) - lo_);
-        }
-        plan.ipos.push_back(pos);
-      }
-    }
-    for (int32_t e : el) plan.conn.insert(plan.conn.end(), conn + (int64_t)e * nen, conn + (int64_t)(e + 1) * nen);
-    plan.items.insert(plan.items.end(), items.begin(), items.end());
-    plan.iptr[c + 1] = (int32_t)plan.items.size();
     plan.elems.insert(plan.elems.end(), el.begin(), el.end());
     plan.eptr[c + 1] = (int32_t)plan.elems.size();
   }
@@ -388,7 +355,7 @@ extern "C" int32_t nls_plan_stats(int32_t dim, int32_t nen, int64_t nelem, const
   if (dim < 1 || dim > 3 || nen < 1 || nelem < 0 || nnodes < 1 || n_owned_nodes < 0 || n_owned_nodes > nnodes || !coords ||
       !out4 || nc < 1 || (nelem > 0 && !conn0)) return NLS_ERR_ARG;
   AsmPlan plan;
-  nls_host_cluster_plan(dim, nen, nelem, conn0, nnodes, n_owned_nodes, coords, nc, nullptr, nullptr, plan);
-  out4[0] = plan.ncl; out4[1] = plan.max_elems; out4[2] = (int64_t)plan.elems.size(); out4[3] = (int64_t)plan.items.size();
+  nls_host_cluster_plan(dim, nen, nelem, conn0, nnodes, n_owned_nodes, coords, nc, plan);
+  out4[0] = plan.ncl; out4[1] = plan.max_elems; out4[2] = (int64_t)plan.elems.size(); out4[3] = plan.max_adj;
   return NLS_OK;
 }

@@ -1,82 +1,74 @@
-// kernels_gather.cu -- gather ("row-owner") assembly of the 2-D Q1 Neo-Hookean residual and
-// CSR Jacobian: no atomics, no zero-fill, every CSR row and R entry written exactly once, and
-// contributions summed in ascending element order -- the order of the reference's serial element
-// loop (compute_dinternalforce, src/materials/defaults.jl:77-81 + assemble!, src/fem/element.jl:70),
+// kernels_gather.cu -- gather ("row-owner") assembly of the 2-D Q1 Neo-Hookean residual and CSR
+// Jacobian: no atomics, no zero-fill, every CSR row and R entry written exactly once, contributions
+// summed in ascending element order -- the order of the reference's serial element loop
+// (compute_dinternalforce, src/materials/defaults.jl:77-81 + assemble!, src/fem/element.jl:70) --
 // so results are bit-reproducible run to run.
 //
-// One CTA per node cluster (host plan: nls_host_cluster_plan, 8x8-node tiles on structured grids,
-// Morton tiles of rank-binned coordinates in general).
-//   phase 1a  one thread per (element touching the cluster, quadrature point): J, dN/dX, F, F^-1,
-//             lnJ, P and the spatial gradients g = F^-T dN/dX -> shared memory (24 doubles per qp)
-//   phase 1b  one thread per (element, local node a) whose node belongs to the cluster: the row
-//             block a of K_e (2 x 8) and f_a, accumulated over the 4 qps from shared memory.
-//             Lanes of one element are adjacent, so the G_b/g_b reads are warp broadcasts.
-//   phase 2   conflict-free accumulation into per-node row buffers in shared memory, in rounds:
-//             round j adds, for every node, the contribution of its j-th adjacent element.
-//   phase 3   rows copied to the CSR values / R.
-// Why: ncu on the atomic-scatter kernel (profiles/r1a_ncu_asm2d_atomic.txt) shows 252 registers,
-// 11% warps active, FP64 pipe 20%, 34 M RED sectors and 295 MB of DRAM traffic for 176 MB of
-// algorithmic bytes; see DESIGN.md section 5.
+// Persistent CTAs walk node clusters (host plan: 8x8-node Morton tiles, nls_host_cluster_plan).
+// Everything a cluster needs is staged into shared memory with cp.async (LDGSTS) while the
+// previous cluster is being computed, so no global-load latency sits on the critical path:
+//   group A(k+2): the list of nodes touched by cluster k+2           (contiguous copy)
+//   group B(k+1): coordinates + displacements of those nodes (16-byte gathers through the list),
+//                 local connectivity, row owners, CSR row bases, gather source lists
+//   compute(k)  : phase 1  one thread per element: K_e (symmetric half accumulated, 8x8 stored)
+//                          and f_e over the 4 quadrature points -> shared memory
+//                 phase 2  one thread per (owned node, component): walks the node's source list
+//                          (element slot, local row, local column block -> CSR column block,
+//                          sorted by column block then element) and writes the row once.
+// History and counters behind this design: DESIGN.md section 5, profiles/r1a..r1e.
 #include <algorithm>
+#include <cstring>
 #include "asm_common.cuh"
 
-#define G2_NC 64         // nodes per cluster
-#define G2_THREADS 256   // >= items per cluster (4 per node on quad meshes)
-#define G2_QS 24         // doubles per (element, qp) record: {G_a[2], g_a[2]} x 4 nodes, c1, c2, c3, wd*P[4], pad
-#define G2_ES (4 * G2_QS + 2)   // doubles per element: 49 x 16 B (odd) -> lanes reading different elements hit different banks
+#define G2_NC 64          // owned nodes per cluster
+#define G2_THREADS 128    // warps 0..2: element integrals (phase 1); warp 3: row gather (phase 2), one cluster behind
+#define G2_EW 96          // element threads
+#define G2_KS 50          // doubles per element in shared memory: 10 symmetric 2x2 blocks, fe[8], pad 2 -> 25 x 16 B (odd)
 
-struct PlanArgs {
-  const int32_t *nodes, *eptr, *iptr;
-  const int4 *conn;        // connectivity of the cluster's elements, contiguous per cluster
-  const uint32_t *items;   // slot | a << 12 | node_local << 16 | rank << 24, sorted by (slot, a)
-  const uint2 *ipos;       // per item: CSR block positions of the element's 4 nodes in the row of node a (4 x uint16)
-  int max_elems, rs, rp, max_adj;
+struct GatherArgs {
+  int64_t ncl;
+  int maxt, maxe, ns;     // padded strides: touched nodes, elements, sources per node
+  const int32_t *tn;      // [ncl][4 + maxt]: {nt, ne, 0, 0}, node ids
+  const uint32_t *lconn;  // [ncl][maxe]: 4 local node indices (bytes) into the touched-node list
+  const int32_t *cn;      // [ncl][G2_NC] owned node ids (-1 = none)
+  const int64_t *b0;      // [ncl][G2_NC] block-row start of the node
+  const int32_t *deg;     // [ncl][G2_NC] block-row length
+  const uint32_t *nsrc;   // [ncl][G2_NC][ns]: Ks offset (14 bits) | lower << 14 | diag << 15 | jb << 16, ~0 = end
 };
 
-template <bool DO_R, bool DO_K>
-__global__ void __launch_bounds__(G2_THREADS, 3)
-k_asm_q1_2d_gather(const AsmArgs A, const PlanArgs P, const __grid_constant__ TabQ1 T,
-                   const __grid_constant__ MatParams mp) {
-  extern __shared__ __align__(16) double smem[];
-  double *Q = smem;                                         // [max_elems] x G2_ES: phase 1a -> 1b
-  double *racc = smem;                                      // [G2_NC][rp] row buffers, ALIASES Q (phase 2 -> 3)
-  double *rres = smem + max((size_t)P.max_elems * G2_ES, (size_t)G2_NC * P.rp);   // [2*G2_NC]
-  double *Tsm = rres + 2 * G2_NC;                           // [4][4][2] dN + [4] w
-  const int tid = threadIdx.x;
-  const int c = blockIdx.x;
-  const int e0 = P.eptr[c], ne = P.eptr[c + 1] - e0;
-  const int it0 = P.iptr[c], nit = P.iptr[c + 1] - it0;
-  // issue every plan load up front so their latency overlaps phase 1a
-  const bool have = tid < nit;
-  unsigned it = 0;
-  uint2 pp = make_uint2(0, 0);
-  if (have) { it = P.items[it0 + tid]; if (DO_K) pp = P.ipos[it0 + tid]; }
-  int my_node = -1, my_deg = 0;
-  int64_t my_b0 = 0;
-  if (tid < 2 * G2_NC) {
-    my_node = P.nodes[c * G2_NC + (tid >> 1)];
-    if (my_node >= 0 && DO_K) { my_b0 = A.browptr[my_node]; my_deg = (int)(A.browptr[my_node + 1] - my_b0); }
-  }
-  if (tid < 32) Tsm[tid] = T.dN[tid >> 3][(tid >> 1) & 3][tid & 1];
-  else if (tid < 36) Tsm[tid] = T.w[tid - 32];
-  if (tid < 2 * G2_NC) rres[tid] = 0.0;
-  __syncthreads();
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-  const double mu = mp.p[0], lam = mp.p[1];
-  // ---- phase 1a: geometry + kinematics of one quadrature point per thread ----
-  for (int w = tid; w < ne * 4; w += G2_THREADS) {
-    const int s = w >> 2, q = w & 3;
-    const int4 c4 = P.conn[e0 + s];
-    const int nd[4] = {c4.x, c4.y, c4.z, c4.w};
-    double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2], u[4][2];
+// Element integrals with the tangent's symmetry: blocks b >= a accumulated, mirrored on store.
+template <bool DO_R, bool DO_K>
+__device__ __forceinline__ void q1_2d_element_sym(const double (&X)[4][2], const double (&u)[4][2],
+                                                  const double *__restrict__ Tsm, const double mu, const double lam,
+                                                  double *__restrict__ dst) {
+  double fe[8], Kd[4][4], Ko[6][4];   // diagonal blocks (a,a) and the 6 blocks a < b, each [i][k] row-major
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fe[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Kd[i][j] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ko[i][j] = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2], g[4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      const double2 x = reinterpret_cast<const double2 *>(A.coords)[nd[a]];
-      const double2 v = reinterpret_cast<const double2 *>(A.U)[nd[a]];
-      u[a][0] = v.x; u[a][1] = v.y;
       const double d0 = Tsm[q * 8 + a * 2], d1 = Tsm[q * 8 + a * 2 + 1];
       G[a][0] = d0; G[a][1] = d1;
-      J[0] = fma(x.x, d0, J[0]); J[1] = fma(x.x, d1, J[1]); J[2] = fma(x.y, d0, J[2]); J[3] = fma(x.y, d1, J[3]);
+      J[0] = fma(X[a][0], d0, J[0]); J[1] = fma(X[a][0], d1, J[1]);
+      J[2] = fma(X[a][1], d0, J[2]); J[3] = fma(X[a][1], d1, J[3]);
     }
     const double detJ = inv2(J, Ji);
 #pragma unroll
@@ -90,101 +82,308 @@ k_asm_q1_2d_gather(const AsmArgs A, const PlanArgs P, const __grid_constant__ Ta
     const double detF = inv2(F, Fi);
     const double lnJ = log(detF);
     const double wd = Tsm[32 + q] * detJ;
-    double2 *rec = reinterpret_cast<double2 *>(Q + (size_t)s * G2_ES + q * G2_QS);
+    const double wmu = wd * mu, wcl = wd * lam * lnJ;
+    if (DO_R) {
+      const double P00 = fma(wmu, F[0] - Fi[0], wcl * Fi[0]), P01 = fma(wmu, F[1] - Fi[2], wcl * Fi[2]);
+      const double P10 = fma(wmu, F[2] - Fi[1], wcl * Fi[1]), P11 = fma(wmu, F[3] - Fi[3], wcl * Fi[3]);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {   // per node: {G_a, g_a} = 32 B, so the lane-dependent reads of phase 1b do not conflict
-      rec[2 * a] = make_double2(G[a][0], G[a][1]);
-      rec[2 * a + 1] = make_double2(fma(G[a][0], Fi[0], G[a][1] * Fi[2]), fma(G[a][0], Fi[1], G[a][1] * Fi[3]));
-    }
-    const double cl = lam * lnJ, wmu = wd * mu, wcl = wd * cl;
-    rec[8] = make_double2(wmu, wd * lam);
-    rec[9] = make_double2(wmu - wcl, fma(wmu, F[0] - Fi[0], wcl * Fi[0]));                     // c3, P00
-    rec[10] = make_double2(fma(wmu, F[1] - Fi[2], wcl * Fi[2]), fma(wmu, F[2] - Fi[1], wcl * Fi[1]));  // P01, P10
-    rec[11] = make_double2(fma(wmu, F[3] - Fi[3], wcl * Fi[3]), 0.0);                           // P11
-  }
-  __syncthreads();
-
-  // ---- phase 1b: row block a of K_e and f_a for this thread's (element, local node) item ----
-  double K[4][2][2], f[2] = {0.0, 0.0};
-  const int s = it & 0xfff, a = (it >> 12) & 7;
-  const int nl = (it >> 16) & 0xff, rank = have ? (int)(it >> 24) : -1;
-#pragma unroll
-  for (int b = 0; b < 4; ++b) { K[b][0][0] = K[b][0][1] = K[b][1][0] = K[b][1][1] = 0.0; }
-  if (have) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const double2 *rec = reinterpret_cast<const double2 *>(Q + (size_t)s * G2_ES + q * G2_QS);
-      const double2 Ga = rec[2 * a], ga = rec[2 * a + 1];
-      const double2 c12 = rec[8], c3p = rec[9];
-      if (DO_R) {
-        const double2 p1 = rec[10], p2 = rec[11];
-        f[0] = fma(c3p.y, Ga.x, fma(p1.x, Ga.y, f[0]));     // P00 G0 + P01 G1
-        f[1] = fma(p1.y, Ga.x, fma(p2.x, Ga.y, f[1]));      // P10 G0 + P11 G1
-      }
-      if (DO_K) {
-        // K_{ai,bk} += c1 (G_a.G_b) d_ik + c2 g_ai g_bk + c3 g_ak g_bi  -- 10 FMAs per b
-        const double c1Gx = c12.x * Ga.x, c1Gy = c12.x * Ga.y;
-        const double c2g0 = c12.y * ga.x, c2g1 = c12.y * ga.y;
-        const double c3g0 = c3p.x * ga.x, c3g1 = c3p.x * ga.y;
-        const double d0 = c2g0 + c3g0, d1 = c2g1 + c3g1;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double2 Gb = rec[2 * b], gb = rec[2 * b + 1];
-          K[b][0][0] = fma(d0, gb.x, fma(c1Gx, Gb.x, fma(c1Gy, Gb.y, K[b][0][0])));
-          K[b][0][1] = fma(c2g0, gb.y, fma(c3g1, gb.x, K[b][0][1]));
-          K[b][1][0] = fma(c2g1, gb.x, fma(c3g0, gb.y, K[b][1][0]));
-          K[b][1][1] = fma(d1, gb.y, fma(c1Gx, Gb.x, fma(c1Gy, Gb.y, K[b][1][1])));
-        }
+      for (int a = 0; a < 4; ++a) {
+        fe[a * 2] = fma(P00, G[a][0], fma(P01, G[a][1], fe[a * 2]));
+        fe[a * 2 + 1] = fma(P10, G[a][0], fma(P11, G[a][1], fe[a * 2 + 1]));
       }
     }
-  }
-  __syncthreads();                       // everyone is done reading Q: its storage becomes the row buffers
-  if (DO_K) for (int k = tid; k < G2_NC * P.rp; k += G2_THREADS) racc[k] = 0.0;
-  __syncthreads();
-  // ---- phase 2: round j adds every node's j-th adjacent element (ascending element id) ----
-  const int pb[4] = {(int)(pp.x & 0xffff), (int)(pp.x >> 16), (int)(pp.y & 0xffff), (int)(pp.y >> 16)};
-  for (int j = 0; j < P.max_adj; ++j) {
-    if (rank == j) {
-      if (DO_K) {
-        double *r0 = racc + (size_t)nl * P.rp, *r1 = r0 + P.rs;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          r0[2 * pb[b]] += K[b][0][0]; r0[2 * pb[b] + 1] += K[b][0][1];
-          r1[2 * pb[b]] += K[b][1][0]; r1[2 * pb[b] + 1] += K[b][1][1];
-        }
-      }
-      if (DO_R) { rres[nl * 2] += f[0]; rres[nl * 2 + 1] += f[1]; }
-    }
-    __syncthreads();
-  }
-  // ---- phase 3: write each row once ----
-  if (my_node >= 0) {
-    const int i = tid & 1;
     if (DO_K) {
-      double *row = A.vals + 4 * my_b0 + (int64_t)i * 2 * my_deg;
-      const double *acc = racc + (size_t)(tid >> 1) * P.rp + i * P.rs;
-      for (int j = 0; j < 2 * my_deg; ++j) row[j] = acc[j];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        g[a][0] = fma(G[a][0], Fi[0], G[a][1] * Fi[2]);
+        g[a][1] = fma(G[a][0], Fi[1], G[a][1] * Fi[3]);
+      }
+      const double c2 = wd * lam, c3 = wmu - wcl;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double c1Gx = wmu * G[a][0], c1Gy = wmu * G[a][1];
+        const double c2g0 = c2 * g[a][0], c2g1 = c2 * g[a][1], c3g0 = c3 * g[a][0], c3g1 = c3 * g[a][1];
+        const double d0 = c2g0 + c3g0, d1 = c2g1 + c3g1;
+        // diagonal block (a,a): symmetric itself, computed in full
+        Kd[a][0] = fma(d0, g[a][0], fma(c1Gx, G[a][0], fma(c1Gy, G[a][1], Kd[a][0])));
+        Kd[a][1] = fma(c2g0, g[a][1], fma(c3g1, g[a][0], Kd[a][1]));
+        Kd[a][2] = fma(c2g1, g[a][0], fma(c3g0, g[a][1], Kd[a][2]));
+        Kd[a][3] = fma(d1, g[a][1], fma(c1Gx, G[a][0], fma(c1Gy, G[a][1], Kd[a][3])));
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+          const int ob = (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5
+          Ko[ob][0] = fma(d0, g[b][0], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Ko[ob][0])));
+          Ko[ob][1] = fma(c2g0, g[b][1], fma(c3g1, g[b][0], Ko[ob][1]));
+          Ko[ob][2] = fma(c2g1, g[b][0], fma(c3g0, g[b][1], Ko[ob][2]));
+          Ko[ob][3] = fma(d1, g[b][1], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Ko[ob][3])));
+        }
+      }
     }
-    if (DO_R) A.R[2 * (int64_t)my_node + i] = rres[tid];
+  }
+  // symmetric storage: blocks (a,b), a <= b, in the order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3),
+  // each [i][k] row-major (4 doubles); then fe[8]
+  double2 *d2 = reinterpret_cast<double2 *>(dst);
+  if (DO_K) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int bd = (a == 0) ? 0 : (a == 1 ? 4 : (a == 2 ? 7 : 9));
+      d2[bd * 2] = make_double2(Kd[a][0], Kd[a][1]);
+      d2[bd * 2 + 1] = make_double2(Kd[a][2], Kd[a][3]);
+#pragma unroll
+      for (int b = a + 1; b < 4; ++b) {
+        const int ob = (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);
+        const int bo = bd + (b - a);
+        d2[bo * 2] = make_double2(Ko[ob][0], Ko[ob][1]);
+        d2[bo * 2 + 1] = make_double2(Ko[ob][2], Ko[ob][3]);
+      }
+    }
+  }
+  if (DO_R) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) d2[20 + a] = make_double2(fe[a * 2], fe[a * 2 + 1]);
   }
 }
 
-// ---- host side ---------------------------------------------------------------------------------
+template <bool DO_R, bool DO_K>
+__global__ void __launch_bounds__(G2_THREADS, 2)
+k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ TabQ1 T,
+                   const __grid_constant__ MatParams mp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // ---- shared-memory carve-up (all sub-buffers 16-byte aligned) ----
+  const int tn_words = 4 + P.maxt;
+  const size_t ks_sz = (size_t)P.maxe * G2_KS;
+  double *Ks = reinterpret_cast<double *>(smem_raw);                                  // [2][maxe][G2_KS]
+  double *Tsm = Ks + 2 * ks_sz;                                                       // 40 doubles
+  int32_t *tnb = reinterpret_cast<int32_t *>(Tsm + 40);                               // [3][tn_words]
+  unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [3] stage buffers
+  const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NC * 8, b_cn = b_lc + (size_t)P.maxe * 4,
+               b_dg = b_cn + G2_NC * 4, b_ns = b_dg + G2_NC * 4, b_size = b_ns + (size_t)G2_NC * P.ns * 4;
+  const int tid = threadIdx.x;
+  if (tid < 32) Tsm[tid] = T.dN[tid >> 3][(tid >> 1) & 3][tid & 1];
+  else if (tid < 36) Tsm[tid] = T.w[tid - 32];
+
+  auto issue_A = [&](int64_t c, int k) {          // node list of cluster c -> tnb[k % 3]
+    if (c < P.ncl) {
+      const int32_t *src = P.tn + c * tn_words;
+      int32_t *dst = tnb + (k % 3) * tn_words;
+      for (int w = tid * 4; w < tn_words; w += G2_THREADS * 4) cp_async16(dst + w, src + w);
+    }
+    cp_async_commit();
+  };
+  auto issue_B = [&](int64_t c, int k) {          // everything else of cluster c -> stage k % 3
+    if (c < P.ncl) {
+      unsigned char *B = bbase + (size_t)(k % 3) * b_size;
+      const int32_t *tn = tnb + (k % 3) * tn_words;
+      const int nt = tn[0];
+      double *xu = reinterpret_cast<double *>(B + b_xu);
+      for (int t = tid; t < nt; t += G2_THREADS) {
+        const int id = tn[4 + t];
+        cp_async16(xu + 4 * t, A.coords + 2 * (int64_t)id);
+        cp_async16(xu + 4 * t + 2, A.U + 2 * (int64_t)id);
+      }
+      for (int w = tid * 2; w < G2_NC; w += G2_THREADS * 2) cp_async16(B + b_b0 + w * 8, P.b0 + c * G2_NC + w);
+      for (int w = tid * 4; w < P.maxe; w += G2_THREADS * 4) cp_async16(B + b_lc + w * 4, P.lconn + c * P.maxe + w);
+      for (int w = tid * 4; w < G2_NC; w += G2_THREADS * 4) {
+        cp_async16(B + b_cn + w * 4, P.cn + c * G2_NC + w);
+        cp_async16(B + b_dg + w * 4, P.deg + c * G2_NC + w);
+      }
+      const int nsw = G2_NC * P.ns;   // uint32 entries, multiple of 4
+      for (int w = tid * 4; w < nsw; w += G2_THREADS * 4) cp_async16(B + b_ns + w * 4, P.nsrc + c * nsw + w);
+    }
+    cp_async_commit();
+  };
+  // phase 2 of one cluster by one warp: 2*G2_NC rows in passes of 32 lanes
+  auto gather_rows = [&](int k) {
+    const unsigned char *B = bbase + (size_t)(k % 3) * b_size;
+    const double *K2 = Ks + (size_t)(k & 1) * ks_sz;
+    const int lane = tid & 31;
+    for (int r = lane; r < 2 * G2_NC; r += 32) {
+      const int nl = r >> 1, i = r & 1;
+      const int node = reinterpret_cast<const int32_t *>(B + b_cn)[nl];
+      if (node < 0) continue;
+      const int64_t b0 = reinterpret_cast<const int64_t *>(B + b_b0)[nl];
+      const int deg = reinterpret_cast<const int32_t *>(B + b_dg)[nl];
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(B + b_ns) + (size_t)nl * P.ns;
+      double *row = A.vals + 4 * b0 + (int64_t)i * 2 * deg;
+      double rsum = 0.0;
+      double2 acc = make_double2(0.0, 0.0);
+      int cur = -1;
+      for (int m = 0; m < P.ns; ++m) {
+        const uint32_t code = src[m];
+        if (code == 0xffffffffu) break;
+        const int off = code & 0x3fff, jb = (code >> 16) & 0xff;
+        if (DO_K) {
+          if (jb != cur) {
+            if (cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
+            acc = make_double2(0.0, 0.0);
+            cur = jb;
+          }
+          if (code & 0x4000u) {       // block stored transposed (local row > local column)
+            acc.x += K2[off + i]; acc.y += K2[off + 2 + i];
+          } else {
+            const double2 v = *reinterpret_cast<const double2 *>(K2 + off + 2 * i);
+            acc.x += v.x; acc.y += v.y;
+          }
+        }
+        if (DO_R && (code & 0x8000u)) rsum += K2[(off / G2_KS) * G2_KS + 40 + (code >> 24) * 2 + i];
+      }
+      if (DO_K && cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
+      if (DO_R) A.R[2 * (int64_t)node + i] = rsum;
+    }
+  };
+
+  const double mu = mp.p[0], lam = mp.p[1];
+  const int64_t c0 = blockIdx.x, cstep = gridDim.x;
+  issue_A(c0, 0);
+  issue_A(c0 + cstep, 1);
+  cp_async_wait<1>();            // A(0) landed
+  __syncthreads();
+  issue_B(c0, 0);
+
+  int k = 0;
+  for (int64_t c = c0; c < P.ncl; c += cstep, ++k) {
+    issue_A(c + 2 * cstep, k + 2);
+    cp_async_wait<1>();          // everything but A(k+2): A(k+1) and B(k) have landed
+    __syncthreads();             // also: phase 1 of k-1 and phase 2 of k-2 are complete
+    issue_B(c + cstep, k + 1);   // flies while cluster k is computed (stage (k+1)%3 was last read by rows of k-2)
+
+    if (tid < G2_EW) {
+      // ---- phase 1 of cluster k: element integrals, one thread per element ----
+      const unsigned char *B = bbase + (size_t)(k % 3) * b_size;
+      const int ne = tnb[(k % 3) * tn_words + 1];
+      if (tid < ne) {
+        const double *xu = reinterpret_cast<const double *>(B + b_xu);
+        const unsigned lc = reinterpret_cast<const unsigned *>(B + b_lc)[tid];
+        double X[4][2], u[4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int t = (lc >> (8 * a)) & 0xff;
+          const double2 x = reinterpret_cast<const double2 *>(xu)[2 * t];
+          const double2 v = reinterpret_cast<const double2 *>(xu)[2 * t + 1];
+          X[a][0] = x.x; X[a][1] = x.y; u[a][0] = v.x; u[a][1] = v.y;
+        }
+        q1_2d_element_sym<DO_R, DO_K>(X, u, Tsm, mu, lam, Ks + (size_t)(k & 1) * ks_sz + (size_t)tid * G2_KS);
+      }
+    } else if (k > 0) {
+      gather_rows(k - 1);        // ---- phase 2 of cluster k-1, overlapped with phase 1 of k ----
+    }
+  }
+  __syncthreads();
+  if (k > 0 && tid >= G2_EW) gather_rows(k - 1);   // rows of the last cluster
+  cp_async_wait<0>();
+}
+
+// ---- host side: pack the cluster plan into fixed-stride device arrays ---------------------------
 bool nls_assembly_overwrites(const nls_context *h) { return h->dim == 2 && h->opt_assembly == 1 && h->have_plan; }
 int nls_gather_nc(void) { return G2_NC; }
-int nls_gather_max_items(void) { return G2_THREADS; }
-size_t nls_gather_smem(int max_elems, int maxdeg) {
-  const size_t rp = (size_t)(4 * maxdeg + 1);
-  return sizeof(double) * (std::max((size_t)max_elems * G2_ES, (size_t)G2_NC * rp) + 2 * G2_NC + 40);
+
+static size_t gather_smem(int maxt, int maxe, int ns) {
+  const size_t bsz = (size_t)maxt * 32 + G2_NC * 8 + (size_t)maxe * 4 + G2_NC * 4 + G2_NC * 4 + (size_t)G2_NC * ns * 4;
+  return (size_t)2 * maxe * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 3 * bsz;
+}
+
+void nls_gather_free(nls_context *h) {
+  GatherPlanDev &g = h->gplan;
+  if (g.tn) cudaFree(g.tn);
+  if (g.lconn) cudaFree(g.lconn);
+  if (g.cn) cudaFree(g.cn);
+  if (g.b0) cudaFree(g.b0);
+  if (g.deg) cudaFree(g.deg);
+  if (g.nsrc) cudaFree(g.nsrc);
+  g = GatherPlanDev();
+  h->have_plan = false;
+}
+
+// Sets h->have_plan when the mesh fits the kernel's packed formats; otherwise leaves it false and
+// the atomic-scatter kernel is used instead.
+int nls_gather_build(nls_context *h, const AsmPlan &plan) {
+  nls_gather_free(h);
+  if (h->dim != 2 || plan.ncl == 0) return NLS_OK;
+  const int nen = 4;
+  const int64_t ncl = plan.ncl;
+  const int32_t *conn = h->h_conn.data();
+  int maxdeg = 0;
+  for (int64_t a = 0; a < h->n_owned; ++a) maxdeg = std::max<int>(maxdeg, (int)(h->h_browptr[a + 1] - h->h_browptr[a]));
+  if (plan.max_elems > G2_EW || (size_t)plan.max_elems * G2_KS > 0x3fff || maxdeg > 255 || plan.max_adj > 8) return NLS_OK;
+  std::vector<std::vector<int32_t>> touched((size_t)ncl);
+  int maxt = 0;
+  for (int64_t c = 0; c < ncl; ++c) {
+    std::vector<int32_t> &t = touched[c];
+    for (int32_t s = plan.eptr[c]; s < plan.eptr[c + 1]; ++s)
+      t.insert(t.end(), conn + (int64_t)plan.elems[s] * nen, conn + (int64_t)(plan.elems[s] + 1) * nen);
+    std::sort(t.begin(), t.end());
+    t.erase(std::unique(t.begin(), t.end()), t.end());
+    maxt = std::max<int>(maxt, (int)t.size());
+  }
+  if (maxt > 255) return NLS_OK;
+  const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, NS = (plan.max_adj * nen + 3) & ~3;
+  if (gather_smem(MAXT, MAXE, NS) > (size_t)200 * 1024) return NLS_OK;
+  const int tnw = 4 + MAXT;
+  std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NC, -1), deg((size_t)ncl * G2_NC, 0);
+  std::vector<uint32_t> lconn((size_t)ncl * MAXE, 0);
+  std::vector<int64_t> b0((size_t)ncl * G2_NC, 0);
+  std::vector<uint32_t> nsrc((size_t)ncl * G2_NC * NS, 0xffffffffu);
+  std::vector<uint32_t> codes;
+  for (int64_t c = 0; c < ncl; ++c) {
+    const std::vector<int32_t> &t = touched[c];
+    const int32_t e0 = plan.eptr[c], ne = plan.eptr[c + 1] - e0;
+    tn[c * tnw] = (int32_t)t.size(); tn[c * tnw + 1] = ne;
+    std::copy(t.begin(), t.end(), tn.begin() + c * tnw + 4);
+    for (int32_t s = 0; s < ne; ++s) {
+      uint32_t packed = 0;
+      for (int a = 0; a < nen; ++a) {
+        const int32_t nd = conn[(int64_t)plan.elems[e0 + s] * nen + a];
+        packed |= (uint32_t)(std::lower_bound(t.begin(), t.end(), nd) - t.begin()) << (8 * a);
+      }
+      lconn[c * MAXE + s] = packed;
+    }
+    for (int nl = 0; nl < G2_NC; ++nl) {
+      const int32_t a = plan.nodes[c * G2_NC + nl];
+      if (a < 0) continue;
+      cn[c * G2_NC + nl] = a;
+      b0[c * G2_NC + nl] = h->h_browptr[a];
+      deg[c * G2_NC + nl] = (int32_t)(h->h_browptr[a + 1] - h->h_browptr[a]);
+      const int32_t *lo = h->h_bcol.data() + h->h_browptr[a], *hi = h->h_bcol.data() + h->h_browptr[a + 1];
+      codes.clear();
+      for (int32_t s = 0; s < ne; ++s) {          // ascending slot = ascending element id
+        const int32_t *ce = conn + (int64_t)plan.elems[e0 + s] * nen;
+        int al = -1;
+        for (int q = 0; q < nen; ++q) if (ce[q] == a) al = q;
+        if (al < 0) continue;
+        for (int b = 0; b < nen; ++b) {
+          const uint32_t jb = (uint32_t)(std::lower_bound(lo, hi, ce[b]) - lo);
+          codes.push_back((jb << 16) | ((uint32_t)s << 4) | ((uint32_t)al << 2) | (uint32_t)b);   // sort key: (jb, slot)
+        }
+      }
+      std::sort(codes.begin(), codes.end());
+      if ((int)codes.size() > NS) return NLS_OK;   // cannot happen: NS >= max_adj * nen
+      for (size_t m = 0; m < codes.size(); ++m) {
+        const uint32_t kk = codes[m], jb = kk >> 16, s = (kk >> 4) & 0xfff, al = (kk >> 2) & 3, b = kk & 3;
+        static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
+        const uint32_t lo_ = std::min(al, b), hi_ = std::max(al, b);
+        const uint32_t off = s * G2_KS + (uint32_t)(bd[lo_] + (hi_ - lo_)) * 4;
+        nsrc[((size_t)c * G2_NC + nl) * NS + m] = off | (al > b ? 0x4000u : 0u) | (al == b ? 0x8000u : 0u) | (jb << 16) | (al << 24);
+      }
+    }
+  }
+  GatherPlanDev &g = h->gplan;
+  g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.ns = NS;
+#define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&g.field, sizeof(vec[0]) * vec.size())); \
+  NLS_CUDA(h, cudaMemcpyAsync(g.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
+  UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(nsrc, nsrc);
+#undef UP
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_plan = true;
+  return NLS_OK;
 }
 
 int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
   AsmArgs a{};
   a.nel = h->nel; a.n_owned = h->n_owned; a.conn = h->d_conn; a.coords = h->d_coords; a.U = h->d_U;
   a.R = h->d_R; a.vals = h->d_vals; a.browptr = h->d_browptr; a.pos = h->d_pos;
-  PlanArgs p{h->d_cl_nodes, h->d_cl_eptr, h->d_cl_iptr, reinterpret_cast<const int4 *>(h->d_cl_conn), h->d_cl_items,
-             reinterpret_cast<const uint2 *>(h->d_cl_ipos), h->plan_max_elems, 2 * h->plan_maxdeg, 4 * h->plan_maxdeg + 1, h->plan_max_adj};
-  const size_t shm = nls_gather_smem(h->plan_max_elems, h->plan_maxdeg);
+  const GatherPlanDev &g = h->gplan;
+  GatherArgs p{g.ncl, g.maxt, g.maxe, g.ns, g.tn, g.lconn, g.cn, g.b0, g.deg, g.nsrc};
+  const size_t shm = gather_smem(g.maxt, g.maxe, g.ns);
   static size_t shm_set = 0;
   if (shm > shm_set) {
     cudaFuncSetAttribute(k_asm_q1_2d_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
@@ -192,10 +391,11 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
     cudaFuncSetAttribute(k_asm_q1_2d_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
     shm_set = shm;
   }
-  const unsigned g = (unsigned)h->plan_ncl;
-  if (want_r && want_k) k_asm_q1_2d_gather<true, true><<<g, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
-  else if (want_r)      k_asm_q1_2d_gather<true, false><<<g, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
-  else                  k_asm_q1_2d_gather<false, true><<<g, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
+  const int per_sm = h->opt_gather_ctas > 0 ? h->opt_gather_ctas : 2;
+  const unsigned grid = (unsigned)std::min<int64_t>(g.ncl, (int64_t)h->sm_count * per_sm);
+  if (want_r && want_k) k_asm_q1_2d_gather<true, true><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
+  else if (want_r)      k_asm_q1_2d_gather<true, false><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
+  else                  k_asm_q1_2d_gather<false, true><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string("gather kernel launch: ") + cudaGetErrorString(e); return NLS_ERR_CUDA; }
   h->launches++;

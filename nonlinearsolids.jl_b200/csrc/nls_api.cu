@@ -44,8 +44,7 @@ __global__ void k_negate_into(int64_t n, const double *x, double *y) {
 static void free_pattern(nls_context *h) {
   dev_free(&h->d_browptr); dev_free(&h->d_bcol); dev_free(&h->d_rowptr); dev_free(&h->d_colind);
   dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
-  dev_free(&h->d_cl_nodes); dev_free(&h->d_cl_eptr); dev_free(&h->d_cl_elems); dev_free(&h->d_cl_iptr); dev_free(&h->d_cl_items); dev_free(&h->d_cl_conn); dev_free(&h->d_cl_ipos);
-  h->have_plan = false;
+  nls_gather_free(h);
   h->h_browptr.clear(); h->h_bcol.clear();
   h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
 }
@@ -345,28 +344,9 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
   // plan of the gather (row-owner) assembly: 2-D only for now; falls back to the atomic scatter
   // when a cluster would not fit in shared memory
   if (h->dim == 2 && h->n_owned > 0 && h->nel > 0) {
-    int maxdeg = 0;
-    for (int64_t a = 0; a < h->n_owned; ++a) maxdeg = std::max<int>(maxdeg, (int)(h->h_browptr[a + 1] - h->h_browptr[a]));
     AsmPlan plan;
-    nls_host_cluster_plan(h->dim, h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_coords.data(), nls_gather_nc(),
-                          &h->h_browptr, &h->h_bcol, plan);
-    if (nls_gather_smem(plan.max_elems, maxdeg) <= (size_t)110 * 1024 && plan.max_elems < 4096 && plan.max_adj < 256 &&
-        plan.max_items <= nls_gather_max_items()) {
-      h->plan_nc = plan.nc; h->plan_ncl = plan.ncl; h->plan_max_elems = plan.max_elems; h->plan_maxdeg = maxdeg; h->plan_max_adj = plan.max_adj;
-      NLS_TRY(dev_alloc(h, &h->d_cl_nodes, plan.nodes.size())); NLS_TRY(dev_alloc(h, &h->d_cl_eptr, plan.eptr.size()));
-      NLS_TRY(dev_alloc(h, &h->d_cl_elems, plan.elems.size())); NLS_TRY(dev_alloc(h, &h->d_cl_iptr, plan.iptr.size()));
-      NLS_TRY(dev_alloc(h, &h->d_cl_items, plan.items.size()));
-      NLS_TRY(dev_alloc(h, &h->d_cl_conn, plan.conn.size())); NLS_TRY(dev_alloc(h, &h->d_cl_ipos, plan.ipos.size()));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_conn, plan.conn.data(), sizeof(int32_t) * plan.conn.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_ipos, plan.ipos.data(), sizeof(uint16_t) * plan.ipos.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_nodes, plan.nodes.data(), sizeof(int32_t) * plan.nodes.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_eptr, plan.eptr.data(), sizeof(int32_t) * plan.eptr.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_elems, plan.elems.data(), sizeof(int32_t) * plan.elems.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_iptr, plan.iptr.data(), sizeof(int32_t) * plan.iptr.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaMemcpyAsync(h->d_cl_items, plan.items.data(), sizeof(uint32_t) * plan.items.size(), cudaMemcpyHostToDevice, h->stream));
-      NLS_CUDA(h, cudaStreamSynchronize(h->stream));
-      h->have_plan = true;
-    }
+    nls_host_cluster_plan(h->dim, h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_coords.data(), nls_gather_nc(), plan);
+    NLS_TRY(nls_gather_build(h, plan));
   }
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_pattern = true;
@@ -680,6 +660,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
+  if (!std::strcmp(key, "gather_ctas")) { h->opt_gather_ctas = value; return NLS_OK; }
   if (!std::strcmp(key, "spmv_lanes")) { h->opt_spmv_lanes = value; return NLS_OK; }
   NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: unknown key");
 }

@@ -46,19 +46,24 @@ struct AsmPlan {
   int64_t ncl = 0;                // clusters
   int max_elems = 0;              // largest element count of a cluster
   int max_adj = 0;                // largest number of elements around a node
-  int max_items = 0;              // largest number of (element, node) items of a cluster
-  std::vector<int32_t> conn;      // [elems.size()][nen] connectivity rows of the cluster elements
-  std::vector<uint16_t> ipos;     // [items.size()][nen] block positions of the element's nodes in the row of node a
   std::vector<int32_t> nodes;     // [ncl*nc] owned node id or -1
   std::vector<int32_t> eptr;      // [ncl+1] into elems
-  std::vector<int32_t> elems;     // element ids, ascending per cluster
-  std::vector<int32_t> iptr;      // [ncl+1] into items
-  std::vector<uint32_t> items;    // (element slot, local node a) pairs whose node is in the cluster:
-                                  // slot | a << 12 | node_local << 16 | rank << 24, sorted by (slot, a)
+  std::vector<int32_t> elems;     // element ids touching the cluster, ascending per cluster
 };
 void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
-                           const double *coords, int nc, const std::vector<int64_t> *browptr,
-                           const std::vector<int32_t> *bcol, AsmPlan &plan);
+                           const double *coords, int nc, AsmPlan &plan);
+
+// packed, fixed-stride device copy of the plan (kernels_gather.cu)
+struct GatherPlanDev {
+  int64_t ncl = 0;
+  int maxt = 0, maxe = 0, ns = 0;
+  int32_t *tn = nullptr;
+  uint32_t *lconn = nullptr;
+  int32_t *cn = nullptr;
+  int64_t *b0 = nullptr;
+  int32_t *deg = nullptr;
+  uint32_t *nsrc = nullptr;
+};
 
 // ---- device control block of the PCG loop (lives in device memory) ----
 struct PcgCtl {
@@ -122,14 +127,9 @@ struct nls_context {
   uint16_t *d_pos = nullptr;            // [nel][nen][nen] position of node b in block row of node a
   int32_t *d_diag = nullptr;            // [nrows] offset of the diagonal entry within its row
 
-  // gather-assembly plan (device copies)
+  // gather-assembly plan (device copy)
   bool have_plan = false;
-  int plan_nc = 0, plan_max_elems = 0, plan_maxdeg = 0, plan_max_adj = 0;
-  int64_t plan_ncl = 0;
-  int32_t *d_cl_nodes = nullptr, *d_cl_eptr = nullptr, *d_cl_elems = nullptr, *d_cl_iptr = nullptr;
-  uint32_t *d_cl_items = nullptr;
-  int32_t *d_cl_conn = nullptr;
-  uint16_t *d_cl_ipos = nullptr;
+  GatherPlanDev gplan;
   std::vector<double> h_coords;
 
   // vectors (ndof_local unless noted)
@@ -153,6 +153,7 @@ struct nls_context {
   // options
   int opt_spmv = 1;        // 0: scalar CSR SpMV; 1: block-aware traversal (dim >= 2)
   int opt_spmv_lanes = 0;  // lanes per node for the block-aware SpMV (0 = default)
+  int opt_gather_ctas = 0; // persistent CTAs per SM of the gather kernel (0 = default)
   int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: gather (row-owner) kernel where available
 
   // distributed
@@ -178,8 +179,8 @@ struct nls_context {
 int nls_launch_assembly(nls_context *h, bool want_r, bool want_k);
 bool nls_assembly_overwrites(const nls_context *h);
 int nls_gather_nc(void);
-int nls_gather_max_items(void);
-size_t nls_gather_smem(int max_elems, int maxdeg);
+int nls_gather_build(nls_context *h, const AsmPlan &plan);
+void nls_gather_free(nls_context *h);
 int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k);
 int nls_launch_apply_dirichlet(nls_context *h, double *U);
 int nls_launch_neumann(nls_context *h, double *R);
