@@ -21,9 +21,10 @@
 #include "asm_common.cuh"
 
 #define G2_NC 64          // owned nodes per cluster
-#define G2_THREADS 128    // warps 0..2: element integrals (phase 1); warp 3: row gather (phase 2), one cluster behind
-#define G2_EW 96          // element threads
-#define G2_KS 50          // doubles per element in shared memory: 10 symmetric 2x2 blocks, fe[8], pad 2 -> 25 x 16 B (odd)
+#define G2_THREADS 128
+#define G2_QS 24          // doubles per (element, quadrature point) record
+#define G2_KS (4 * G2_QS + 2)   // doubles per element in shared memory: 4 records, later overwritten by the
+                                // 10 symmetric 2x2 blocks + fe[8]; 49 x 16 B (odd stride -> conflict-free across elements)
 
 struct GatherArgs {
   int64_t ncl;
@@ -44,12 +45,49 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Element integrals with the tangent's symmetry: blocks b >= a accumulated, mirrored on store.
+// phase 1a: one quadrature point. Record (24 doubles): {G_a[2], g_a[2]} x 4 nodes, c1, c2, c3, wd*P[4], pad.
 template <bool DO_R, bool DO_K>
-__device__ __forceinline__ void q1_2d_element_sym(const double (&X)[4][2], const double (&u)[4][2],
-                                                  const double *__restrict__ Tsm, const double mu, const double lam,
-                                                  double *__restrict__ dst) {
-  double fe[8], Kd[4][4], Ko[6][4];   // diagonal blocks (a,a) and the 6 blocks a < b, each [i][k] row-major
+__device__ __forceinline__ void q1_2d_qp_record(const double (&X)[4][2], const double (&u)[4][2], const double *__restrict__ Tq,
+                                                const double w, const double mu, const double lam, double2 *__restrict__ rec) {
+  double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double d0 = Tq[a * 2], d1 = Tq[a * 2 + 1];
+    G[a][0] = d0; G[a][1] = d1;
+    J[0] = fma(X[a][0], d0, J[0]); J[1] = fma(X[a][0], d1, J[1]);
+    J[2] = fma(X[a][1], d0, J[2]); J[3] = fma(X[a][1], d1, J[3]);
+  }
+  const double detJ = inv2(J, Ji);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double d0 = G[a][0], d1 = G[a][1];
+    G[a][0] = fma(d0, Ji[0], d1 * Ji[2]);
+    G[a][1] = fma(d0, Ji[1], d1 * Ji[3]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { F[i * 2] = fma(u[a][i], G[a][0], F[i * 2]); F[i * 2 + 1] = fma(u[a][i], G[a][1], F[i * 2 + 1]); }
+  }
+  const double detF = inv2(F, Fi);
+  const double lnJ = log(detF);
+  const double wd = w * detJ;
+  const double wmu = wd * mu, wcl = wd * lam * lnJ;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    rec[2 * a] = make_double2(G[a][0], G[a][1]);
+    rec[2 * a + 1] = make_double2(fma(G[a][0], Fi[0], G[a][1] * Fi[2]), fma(G[a][0], Fi[1], G[a][1] * Fi[3]));
+  }
+  rec[8] = make_double2(wmu, wd * lam);
+  rec[9] = make_double2(wmu - wcl, fma(wmu, F[0] - Fi[0], wcl * Fi[0]));                        // c3, P00
+  rec[10] = make_double2(fma(wmu, F[1] - Fi[2], wcl * Fi[2]), fma(wmu, F[2] - Fi[1], wcl * Fi[1]));   // P01, P10
+  rec[11] = make_double2(fma(wmu, F[3] - Fi[3], wcl * Fi[3]), 0.0);                             // P11
+}
+
+// phase 1b: K_e (symmetric half) and f_e of one element from its 4 records; result overwrites the
+// start of the element's own record area (thread-private, so no synchronisation is needed):
+// blocks (a,b), a <= b, in the order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3), each [i][k]
+// row-major; then fe[8].
+template <bool DO_R, bool DO_K>
+__device__ __forceinline__ void q1_2d_accumulate_sym(double *__restrict__ el) {
+  double fe[8], Kd[4][4], Ko[6][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) fe[i] = 0.0;
 #pragma unroll
@@ -60,69 +98,43 @@ __device__ __forceinline__ void q1_2d_element_sym(const double (&X)[4][2], const
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) Ko[i][j] = 0.0;
-#pragma unroll 1
+#pragma unroll
   for (int q = 0; q < 4; ++q) {
-    double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2], g[4][2];
+    const double2 *rec = reinterpret_cast<const double2 *>(el + q * G2_QS);
+    double2 G[4], g[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double d0 = Tsm[q * 8 + a * 2], d1 = Tsm[q * 8 + a * 2 + 1];
-      G[a][0] = d0; G[a][1] = d1;
-      J[0] = fma(X[a][0], d0, J[0]); J[1] = fma(X[a][0], d1, J[1]);
-      J[2] = fma(X[a][1], d0, J[2]); J[3] = fma(X[a][1], d1, J[3]);
-    }
-    const double detJ = inv2(J, Ji);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double d0 = G[a][0], d1 = G[a][1];
-      G[a][0] = fma(d0, Ji[0], d1 * Ji[2]);
-      G[a][1] = fma(d0, Ji[1], d1 * Ji[3]);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) { F[i * 2] = fma(u[a][i], G[a][0], F[i * 2]); F[i * 2 + 1] = fma(u[a][i], G[a][1], F[i * 2 + 1]); }
-    }
-    const double detF = inv2(F, Fi);
-    const double lnJ = log(detF);
-    const double wd = Tsm[32 + q] * detJ;
-    const double wmu = wd * mu, wcl = wd * lam * lnJ;
+    for (int a = 0; a < 4; ++a) { G[a] = rec[2 * a]; g[a] = rec[2 * a + 1]; }
+    const double2 c12 = rec[8], c3p = rec[9];
     if (DO_R) {
-      const double P00 = fma(wmu, F[0] - Fi[0], wcl * Fi[0]), P01 = fma(wmu, F[1] - Fi[2], wcl * Fi[2]);
-      const double P10 = fma(wmu, F[2] - Fi[1], wcl * Fi[1]), P11 = fma(wmu, F[3] - Fi[3], wcl * Fi[3]);
+      const double2 p1 = rec[10], p2 = rec[11];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        fe[a * 2] = fma(P00, G[a][0], fma(P01, G[a][1], fe[a * 2]));
-        fe[a * 2 + 1] = fma(P10, G[a][0], fma(P11, G[a][1], fe[a * 2 + 1]));
+        fe[a * 2] = fma(c3p.y, G[a].x, fma(p1.x, G[a].y, fe[a * 2]));
+        fe[a * 2 + 1] = fma(p1.y, G[a].x, fma(p2.x, G[a].y, fe[a * 2 + 1]));
       }
     }
     if (DO_K) {
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        g[a][0] = fma(G[a][0], Fi[0], G[a][1] * Fi[2]);
-        g[a][1] = fma(G[a][0], Fi[1], G[a][1] * Fi[3]);
-      }
-      const double c2 = wd * lam, c3 = wmu - wcl;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double c1Gx = wmu * G[a][0], c1Gy = wmu * G[a][1];
-        const double c2g0 = c2 * g[a][0], c2g1 = c2 * g[a][1], c3g0 = c3 * g[a][0], c3g1 = c3 * g[a][1];
+        const double c1Gx = c12.x * G[a].x, c1Gy = c12.x * G[a].y;
+        const double c2g0 = c12.y * g[a].x, c2g1 = c12.y * g[a].y, c3g0 = c3p.x * g[a].x, c3g1 = c3p.x * g[a].y;
         const double d0 = c2g0 + c3g0, d1 = c2g1 + c3g1;
-        // diagonal block (a,a): symmetric itself, computed in full
-        Kd[a][0] = fma(d0, g[a][0], fma(c1Gx, G[a][0], fma(c1Gy, G[a][1], Kd[a][0])));
-        Kd[a][1] = fma(c2g0, g[a][1], fma(c3g1, g[a][0], Kd[a][1]));
-        Kd[a][2] = fma(c2g1, g[a][0], fma(c3g0, g[a][1], Kd[a][2]));
-        Kd[a][3] = fma(d1, g[a][1], fma(c1Gx, G[a][0], fma(c1Gy, G[a][1], Kd[a][3])));
+        Kd[a][0] = fma(d0, g[a].x, fma(c1Gx, G[a].x, fma(c1Gy, G[a].y, Kd[a][0])));
+        Kd[a][1] = fma(c2g0, g[a].y, fma(c3g1, g[a].x, Kd[a][1]));
+        Kd[a][2] = fma(c2g1, g[a].x, fma(c3g0, g[a].y, Kd[a][2]));
+        Kd[a][3] = fma(d1, g[a].y, fma(c1Gx, G[a].x, fma(c1Gy, G[a].y, Kd[a][3])));
 #pragma unroll
         for (int b = a + 1; b < 4; ++b) {
           const int ob = (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5
-          Ko[ob][0] = fma(d0, g[b][0], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Ko[ob][0])));
-          Ko[ob][1] = fma(c2g0, g[b][1], fma(c3g1, g[b][0], Ko[ob][1]));
-          Ko[ob][2] = fma(c2g1, g[b][0], fma(c3g0, g[b][1], Ko[ob][2]));
-          Ko[ob][3] = fma(d1, g[b][1], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Ko[ob][3])));
+          Ko[ob][0] = fma(d0, g[b].x, fma(c1Gx, G[b].x, fma(c1Gy, G[b].y, Ko[ob][0])));
+          Ko[ob][1] = fma(c2g0, g[b].y, fma(c3g1, g[b].x, Ko[ob][1]));
+          Ko[ob][2] = fma(c2g1, g[b].x, fma(c3g0, g[b].y, Ko[ob][2]));
+          Ko[ob][3] = fma(d1, g[b].y, fma(c1Gx, G[b].x, fma(c1Gy, G[b].y, Ko[ob][3])));
         }
       }
     }
   }
-  // symmetric storage: blocks (a,b), a <= b, in the order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3),
-  // each [i][k] row-major (4 doubles); then fe[8]
-  double2 *d2 = reinterpret_cast<double2 *>(dst);
+  double2 *d2 = reinterpret_cast<double2 *>(el);
   if (DO_K) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -151,11 +163,10 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // ---- shared-memory carve-up (all sub-buffers 16-byte aligned) ----
   const int tn_words = 4 + P.maxt;
-  const size_t ks_sz = (size_t)P.maxe * G2_KS;
-  double *Ks = reinterpret_cast<double *>(smem_raw);                                  // [2][maxe][G2_KS]
-  double *Tsm = Ks + 2 * ks_sz;                                                       // 40 doubles
+  double *Qs = reinterpret_cast<double *>(smem_raw);                                  // [maxe][G2_KS]
+  double *Tsm = Qs + (size_t)P.maxe * G2_KS;                                          // 40 doubles
   int32_t *tnb = reinterpret_cast<int32_t *>(Tsm + 40);                               // [3][tn_words]
-  unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [3] stage buffers
+  unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [2] stage buffers
   const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NC * 8, b_cn = b_lc + (size_t)P.maxe * 4,
                b_dg = b_cn + G2_NC * 4, b_ns = b_dg + G2_NC * 4, b_size = b_ns + (size_t)G2_NC * P.ns * 4;
   const int tid = threadIdx.x;
@@ -170,9 +181,9 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
     }
     cp_async_commit();
   };
-  auto issue_B = [&](int64_t c, int k) {          // everything else of cluster c -> stage k % 3
+  auto issue_B = [&](int64_t c, int k) {          // everything else of cluster c -> stage k & 1
     if (c < P.ncl) {
-      unsigned char *B = bbase + (size_t)(k % 3) * b_size;
+      unsigned char *B = bbase + (size_t)(k & 1) * b_size;
       const int32_t *tn = tnb + (k % 3) * tn_words;
       const int nt = tn[0];
       double *xu = reinterpret_cast<double *>(B + b_xu);
@@ -192,45 +203,6 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
     }
     cp_async_commit();
   };
-  // phase 2 of one cluster by one warp: 2*G2_NC rows in passes of 32 lanes
-  auto gather_rows = [&](int k) {
-    const unsigned char *B = bbase + (size_t)(k % 3) * b_size;
-    const double *K2 = Ks + (size_t)(k & 1) * ks_sz;
-    const int lane = tid & 31;
-    for (int r = lane; r < 2 * G2_NC; r += 32) {
-      const int nl = r >> 1, i = r & 1;
-      const int node = reinterpret_cast<const int32_t *>(B + b_cn)[nl];
-      if (node < 0) continue;
-      const int64_t b0 = reinterpret_cast<const int64_t *>(B + b_b0)[nl];
-      const int deg = reinterpret_cast<const int32_t *>(B + b_dg)[nl];
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(B + b_ns) + (size_t)nl * P.ns;
-      double *row = A.vals + 4 * b0 + (int64_t)i * 2 * deg;
-      double rsum = 0.0;
-      double2 acc = make_double2(0.0, 0.0);
-      int cur = -1;
-      for (int m = 0; m < P.ns; ++m) {
-        const uint32_t code = src[m];
-        if (code == 0xffffffffu) break;
-        const int off = code & 0x3fff, jb = (code >> 16) & 0xff;
-        if (DO_K) {
-          if (jb != cur) {
-            if (cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
-            acc = make_double2(0.0, 0.0);
-            cur = jb;
-          }
-          if (code & 0x4000u) {       // block stored transposed (local row > local column)
-            acc.x += K2[off + i]; acc.y += K2[off + 2 + i];
-          } else {
-            const double2 v = *reinterpret_cast<const double2 *>(K2 + off + 2 * i);
-            acc.x += v.x; acc.y += v.y;
-          }
-        }
-        if (DO_R && (code & 0x8000u)) rsum += K2[(off / G2_KS) * G2_KS + 40 + (code >> 24) * 2 + i];
-      }
-      if (DO_K && cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
-      if (DO_R) A.R[2 * (int64_t)node + i] = rsum;
-    }
-  };
 
   const double mu = mp.p[0], lam = mp.p[1];
   const int64_t c0 = blockIdx.x, cstep = gridDim.x;
@@ -244,16 +216,19 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   for (int64_t c = c0; c < P.ncl; c += cstep, ++k) {
     issue_A(c + 2 * cstep, k + 2);
     cp_async_wait<1>();          // everything but A(k+2): A(k+1) and B(k) have landed
-    __syncthreads();             // also: phase 1 of k-1 and phase 2 of k-2 are complete
-    issue_B(c + cstep, k + 1);   // flies while cluster k is computed (stage (k+1)%3 was last read by rows of k-2)
+    __syncthreads();
+    issue_B(c + cstep, k + 1);   // flies while cluster k is computed
 
-    if (tid < G2_EW) {
-      // ---- phase 1 of cluster k: element integrals, one thread per element ----
-      const unsigned char *B = bbase + (size_t)(k % 3) * b_size;
-      const int ne = tnb[(k % 3) * tn_words + 1];
-      if (tid < ne) {
-        const double *xu = reinterpret_cast<const double *>(B + b_xu);
-        const unsigned lc = reinterpret_cast<const unsigned *>(B + b_lc)[tid];
+    const unsigned char *B = bbase + (size_t)(k & 1) * b_size;
+    const int ne = tnb[(k % 3) * tn_words + 1];
+    // ---- phase 1a: one thread per (element, quadrature point): the latency-bound geometry chain
+    //      (J, J^-1, F, F^-1, log) gets 4x the thread-level parallelism of a per-element thread ----
+    {
+      const double *xu = reinterpret_cast<const double *>(B + b_xu);
+      const unsigned *lcv = reinterpret_cast<const unsigned *>(B + b_lc);
+      for (int w = tid; w < ne * 4; w += G2_THREADS) {
+        const int sl = w >> 2, q = w & 3;
+        const unsigned lc = lcv[sl];
         double X[4][2], u[4][2];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -262,14 +237,51 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
           const double2 v = reinterpret_cast<const double2 *>(xu)[2 * t + 1];
           X[a][0] = x.x; X[a][1] = x.y; u[a][0] = v.x; u[a][1] = v.y;
         }
-        q1_2d_element_sym<DO_R, DO_K>(X, u, Tsm, mu, lam, Ks + (size_t)(k & 1) * ks_sz + (size_t)tid * G2_KS);
+        q1_2d_qp_record<DO_R, DO_K>(X, u, Tsm + q * 8, Tsm[32 + q], mu, lam,
+                                    reinterpret_cast<double2 *>(Qs + (size_t)sl * G2_KS + q * G2_QS));
       }
-    } else if (k > 0) {
-      gather_rows(k - 1);        // ---- phase 2 of cluster k-1, overlapped with phase 1 of k ----
     }
+    __syncthreads();
+    // ---- phase 1b: one thread per element: pure FMA stream over its 4 records ----
+    if (tid < ne) q1_2d_accumulate_sym<DO_R, DO_K>(Qs + (size_t)tid * G2_KS);
+    __syncthreads();
+    // ---- phase 2: one thread per (owned node, component) writes its row ----
+    {
+      const int nl = tid >> 1, i = tid & 1;
+      const int node = reinterpret_cast<const int32_t *>(B + b_cn)[nl];
+      if (node >= 0) {
+        const int64_t b0 = reinterpret_cast<const int64_t *>(B + b_b0)[nl];
+        const int deg = reinterpret_cast<const int32_t *>(B + b_dg)[nl];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(B + b_ns) + (size_t)nl * P.ns;
+        double *row = A.vals + 4 * b0 + (int64_t)i * 2 * deg;
+        double rsum = 0.0;
+        double2 acc = make_double2(0.0, 0.0);
+        int cur = -1;
+        for (int m = 0; m < P.ns; ++m) {
+          const uint32_t code = src[m];
+          if (code == 0xffffffffu) break;
+          const int off = code & 0x3fff, jb = (code >> 16) & 0xff;
+          if (DO_K) {
+            if (jb != cur) {
+              if (cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
+              acc = make_double2(0.0, 0.0);
+              cur = jb;
+            }
+            if (code & 0x4000u) {       // block stored transposed (local row > local column)
+              acc.x += Qs[off + i]; acc.y += Qs[off + 2 + i];
+            } else {
+              const double2 v = *reinterpret_cast<const double2 *>(Qs + off + 2 * i);
+              acc.x += v.x; acc.y += v.y;
+            }
+          }
+          if (DO_R && (code & 0x8000u)) rsum += Qs[(off / G2_KS) * G2_KS + 40 + (code >> 24) * 2 + i];
+        }
+        if (DO_K && cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
+        if (DO_R) A.R[2 * (int64_t)node + i] = rsum;
+      }
+    }
+    __syncthreads();             // Qs and stage k & 1 are free again
   }
-  __syncthreads();
-  if (k > 0 && tid >= G2_EW) gather_rows(k - 1);   // rows of the last cluster
   cp_async_wait<0>();
 }
 
@@ -279,7 +291,7 @@ int nls_gather_nc(void) { return G2_NC; }
 
 static size_t gather_smem(int maxt, int maxe, int ns) {
   const size_t bsz = (size_t)maxt * 32 + G2_NC * 8 + (size_t)maxe * 4 + G2_NC * 4 + G2_NC * 4 + (size_t)G2_NC * ns * 4;
-  return (size_t)2 * maxe * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 3 * bsz;
+  return (size_t)maxe * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
 }
 
 void nls_gather_free(nls_context *h) {
@@ -304,7 +316,7 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   const int32_t *conn = h->h_conn.data();
   int maxdeg = 0;
   for (int64_t a = 0; a < h->n_owned; ++a) maxdeg = std::max<int>(maxdeg, (int)(h->h_browptr[a + 1] - h->h_browptr[a]));
-  if (plan.max_elems > G2_EW || (size_t)plan.max_elems * G2_KS > 0x3fff || maxdeg > 255 || plan.max_adj > 8) return NLS_OK;
+  if (plan.max_elems > G2_THREADS || (size_t)plan.max_elems * G2_KS > 0x3fff || maxdeg > 255 || plan.max_adj > 8) return NLS_OK;
   std::vector<std::vector<int32_t>> touched((size_t)ncl);
   int maxt = 0;
   for (int64_t c = 0; c < ncl; ++c) {
