@@ -28,13 +28,14 @@
 
 struct GatherArgs {
   int64_t ncl;
-  int maxt, maxe, ns;     // padded strides: touched nodes, elements, sources per node
+  int maxt, maxe, ns, rp; // padded strides: touched nodes, elements, sources per node, row-buffer doubles per node
   const int32_t *tn;      // [ncl][4 + maxt]: {nt, ne, 0, 0}, node ids
   const uint32_t *lconn;  // [ncl][maxe]: 4 local node indices (bytes) into the touched-node list
   const int32_t *cn;      // [ncl][G2_NC] owned node ids (-1 = none)
   const int64_t *b0;      // [ncl][G2_NC] block-row start of the node
   const int32_t *deg;     // [ncl][G2_NC] block-row length
   const uint32_t *nsrc;   // [ncl][G2_NC][ns]: Ks offset (14 bits) | lower << 14 | diag << 15 | jb << 16, ~0 = end
+  unsigned long long *prof; // optional per-phase cycle counters (nls_set_option "profile_phases"), else NULL
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -164,7 +165,7 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   // ---- shared-memory carve-up (all sub-buffers 16-byte aligned) ----
   const int tn_words = 4 + P.maxt;
   double *Qs = reinterpret_cast<double *>(smem_raw);                                  // [maxe][G2_KS]
-  double *Tsm = Qs + (size_t)P.maxe * G2_KS;                                          // 40 doubles
+  double *Tsm = Qs + (size_t)P.maxe * G2_KS + 4;                                      // 4 zero doubles (dummy source), then 40 doubles
   int32_t *tnb = reinterpret_cast<int32_t *>(Tsm + 40);                               // [3][tn_words]
   unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [2] stage buffers
   const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NC * 8, b_cn = b_lc + (size_t)P.maxe * 4,
@@ -172,6 +173,7 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   const int tid = threadIdx.x;
   if (tid < 32) Tsm[tid] = T.dN[tid >> 3][(tid >> 1) & 3][tid & 1];
   else if (tid < 36) Tsm[tid] = T.w[tid - 32];
+  else if (tid < 40) Tsm[tid - 40] = 0.0;   // the zero slot just below Tsm
 
   auto issue_A = [&](int64_t c, int k) {          // node list of cluster c -> tnb[k % 3]
     if (c < P.ncl) {
@@ -214,10 +216,12 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
 
   int k = 0;
   for (int64_t c = c0; c < P.ncl; c += cstep, ++k) {
+    const long long tp0 = P.prof ? clock64() : 0;
     issue_A(c + 2 * cstep, k + 2);
     cp_async_wait<1>();          // everything but A(k+2): A(k+1) and B(k) have landed
     __syncthreads();
     issue_B(c + cstep, k + 1);   // flies while cluster k is computed
+    const long long tp1 = P.prof ? clock64() : 0;
 
     const unsigned char *B = bbase + (size_t)(k & 1) * b_size;
     const int ne = tnb[(k % 3) * tn_words + 1];
@@ -242,9 +246,11 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
       }
     }
     __syncthreads();
+    const long long tp2 = P.prof ? clock64() : 0;
     // ---- phase 1b: one thread per element: pure FMA stream over its 4 records ----
     if (tid < ne) q1_2d_accumulate_sym<DO_R, DO_K>(Qs + (size_t)tid * G2_KS);
     __syncthreads();
+    const long long tp3 = P.prof ? clock64() : 0;
     // ---- phase 2: one thread per (owned node, component) writes its row ----
     {
       const int nl = tid >> 1, i = tid & 1;
@@ -256,31 +262,35 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
         double *row = A.vals + 4 * b0 + (int64_t)i * 2 * deg;
         double rsum = 0.0;
         double2 acc = make_double2(0.0, 0.0);
-        int cur = -1;
+        // branch-free walk: every list has exactly P.ns entries (padded with sources that point at the
+        // zero slot); bit 14 = block stored transposed, bit 15 = diagonal block (adds f_e), bit 26 = last
+        // source of its column block (flush)
+#pragma unroll 4
         for (int m = 0; m < P.ns; ++m) {
           const uint32_t code = src[m];
-          if (code == 0xffffffffu) break;
-          const int off = code & 0x3fff, jb = (code >> 16) & 0xff;
+          const int off = code & 0x3fff, tr = (code >> 14) & 1;
           if (DO_K) {
-            if (jb != cur) {
-              if (cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
+            const int xo = off + i * (2 - tr);
+            acc.x += Qs[xo]; acc.y += Qs[xo + 1 + tr];
+            if (code & (1u << 26)) {
+              *reinterpret_cast<double2 *>(row + 2 * ((code >> 16) & 0xff)) = acc;
               acc = make_double2(0.0, 0.0);
-              cur = jb;
-            }
-            if (code & 0x4000u) {       // block stored transposed (local row > local column)
-              acc.x += Qs[off + i]; acc.y += Qs[off + 2 + i];
-            } else {
-              const double2 v = *reinterpret_cast<const double2 *>(Qs + off + 2 * i);
-              acc.x += v.x; acc.y += v.y;
             }
           }
-          if (DO_R && (code & 0x8000u)) rsum += Qs[(off / G2_KS) * G2_KS + 40 + (code >> 24) * 2 + i];
+          if (DO_R && (code & 0x8000u)) rsum += Qs[(off / G2_KS) * G2_KS + 40 + ((code >> 24) & 3) * 2 + i];
         }
-        if (DO_K && cur >= 0) *reinterpret_cast<double2 *>(row + 2 * cur) = acc;
         if (DO_R) A.R[2 * (int64_t)node + i] = rsum;
       }
     }
     __syncthreads();             // Qs and stage k & 1 are free again
+    if (P.prof && tid == 0) {
+      const long long tp4 = clock64();
+      atomicAdd(P.prof + 0, (unsigned long long)(tp1 - tp0));   // staging wait + issue
+      atomicAdd(P.prof + 1, (unsigned long long)(tp2 - tp1));   // phase 1a
+      atomicAdd(P.prof + 2, (unsigned long long)(tp3 - tp2));   // phase 1b
+      atomicAdd(P.prof + 3, (unsigned long long)(tp4 - tp3));   // phase 2
+      atomicAdd(P.prof + 4, 1ull);                               // clusters
+    }
   }
   cp_async_wait<0>();
 }
@@ -289,9 +299,10 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
 bool nls_assembly_overwrites(const nls_context *h) { return h->dim == 2 && h->opt_assembly == 1 && h->have_plan; }
 int nls_gather_nc(void) { return G2_NC; }
 
-static size_t gather_smem(int maxt, int maxe, int ns) {
+static size_t gather_smem(int maxt, int maxe, int ns, int rp) {
   const size_t bsz = (size_t)maxt * 32 + G2_NC * 8 + (size_t)maxe * 4 + G2_NC * 4 + G2_NC * 4 + (size_t)G2_NC * ns * 4;
-  return (size_t)maxe * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
+  (void)rp;   // staging the rows in shared memory for coalesced stores was measured slower
+  return (size_t)maxe * G2_KS * 8 + 44 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
 }
 
 void nls_gather_free(nls_context *h) {
@@ -316,7 +327,7 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   const int32_t *conn = h->h_conn.data();
   int maxdeg = 0;
   for (int64_t a = 0; a < h->n_owned; ++a) maxdeg = std::max<int>(maxdeg, (int)(h->h_browptr[a + 1] - h->h_browptr[a]));
-  if (plan.max_elems > G2_THREADS || (size_t)plan.max_elems * G2_KS > 0x3fff || maxdeg > 255 || plan.max_adj > 8) return NLS_OK;
+  if (plan.max_elems > G2_THREADS || (size_t)(plan.max_elems + 4) * G2_KS + 4 > 0x3fff || maxdeg > 255 || plan.max_adj > 8) return NLS_OK;
   std::vector<std::vector<int32_t>> touched((size_t)ncl);
   int maxt = 0;
   for (int64_t c = 0; c < ncl; ++c) {
@@ -329,12 +340,14 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   }
   if (maxt > 255) return NLS_OK;
   const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, NS = (plan.max_adj * nen + 3) & ~3;
-  if (gather_smem(MAXT, MAXE, NS) > (size_t)200 * 1024) return NLS_OK;
+  const int RP = 4 * maxdeg + 2;   // doubles per node in the row buffer; (2 maxdeg + 1) x 16 B = odd
+  if (gather_smem(MAXT, MAXE, NS, RP) > (size_t)110 * 1024) return NLS_OK;
   const int tnw = 4 + MAXT;
   std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NC, -1), deg((size_t)ncl * G2_NC, 0);
   std::vector<uint32_t> lconn((size_t)ncl * MAXE, 0);
   std::vector<int64_t> b0((size_t)ncl * G2_NC, 0);
-  std::vector<uint32_t> nsrc((size_t)ncl * G2_NC * NS, 0xffffffffu);
+  const uint32_t dummy = (uint32_t)(MAXE * G2_KS);   // offset of the zero slot, no flags
+  std::vector<uint32_t> nsrc((size_t)ncl * G2_NC * NS, dummy);
   std::vector<uint32_t> codes;
   for (int64_t c = 0; c < ncl; ++c) {
     const std::vector<int32_t> &t = touched[c];
@@ -374,12 +387,14 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
         static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
         const uint32_t lo_ = std::min(al, b), hi_ = std::max(al, b);
         const uint32_t off = s * G2_KS + (uint32_t)(bd[lo_] + (hi_ - lo_)) * 4;
-        nsrc[((size_t)c * G2_NC + nl) * NS + m] = off | (al > b ? 0x4000u : 0u) | (al == b ? 0x8000u : 0u) | (jb << 16) | (al << 24);
+        const bool last = (m + 1 == codes.size()) || ((codes[m + 1] >> 16) != jb);
+        nsrc[((size_t)c * G2_NC + nl) * NS + m] = off | (al > b ? 0x4000u : 0u) | (al == b ? 0x8000u : 0u) | (jb << 16) | (al << 24) |
+                                                   (last ? (1u << 26) : 0u);
       }
     }
   }
   GatherPlanDev &g = h->gplan;
-  g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.ns = NS;
+  g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.ns = NS; g.rp = RP;
 #define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&g.field, sizeof(vec[0]) * vec.size())); \
   NLS_CUDA(h, cudaMemcpyAsync(g.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
   UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(nsrc, nsrc);
@@ -394,8 +409,9 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
   a.nel = h->nel; a.n_owned = h->n_owned; a.conn = h->d_conn; a.coords = h->d_coords; a.U = h->d_U;
   a.R = h->d_R; a.vals = h->d_vals; a.browptr = h->d_browptr; a.pos = h->d_pos;
   const GatherPlanDev &g = h->gplan;
-  GatherArgs p{g.ncl, g.maxt, g.maxe, g.ns, g.tn, g.lconn, g.cn, g.b0, g.deg, g.nsrc};
-  const size_t shm = gather_smem(g.maxt, g.maxe, g.ns);
+  GatherArgs p{g.ncl, g.maxt, g.maxe, g.ns, g.rp, g.tn, g.lconn, g.cn, g.b0, g.deg, g.nsrc,
+               h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr};
+  const size_t shm = gather_smem(g.maxt, g.maxe, g.ns, g.rp);
   static size_t shm_set = 0;
   if (shm > shm_set) {
     cudaFuncSetAttribute(k_asm_q1_2d_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);

@@ -107,7 +107,7 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   dev_free(&h->d_neu_dofs); dev_free(&h->d_neu_vals);
   dev_free(&h->d_U); dev_free(&h->d_R); dev_free(&h->d_dU); dev_free(&h->d_r); dev_free(&h->d_p);
   dev_free(&h->d_Ap); dev_free(&h->d_dinv); dev_free(&h->d_b); dev_free(&h->d_tmp);
-  dev_free(&h->d_partial); dev_free(&h->d_ctl); dev_free(&h->d_scal);
+  dev_free(&h->d_partial); dev_free(&h->d_ctl); dev_free(&h->d_scal); dev_free(&h->d_prof);
   for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
   dev_free(&h->d_u_n);
   dev_free(&h->d_send_nodes); dev_free(&h->d_recv_nodes); dev_free(&h->d_sendbuf); dev_free(&h->d_recvbuf);
@@ -655,12 +655,29 @@ extern "C" int32_t nls_flush_l2(nls_handle h) {
 }
 extern "C" int64_t nls_kernel_launches(nls_handle h) { return h ? h->launches : 0; }
 
+extern "C" int32_t nls_debug_counters(nls_handle h, int64_t *out8) {
+  NLS_ENTER(h);
+  if (!out8) NLS_FAIL(h, NLS_ERR_ARG, "nls_debug_counters: null output");
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (h->d_prof) {
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    NLS_CUDA(h, cudaMemcpy(out8, h->d_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  return NLS_OK;
+}
+
 extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) {
   NLS_ENTER(h);
   if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
   if (!std::strcmp(key, "gather_ctas")) { h->opt_gather_ctas = value; return NLS_OK; }
+  if (!std::strcmp(key, "profile_phases")) {
+    if (!h->d_prof) NLS_CUDA(h, cudaMalloc((void **)&h->d_prof, 8 * sizeof(uint64_t)));
+    NLS_CUDA(h, cudaMemset(h->d_prof, 0, 8 * sizeof(uint64_t)));
+    h->opt_profile_phases = value;
+    return NLS_OK;
+  }
   if (!std::strcmp(key, "spmv_lanes")) { h->opt_spmv_lanes = value; return NLS_OK; }
   NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: unknown key");
 }

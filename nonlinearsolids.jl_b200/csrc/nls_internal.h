@@ -56,7 +56,7 @@ void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, i
 // packed, fixed-stride device copy of the plan (kernels_gather.cu)
 struct GatherPlanDev {
   int64_t ncl = 0;
-  int maxt = 0, maxe = 0, ns = 0;
+  int maxt = 0, maxe = 0, ns = 0, rp = 0;
   int32_t *tn = nullptr;
   uint32_t *lconn = nullptr;
   int32_t *cn = nullptr;
@@ -153,6 +153,8 @@ struct nls_context {
   // options
   int opt_spmv = 1;        // 0: scalar CSR SpMV; 1: block-aware traversal (dim >= 2)
   int opt_spmv_lanes = 0;  // lanes per node for the block-aware SpMV (0 = default)
+  int opt_profile_phases = 0; // debug: per-phase cycle counters of the gather kernel
+  uint64_t *d_prof = nullptr;
   int opt_gather_ctas = 0; // persistent CTAs per SM of the gather kernel (0 = default)
   int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: gather (row-owner) kernel where available
 

@@ -27,6 +27,15 @@ H.call("nls_pattern_size", C.byref(nrows), C.byref(nnz))
 abytes = 4 * mesh.nen * mesh.nel + 8 * dim * mesh.nn + 16 * nrows.value + 8 * nnz.value
 print("dim %d n %d ndof %d nnz %d  assembly %.3f ms  (%.1f GB/s algorithmic, %.2e DoF/s)" % (
     dim, n, fem.ndof, nnz.value, ms.value, abytes / ms.value / 1e6, fem.ndof / ms.value * 1e3))
+if dim == 2:
+    H.call("nls_set_option", b"profile_phases", 1)
+    for _ in range(5): H.call("nls_dev_assemble", 1, 1)
+    cnt = np.zeros(8, dtype=np.int64)
+    H.call("nls_debug_counters", cnt.ctypes.data_as(C.POINTER(C.c_int64)))
+    ncl = max(1, cnt[4])
+    print("gather phases, cycles per cluster: staging %.0f, 1a %.0f, 1b %.0f, 2 %.0f (clusters %d)" % (
+        cnt[0] / ncl, cnt[1] / ncl, cnt[2] / ncl, cnt[3] / ncl, ncl))
+    H.call("nls_set_option", b"profile_phases", 0)
 H.call("nls_dev_pcg_iterations", 20)
 H.call("nls_timer_start"); H.call("nls_dev_pcg_iterations", iters); H.call("nls_timer_stop", C.byref(ms))
 it_bytes = 12 * nnz.value + 24 * nrows.value + 128 * nrows.value
