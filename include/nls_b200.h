@@ -120,6 +120,10 @@ int32_t nls_set_dirichlet_values(nls_handle h, int64_t n, const double *vals);
 /* addboundary!(fem, Neumann(nodes, values)) (boundary.jl:32-39) */
 int32_t nls_set_neumann(nls_handle h, int64_t n, const int64_t *dofs0, const double *vals);
 int32_t nls_set_neumann_values(nls_handle h, int64_t n, const double *vals);
+/* DistributedForce(fdist) (src/gallery/distributedforce.jl:3-27): body-force density per component at the
+ * current time (the host evaluates fdist_fn(time(ctx))). Adds F_ext,a = sum_q (J f N_a) w_q, i.e. R -= F_ext
+ * (residual.jl:19-25). ncomp = dim, or 0 to remove it. */
+int32_t nls_set_body_force(nls_handle h, int32_t ncomp, const double *f);
 /* initialize_state!(material, fem) (linearelastoplasticity.jl:106-117) */
 int32_t nls_init_state(nls_handle h);
 /* save_state!(material, fem, U, ctx), called from poststep! (timesteppers/types.jl:74-78) */

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "nls_set_dirichlet_values": (C.c_int32, [_H, C.c_int64, _dp]),
     "nls_set_neumann": (C.c_int32, [_H, C.c_int64, _lp, _dp]),
     "nls_set_neumann_values": (C.c_int32, [_H, C.c_int64, _dp]),
+    "nls_set_body_force": (C.c_int32, [_H, C.c_int32, _dp]),
     "nls_init_state": (C.c_int32, [_H]),
     "nls_commit_state": (C.c_int32, [_H, _dp]),
     "nls_get_state": (C.c_int32, [_H, C.c_char_p, _dp]),

@@ -114,7 +114,10 @@ int nls_host_tab1d(int p, int nq, Tab1D *t) {
   nls_host_lagrange_nodes(p, 0, nodes);
   nls_host_lagrange_weights(p + 1, nodes, bw);
   nls_host_gauss(nq, xq, t->w);
-  for (int q = 0; q < nq; ++q) nls_host_shape_dN(p + 1, nodes, bw, xq[q], t->dN[q]);
+  for (int q = 0; q < nq; ++q) {
+    nls_host_shape_dN(p + 1, nodes, bw, xq[q], t->dN[q]);
+    nls_host_shape_N(p + 1, nodes, bw, xq[q], t->N[q]);
+  }
   return 0;
 }
 
@@ -144,6 +147,9 @@ int nls_host_tabq1(int dim, TabQ1 *t) {
         for (int d = 1; d < dim; ++d) v *= (d == D) ? D1[qd[d]][ad[d]] : N1[qd[d]][ad[d]];
         t->dN[q][a][D] = v;
       }
+      double nv = N1[qd[0]][ad[0]];
+      for (int d = 1; d < dim; ++d) nv *= N1[qd[d]][ad[d]];
+      t->N[q][a] = nv;
     }
   }
   return 0;

@@ -400,6 +400,63 @@ __global__ void k_neumann(int64_t n, const int64_t *dofs, const double *vals, do
   if (k < n && dofs[k] < nrows) atomicAdd(R + dofs[k], -vals[k]);
 }
 
+// DistributedForce (src/gallery/distributedforce.jl:7-27): F_ext,a = sum_q (J f N_a(xi_q)) w_q per element,
+// and R -= F_ext (residual.jl:19-25). 1-D: J = length(e)/2 as in the reference; Q1: J = det(dX/dxi).
+template <int M>
+__global__ void k_body_force_1d(int64_t nel, int64_t n_owned, const int32_t *conn, const double *coords, double f,
+                                const __grid_constant__ Tab1D T, double *R) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  int nd[M];
+#pragma unroll
+  for (int a = 0; a < M; ++a) nd[a] = conn[e * M + a];
+  const double J = (coords[nd[M - 1]] - coords[nd[0]]) / 2.0;
+  const double Jf = J * f;
+#pragma unroll
+  for (int a = 0; a < M; ++a) {
+    double s = 0.0;
+    for (int q = 0; q < T.nq; ++q) { const double v = (Jf * T.N[q][a]) * T.w[q]; s = (q == 0) ? v : s + v; }
+    if (nd[a] < n_owned) atomicAdd(R + nd[a], -s);
+  }
+}
+template <int DIM>
+__global__ void k_body_force_q1(int64_t nel, int64_t n_owned, const int32_t *conn, const double *coords, double f0, double f1,
+                                double f2, const __grid_constant__ TabQ1 T, double *R) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  constexpr int NEN = 1 << DIM;
+  int nd[NEN];
+  double X[NEN][DIM], s[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    nd[a] = conn[e * NEN + a];
+    s[a] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) X[a][d] = coords[(int64_t)nd[a] * DIM + d];
+  }
+  for (int q = 0; q < NEN; ++q) {
+    double J[DIM * DIM], Ji[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; ++i) J[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NEN; ++a)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int D = 0; D < DIM; ++D) J[d * DIM + D] += X[a][d] * T.dN[q][a][D];
+    const double wd = T.w[q] * (DIM == 2 ? inv2(J, Ji) : inv3(J, Ji));
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) s[a] += wd * T.N[q][a];
+  }
+  const double f[3] = {f0, f1, f2};
+#pragma unroll
+  for (int a = 0; a < NEN; ++a)
+    if (nd[a] < n_owned)
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        if (f[d] != 0.0) atomicAdd(R + (int64_t)nd[a] * DIM + d, -s[a] * f[d]);
+}
+
 // position of node b in the (ascending) block row of node a, for every element node pair
 __global__ void k_build_pos(int64_t nel, int nen, int64_t n_owned, const int32_t *conn,
                             const int64_t *browptr, const int32_t *bcol, uint16_t *pos) {
@@ -523,6 +580,25 @@ int nls_launch_apply_dirichlet(nls_context *h, double *U) {
 int nls_launch_neumann(nls_context *h, double *R) {
   if (h->nneu == 0) return NLS_OK;
   k_neumann<<<nblk(h->nneu, 256), 256, 0, h->stream>>>(h->nneu, h->d_neu_dofs, h->d_neu_vals, R, h->nrows);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+int nls_launch_body_force(nls_context *h, double *R) {
+  if (!h->have_body || h->nel == 0) return NLS_OK;
+  const unsigned g = nblk(h->nel, 128);
+  if (h->dim == 1) {
+    switch (h->nen) {
+#define BF(M) case M: k_body_force_1d<M><<<g, 128, 0, h->stream>>>(h->nel, h->n_owned, h->d_conn, h->d_coords, h->body[0], h->tab1, R); break;
+      BF(2) BF(3) BF(4) BF(5) BF(6) BF(7) BF(8)
+#undef BF
+      default: NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D elements support p = 1..7");
+    }
+  } else if (h->dim == 2) {
+    k_body_force_q1<2><<<g, 128, 0, h->stream>>>(h->nel, h->n_owned, h->d_conn, h->d_coords, h->body[0], h->body[1], 0.0, h->tabq, R);
+  } else {
+    k_body_force_q1<3><<<g, 128, 0, h->stream>>>(h->nel, h->n_owned, h->d_conn, h->d_coords, h->body[0], h->body[1], h->body[2], h->tabq, R);
+  }
   NLS_KCHECK(h);
   return NLS_OK;
 }

@@ -149,7 +149,7 @@ extern "C" int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64
   NLS_CUDA(h, cudaMemsetAsync(h->d_dU, 0, nd * sizeof(double), h->stream));
   NLS_CUDA(h, cudaMemsetAsync(h->d_p, 0, nd * sizeof(double), h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->ndir = h->ndir_user = 0; h->nneu = 0;
+  h->ndir = h->ndir_user = 0; h->nneu = 0; h->have_body = false;
   h->dir_user_dofs.clear(); h->dir_slot.clear();
   for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
   dev_free(&h->d_u_n);
@@ -274,6 +274,16 @@ extern "C" int32_t nls_set_neumann_values(nls_handle h, int64_t n, const double 
   return NLS_OK;
 }
 
+extern "C" int32_t nls_set_body_force(nls_handle h, int32_t ncomp, const double *f) {
+  NLS_ENTER(h);
+  if (!h->have_mesh) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_body_force: call nls_set_mesh first");
+  if (ncomp != 0 && (ncomp != h->dim || !f)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_body_force: need one value per spatial dimension");
+  h->have_body = false;
+  for (int d = 0; d < 3; ++d) h->body[d] = 0.0;
+  for (int d = 0; d < ncomp; ++d) { h->body[d] = f[d]; h->have_body = h->have_body || f[d] != 0.0; }
+  return NLS_OK;
+}
+
 extern "C" int32_t nls_init_state(nls_handle h) {
   NLS_ENTER(h);
   if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D) return NLS_OK;
@@ -392,6 +402,7 @@ static int assemble(nls_context *h, bool want_r, bool want_k) {
     if (want_k) NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));  // jacobian.jl:13
   }
   NLS_TRY(nls_launch_assembly(h, want_r, want_k));
+  if (want_r) NLS_TRY(nls_launch_body_force(h, h->d_R));       // residual.jl:19-23 (DistributedForce)
   if (want_r) NLS_TRY(nls_launch_neumann(h, h->d_R));          // residual.jl:24-25
   return NLS_OK;
 }

@@ -14,11 +14,13 @@ struct Tab1D {            // dN_i/dxi at each Gauss point, shapefunctions.jl:64-
   int m, nq;
   double w[NLS_MAX_NQ];
   double dN[NLS_MAX_NQ][NLS_MAX_NEN1D];
+  double N[NLS_MAX_NQ][NLS_MAX_NEN1D];   // N_i at each Gauss point (shapefunctions.jl:50-61), for body forces
 };
 struct TabQ1 {            // tensor-product Q1: [qp][node][ref dir], x fastest
   int dim, nen, nqp;
   double w[8];
   double dN[8][8][3];
+  double N[8][8];           // [qp][node]
 };
 struct MatParams {
   int kind;
@@ -110,6 +112,8 @@ struct nls_context {
   int64_t *d_dir_dofs = nullptr;
   double *d_dir_vals = nullptr;
   uint8_t *d_con = nullptr;             // constrained mask, ndof_local
+  double body[3] = {0.0, 0.0, 0.0};     // DistributedForce density per component at the current time
+  bool have_body = false;
   int64_t nneu = 0;
   int64_t *d_neu_dofs = nullptr;
   double *d_neu_vals = nullptr;
@@ -186,6 +190,7 @@ void nls_gather_free(nls_context *h);
 int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k);
 int nls_launch_apply_dirichlet(nls_context *h, double *U);
 int nls_launch_neumann(nls_context *h, double *R);
+int nls_launch_body_force(nls_context *h, double *R);
 int nls_launch_build_pos(nls_context *h);
 int nls_launch_expand_pattern(nls_context *h);
 int nls_launch_commit_state(nls_context *h, const double *dU);

@@ -24,19 +24,47 @@ class CSRMatrix:
         return A
 
 
+class DistributedForce:
+    """DistributedForce(fdist_fn) (distributedforce.jl:3-27): body-force density, a number (or a vector
+    with one entry per spatial dimension) or a function of time `fdist_fn(time(ctx))`. The element
+    integrals run on the device; the host only evaluates the function of time."""
+
+    def __init__(self, fdist_fn):
+        self.fdist_fn = fdist_fn
+
+    def density(self, ctx, dim):
+        f = self.fdist_fn(ctx.time()) if callable(self.fdist_fn) else self.fdist_fn
+        f = np.atleast_1d(np.asarray(f, dtype=np.float64))
+        if len(f) != dim:
+            raise ValueError("DistributedForce needs one density value per spatial dimension")
+        return f
+
+
+def _sync_external_forces(H, fem, forces, ctx):
+    total = np.zeros(fem.mesh.dim)
+    for f in forces:
+        if not isinstance(f, DistributedForce):
+            raise NotImplementedError("only DistributedForce external forces run on the device path")
+        total += f.density(ctx, fem.mesh.dim)
+    H.call("nls_set_body_force", len(total) if len(forces) else 0, dptr(total))
+
+
 class Residual:
     """Residual(material, externalforces=[]) (residual.jl:5-9). R = F_int(U) - F_ext."""
 
     def __init__(self, material, externalforces=()):
-        if len(externalforces):
-            raise NotImplementedError("external force functors are not on the device path yet (SURVEY 8f-1)")
+        for f in externalforces:
+            if not isinstance(f, DistributedForce):
+                raise NotImplementedError("only DistributedForce external forces run on the device path")
         self.material = material
         self.externalforces = list(externalforces)
 
     def __call__(self, fem, U, R, ctx=None):
         if not (isinstance(U, np.ndarray) and U.dtype == np.float64 and U.flags.c_contiguous):
             raise TypeError("U must be a contiguous float64 array (it is updated in place)")
-        fem.handle(self.material).call("nls_residual", dptr(U), dptr(R))
+        H = fem.handle(self.material)
+        _sync_external_forces(H, fem, self.externalforces, ctx)
+        H.call("nls_residual", dptr(U), dptr(R))
 
 
 class Jacobian:

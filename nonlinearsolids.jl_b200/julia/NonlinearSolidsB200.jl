@@ -101,6 +101,19 @@ function sync_boundaries!(m::B200Model)
     check(m.h, ccall((:nls_set_neumann, libnls), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}), m.h, length(nn), nn, nv))
 end
 
+"""DistributedForce functors (gallery/distributedforce.jl:3-27): the host evaluates fdist_fn(time(ctx)),
+the element integrals run on the device (nls_set_body_force)."""
+function sync_external_forces!(m::B200Model, forces, ctx)
+    total = zeros(m.dim)
+    for f in forces
+        f isa DistributedForce || error("only DistributedForce external forces run on the device path")
+        fd = f.fdist_fn isa Function ? f.fdist_fn(time(ctx)) : f.fdist_fn
+        total .+= fd
+    end
+    check(m.h, ccall((:nls_set_body_force, libnls), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}),
+                     m.h, isempty(forces) ? 0 : m.dim, total))
+end
+
 # ---- dispatch point (2): material-level global loops on a device model -------------------------
 """compute_internalforce(material, ::B200Model, U, Fint, ctx; mode): F_int via the element kernel.
 `mode=:add` adds to Fint like the reference (defaults.jl:29-46)."""
@@ -180,8 +193,8 @@ is_converged(s::B200NewtonSolver; allow_maxits=s.allow_maxits) = is_converged(s.
 function solve!(s::B200NewtonSolver, U0::AbstractVector=zeros(numdof(s.fem)))
     s.residual_fn! isa Residual && s.jacobian_fn! isa Jacobian ||
         error("B200NewtonSolver needs the gallery Residual/Jacobian functors (their material selects the device law)")
-    isempty(s.residual_fn!.externalforces) || error("external force functors are not on the device path yet")
     sync_material!(s.dev, s.residual_fn!.material)
+    sync_external_forces!(s.dev, s.residual_fn!.externalforces, s.ctx)
     sync_boundaries!(s.dev)                     # TimeDependent values were updated by step!(ts, Δt)
     opts = NewtonOpts(s.type == :modified, s.atol, s.rtol, s.dtol, s.maxits, s.lin_rtol, s.lin_maxits)
     res = NewtonResult()

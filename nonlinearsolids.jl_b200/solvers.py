@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import dptr
-from .gallery import Jacobian, Residual
+from .gallery import Jacobian, Residual, _sync_external_forces
 from .materials import save_state
 
 
@@ -101,6 +101,7 @@ class NewtonSolver:
         if U0.shape != (fem.ndof,):
             raise ValueError("U0 has the wrong length")
         H = fem.handle(self.residual_fn.material)
+        _sync_external_forces(H, fem, self.residual_fn.externalforces, self.ctx)   # fdist_fn(time(ctx))
         opts = _lib.NewtonOpts(int(self.type == "modified"), self.atol, self.rtol, self.dtol, self.maxits,
                                self.lin_rtol, self.lin_maxits)
         res = _lib.NewtonResult()

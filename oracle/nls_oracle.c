@@ -454,6 +454,45 @@ static inline void orc_sink_add(const orc_sink *s, int64_t gi, int64_t gj, doubl
   if (s->atomic) orc_atomic_add(p, v); else *p += v;
 }
 
+/* DistributedForce: distributedforce.jl:7-27. 1-D: f_e = integrate(Q, xi -> J * fdist * N(P, xi)), J = length(e)/2;
+ * Q1 (builder-defined): f_{a,i} = sum_q w_q det(dX/dxi) N_a f_i. Fext[nodes] += f_e in element order. */
+static void orc_body_force(const orc_model *mo, double *Fext) {
+  int dim = mo->dim, nen = mo->nen;
+  if (dim == 1) {
+    double nodes[ORC_MAXN], w[ORC_MAXN], xq[ORC_MAXQ], wq[ORC_MAXQ], N[ORC_MAXQ][ORC_MAXN];
+    orc_lagrange_nodes(mo->p, 0, nodes); orc_lagrange_weights(nen, nodes, w); orc_gauss(mo->nq, xq, wq);
+    for (int q = 0; q < mo->nq; ++q) orc_shape_N(nen, nodes, w, xq[q], N[q]);
+    for (int64_t e = 0; e < mo->nel; ++e) {
+      double J = orc_el_dxdxi(mo, e);
+      for (int a = 0; a < nen; ++a) {
+        double s = 0.0;
+        for (int q = 0; q < mo->nq; ++q) { double v = (J * mo->body[0] * N[q][a]) * wq[q]; s = (q == 0) ? v : s + v; }
+        Fext[mo->conn[e * nen + a]] += s;
+      }
+    }
+    return;
+  }
+  orc_tabq1 t; orc_tabq1_init(mo, &t);
+  double nodes[2], bw[2], xq[ORC_MAXQ], wq[ORC_MAXQ], N1[2][2];
+  orc_lagrange_nodes(1, 0, nodes); orc_lagrange_weights(2, nodes, bw); orc_gauss(2, xq, wq);
+  for (int q = 0; q < 2; ++q) orc_shape_N(2, nodes, bw, xq[q], N1[q]);
+  for (int64_t e = 0; e < mo->nel; ++e) {
+    const int32_t *c = mo->conn + e * nen;
+    for (int q = 0; q < t.nqp; ++q) {
+      double J[9] = {0}, Ji[9];
+      for (int a = 0; a < nen; ++a)
+        for (int d = 0; d < dim; ++d)
+          for (int D = 0; D < dim; ++D) J[d * dim + D] += mo->coords[(int64_t)c[a] * dim + d] * t.dN[q][a][D];
+      double wd = t.w[q] * orc_inv(dim, J, Ji);
+      for (int a = 0; a < nen; ++a) {
+        double Na = 1.0;
+        for (int d = 0; d < dim; ++d) Na = (d == 0) ? N1[(q >> d) & 1][(a >> d) & 1] : Na * N1[(q >> d) & 1][(a >> d) & 1];
+        for (int d = 0; d < dim; ++d) Fext[(int64_t)c[a] * dim + d] += wd * Na * mo->body[d];
+      }
+    }
+  }
+}
+
 typedef struct { orc_model *mo; double *U, *R; const orc_sink *K; const orc_tab1d *t1; const orc_tabq1 *tq; int nth; } orc_asm_ctx;
 
 static void orc_assemble_range(void *vc, int64_t lo, int64_t hi, int tid) {
@@ -496,6 +535,7 @@ static void orc_assemble(orc_model *mo, double *U, double *R, const orc_sink *K)
   orc_parallel_for(nth, mo->nel, orc_assemble_range, &ctx);
   if (R) {                                         /* residual.jl:15,24-25 */
     double *Fext = (double *)calloc((size_t)ndof, sizeof(double));
+    if (mo->has_body) orc_body_force(mo, Fext);     /* residual.jl:19-23 */
     for (int64_t k = 0; k < mo->nneu; ++k) Fext[mo->neu_dofs[k]] += mo->neu_vals[k];
     for (int64_t i = 0; i < ndof; ++i) R[i] -= Fext[i];
     free(Fext);

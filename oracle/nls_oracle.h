@@ -62,6 +62,8 @@ typedef struct {
   double *sig_n, *alp_n, *kap_n, *gam_n;
   double *u_n;          /* [nel][nen] */
   int32_t nthreads;     /* worker threads (pthreads) for the scalable (CSR) paths; 1 = serial & deterministic */
+  int32_t has_body;     /* DistributedForce (gallery/distributedforce.jl): density per component */
+  double body[3];
 } orc_model;
 
 typedef struct {

@@ -32,7 +32,7 @@ class _Model(C.Structure):
                 ("nneu", C.c_int64), ("neu_dofs", _lp), ("neu_vals", _dp),
                 ("sig", _dp), ("alp", _dp), ("kap", _dp), ("gam", _dp), ("dsig", _dp),
                 ("sig_n", _dp), ("alp_n", _dp), ("kap_n", _dp), ("gam_n", _dp), ("u_n", _dp),
-                ("nthreads", C.c_int32)]
+                ("nthreads", C.c_int32), ("has_body", C.c_int32), ("body", C.c_double * 3)]
 
 
 class _Opts(C.Structure):
@@ -148,6 +148,13 @@ class OracleModel:
                 setattr(m, k, _d(v))
             lib().orc_init_state(C.byref(m))
         self._pattern = None
+
+    def set_body_force(self, f):
+        """DistributedForce density per component (gallery/distributedforce.jl); None removes it."""
+        f = [] if f is None else list(np.atleast_1d(f))
+        self.m.has_body = int(any(v != 0.0 for v in f))
+        for i in range(3):
+            self.m.body[i] = f[i] if i < len(f) else 0.0
 
     def set_threads(self, n):
         self.m.nthreads = n

@@ -298,3 +298,39 @@ def test_gather_vs_atomic_assembly_2d(nls, orc, n, kind):
     _, Ro = om.residual(U); Ko = om.jacobian_csr(U)
     for opt in (0, 1):
         assert rel_err(out[opt][0], Ro) <= RTOL and rel_err(out[opt][1], Ko) <= RTOL, opt
+
+
+def test_distributed_force(nls, orc):
+    """DistributedForce on the device (distributedforce.jl:7-27, residual.jl:19-25): 1-D with a function of
+    time evaluated through the timestepper context, and constant 2-D / 3-D body loads."""
+    E, A = 3.0, 0.5
+    mat = nls.LinearElasticity1D(E=E)
+    mesh = nls.bar_mesh(9, 3)
+    fem = nls.FEMModel(mesh, 4, 3, data={"A": A})
+    fem.addboundary(nls.Dirichlet([0], [0.0]))
+    s = _solver(nls, fem, mat, rtol=1e-11, atol=1e-14, maxits=5)
+    nls.set_residual_fn(s, nls.Residual(mat, [nls.DistributedForce(lambda t: 2.0 * t)]))
+    ts = nls.PseudoTimeStepper(s, dt=0.25, maxtime=0.5)
+    nls.set_ctx(s, ts)
+    ts.solve()
+    om = orc.OracleModel(1, mesh.conn, mesh.coords, p=3, nq=4, mat_kind=orc.MAT_LINEAR, mat=(E,), area=A)
+    om.set_dirichlet([0], [0.0])
+    U = np.zeros(fem.ndof)
+    for k, t in [(1, 0.25), (2, 0.5)]:
+        om.set_body_force([2.0 * t])
+        r = om.newton(U0=U, rtol=1e-11, atol=1e-14, maxits=5)
+        U = r["U"]
+        assert rel_err(ts.U[k], U) <= UTOL and ts.num_its[k, 0] == r["iterations"]
+    for dim, n, body in [(2, 11, [0.3, -0.7]), (3, 6, [0.1, 0.2, -0.5])]:
+        mat2 = nls.NeoHookean(E=1.0, nu=0.3)
+        fem2, om2 = grid_problem(nls, orc, n, dim, mat2, compress=-0.1 / (n - 1))
+        X = distorted(fem2.mesh); fem2.mesh.coords[:] = X; om2.coords[:] = X
+        om2.set_body_force(body)
+        U = nls.smooth_field(X, amp=0.1 / (n - 1))
+        R = np.zeros(fem2.ndof)
+        nls.Residual(mat2, [nls.DistributedForce(body)])(fem2, U.copy(), R)
+        assert rel_err(R, om2.residual(U)[1]) <= RTOL
+        R0 = np.zeros(fem2.ndof)
+        nls.Residual(mat2)(fem2, U.copy(), R0)                    # removing the force restores the plain residual
+        om2.set_body_force(None)
+        assert rel_err(R0, om2.residual(U)[1]) <= RTOL and np.abs(R0 - R).max() > 1e-6

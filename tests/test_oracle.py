@@ -360,3 +360,27 @@ def test_threaded_oracle_matches_serial(orc, nls):
     om.set_threads(1)
     rc1, x1, it1, _ = om.pcg(K1, b)
     assert rc1 == rc4 == 0 and abs(it1 - it4) <= 1 and rel_err(x4, x1) <= 1e-9
+
+
+def test_distributed_force_oracle(orc, nls):
+    """DistributedForce (gallery/distributedforce.jl:7-27): total load, and the exact solution of a
+    uniformly loaded linear bar u(x) = f/(E A) (L x - x^2/2), nodally exact for p >= 2."""
+    E, A, f, L = 3.0, 0.5, 1.25, 1.0
+    for p, q in [(2, 3), (3, 4)]:
+        mesh = nls.bar_mesh(6, p)
+        om = orc.OracleModel(1, mesh.conn, mesh.coords, p=p, nq=q, mat_kind=orc.MAT_LINEAR, mat=(E,), area=A)
+        om.set_dirichlet([0], [0.0])
+        om.set_body_force([f])
+        _, R = om.residual(np.zeros(mesh.nn))
+        assert abs(-R.sum() - f * L) <= 1e-14
+        # element nodes sit at the Chebyshev-2 points of each element (geometry is affine between end nodes)
+        r = om.newton(rtol=1e-12, atol=1e-14, maxits=5)
+        assert r["reason"].startswith("CONVERGED") and r["iterations"] == 1
+        ends = mesh.conn[:, [0, -1]].ravel()
+        x = mesh.coords.ravel()[ends]
+        assert np.allclose(r["U"][ends], f / (E * A) * (L * x - x ** 2 / 2), rtol=1e-12, atol=1e-15)
+    m2 = nls.grid_mesh(5, 3)
+    om = orc.OracleModel(3, m2.conn, distorted(m2), mat_kind=orc.MAT_NEOHOOKEAN, mat=(1.0, 1.0))
+    om.set_body_force([0.5, -2.0, 0.25])
+    _, R = om.residual(np.zeros(m2.nn * 3))
+    assert np.allclose(-R.reshape(-1, 3).sum(axis=0), [0.5, -2.0, 0.25], rtol=1e-13)   # unit cube volume
