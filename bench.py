@@ -122,7 +122,21 @@ def build_local_model(nls, nranks, rank, device, uid=None):
     return fem, mat, mesh, n_owned
 
 
+def _quiet_stdout():
+    """Route fd 1 to stderr while the benchmark runs (NCCL prints its version banner to stdout) and
+    return a function that writes the single JSON result line to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real, (json.dumps(obj) + "\n").encode())
+    return emit
+
+
 def run_ours(args):
+    emit = _quiet_stdout()
     import __graft_entry__ as g
     nls = g.build()
     rank = int(os.environ.get("RANK", "0"))
@@ -272,7 +286,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         out["cpu_baseline"] = cpu_baseline(nls, sample_rows=args.cpu_rows)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
