@@ -4,37 +4,41 @@
 // (compute_dinternalforce, src/materials/defaults.jl:77-81 + assemble!, src/fem/element.jl:70) --
 // so results are bit-reproducible run to run.
 //
-// Persistent CTAs walk node clusters (host plan: 8x8-node Morton tiles, nls_host_cluster_plan).
+// Persistent CTAs walk node clusters (host plan: 16x8-node Morton tiles, nls_host_cluster_plan).
 // Everything a cluster needs is staged into shared memory with cp.async (LDGSTS) while the
 // previous cluster is being computed, so no global-load latency sits on the critical path:
 //   group A(k+2): the list of nodes touched by cluster k+2           (contiguous copy)
 //   group B(k+1): coordinates + displacements of those nodes (16-byte gathers through the list),
-//                 local connectivity, row owners, CSR row bases, gather source lists
-//   compute(k)  : phase 1  one thread per element: K_e (symmetric half accumulated, 8x8 stored)
-//                          and f_e over the 4 quadrature points -> shared memory
-//                 phase 2  one thread per (owned node, component): walks the node's source list
-//                          (element slot, local row, local column block -> CSR column block,
-//                          sorted by column block then element) and writes the row once.
-// History and counters behind this design: DESIGN.md section 5, profiles/r1a..r1e.
+//                 local connectivity, row owners, CSR row bases, per-block source lists
+//   compute(k)  : phase 1  one thread per element: the symmetric half of K_e and f_e over the 4
+//                          quadrature points (rolled loop, 48 accumulators) -> shared memory
+//                 phase 2  one task per CSR block of the cluster's rows: sums the element blocks
+//                          that land in it (ascending element order, branch-free padded list)
+//                          and writes its two 16-byte row segments; adjacent tasks write adjacent
+//                          segments, so the stores coalesce. The diagonal block's task also sums R.
+// History and counters behind this design: DESIGN.md section 5, profiles/r1a..r1h.
 #include <algorithm>
 #include <cstring>
 #include "asm_common.cuh"
 
-#define G2_NC 64          // owned nodes per cluster
-#define G2_THREADS 128
-#define G2_QS 24          // doubles per (element, quadrature point) record
-#define G2_KS (4 * G2_QS + 2)   // doubles per element in shared memory: 4 records, later overwritten by the
-                                // 10 symmetric 2x2 blocks + fe[8]; 49 x 16 B (odd stride -> conflict-free across elements)
+#define G2_NC 128         // owned nodes per cluster (16 x 8 tile -> 17 x 9 = 153 elements, 19.5 % evaluated twice)
+#define G2_THREADS 160
+#define G2_KS 50          // doubles per element in shared memory: 10 symmetric 2x2 blocks (40) + f_e (8) + 2 pad;
+                          // 25 x 16 B (odd) -> the reduce-scatter's STS.128 are conflict-free
+#define G2_MAXSRC 8       // most elements around one node the packed block lists can hold
 
 struct GatherArgs {
   int64_t ncl;
-  int maxt, maxe, ns, rp; // padded strides: touched nodes, elements, sources per node, row-buffer doubles per node
-  const int32_t *tn;      // [ncl][4 + maxt]: {nt, ne, 0, 0}, node ids
+  int maxt, maxe, maxb, nsw;  // padded strides: touched nodes, elements, CSR blocks; source words per block (2 or 4)
+  const int32_t *tn;      // [ncl][4 + maxt]: {nt, ne, nb, 0}, node ids
   const uint32_t *lconn;  // [ncl][maxe]: 4 local node indices (bytes) into the touched-node list
   const int32_t *cn;      // [ncl][G2_NC] owned node ids (-1 = none)
   const int64_t *b0;      // [ncl][G2_NC] block-row start of the node
   const int32_t *deg;     // [ncl][G2_NC] block-row length
-  const uint32_t *nsrc;   // [ncl][G2_NC][ns]: Ks offset (14 bits) | lower << 14 | diag << 15 | jb << 16, ~0 = end
+  const uint32_t *bsrc;   // [ncl][1 + nsw][maxb]: word 0 = nl | jb << 8; then 16-bit source codes, two per word:
+                          //   offset of the 2x2 block in Ks (15 bits) | transposed << 15; unused sources point at the
+                          //   zero record Ks[maxe]
+  const uint16_t *rsrc;   // [ncl][G2_NC][G2_MAXSRC]: offsets in Ks of the node's f_e pairs, ascending element; unused -> zero record
   unsigned long long *prof; // optional per-phase cycle counters (nls_set_option "profile_phases"), else NULL
 };
 
@@ -46,114 +50,69 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// phase 1a: one quadrature point. Record (24 doubles): {G_a[2], g_a[2]} x 4 nodes, c1, c2, c3, wd*P[4], pad.
+// One quadrature point of one quad: geometry chain (J, J^-1, F, F^-1, log), then this point's share of the
+// symmetric half of K_e and of f_e is added to the accumulators:
+//   Kb: blocks (a,b), a <= b, in the order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3), each [i][k] row-major.
 template <bool DO_R, bool DO_K>
-__device__ __forceinline__ void q1_2d_qp_record(const double (&X)[4][2], const double (&u)[4][2], const double *__restrict__ Tq,
-                                                const double w, const double mu, const double lam, double2 *__restrict__ rec) {
-  double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2];
+// The nodal coordinates / displacements are re-read from the staged copy in shared memory at every point
+// (8 LDS.128) instead of being held across the loop: 32 registers the accumulators need.
+__device__ __forceinline__ void q1_2d_qp_accumulate(const double2 *__restrict__ xu, const unsigned lc, const double *__restrict__ Tq,
+                                                    const double w, const double mu, const double lam,
+                                                    double (&Kb)[10][4], double2 *__restrict__ ferec, const bool first) {
+  double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2], g[4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
+    const double2 x = xu[2 * ((lc >> (8 * a)) & 0xff)];
     const double d0 = Tq[a * 2], d1 = Tq[a * 2 + 1];
     G[a][0] = d0; G[a][1] = d1;
-    J[0] = fma(X[a][0], d0, J[0]); J[1] = fma(X[a][0], d1, J[1]);
-    J[2] = fma(X[a][1], d0, J[2]); J[3] = fma(X[a][1], d1, J[3]);
+    J[0] = fma(x.x, d0, J[0]); J[1] = fma(x.x, d1, J[1]);
+    J[2] = fma(x.y, d0, J[2]); J[3] = fma(x.y, d1, J[3]);
   }
   const double detJ = inv2(J, Ji);
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
+    const double2 uu = xu[2 * ((lc >> (8 * a)) & 0xff) + 1];
     const double d0 = G[a][0], d1 = G[a][1];
     G[a][0] = fma(d0, Ji[0], d1 * Ji[2]);
     G[a][1] = fma(d0, Ji[1], d1 * Ji[3]);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { F[i * 2] = fma(u[a][i], G[a][0], F[i * 2]); F[i * 2 + 1] = fma(u[a][i], G[a][1], F[i * 2 + 1]); }
+    F[0] = fma(uu.x, G[a][0], F[0]); F[1] = fma(uu.x, G[a][1], F[1]);
+    F[2] = fma(uu.y, G[a][0], F[2]); F[3] = fma(uu.y, G[a][1], F[3]);
   }
   const double detF = inv2(F, Fi);
   const double lnJ = log(detF);
   const double wd = w * detJ;
-  const double wmu = wd * mu, wcl = wd * lam * lnJ;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    rec[2 * a] = make_double2(G[a][0], G[a][1]);
-    rec[2 * a + 1] = make_double2(fma(G[a][0], Fi[0], G[a][1] * Fi[2]), fma(G[a][0], Fi[1], G[a][1] * Fi[3]));
-  }
-  rec[8] = make_double2(wmu, wd * lam);
-  rec[9] = make_double2(wmu - wcl, fma(wmu, F[0] - Fi[0], wcl * Fi[0]));                        // c3, P00
-  rec[10] = make_double2(fma(wmu, F[1] - Fi[2], wcl * Fi[2]), fma(wmu, F[2] - Fi[1], wcl * Fi[1]));   // P01, P10
-  rec[11] = make_double2(fma(wmu, F[3] - Fi[3], wcl * Fi[3]), 0.0);                             // P11
-}
-
-// phase 1b: K_e (symmetric half) and f_e of one element from its 4 records; result overwrites the
-// start of the element's own record area (thread-private, so no synchronisation is needed):
-// blocks (a,b), a <= b, in the order (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3), each [i][k]
-// row-major; then fe[8].
-template <bool DO_R, bool DO_K>
-__device__ __forceinline__ void q1_2d_accumulate_sym(double *__restrict__ el) {
-  double fe[8], Kd[4][4], Ko[6][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) fe[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Kd[i][j] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Ko[i][j] = 0.0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const double2 *rec = reinterpret_cast<const double2 *>(el + q * G2_QS);
-    double2 G[4], g[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { G[a] = rec[2 * a]; g[a] = rec[2 * a + 1]; }
-    const double2 c12 = rec[8], c3p = rec[9];
-    if (DO_R) {
-      const double2 p1 = rec[10], p2 = rec[11];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        fe[a * 2] = fma(c3p.y, G[a].x, fma(p1.x, G[a].y, fe[a * 2]));
-        fe[a * 2 + 1] = fma(p1.y, G[a].x, fma(p2.x, G[a].y, fe[a * 2 + 1]));
-      }
-    }
-    if (DO_K) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double c1Gx = c12.x * G[a].x, c1Gy = c12.x * G[a].y;
-        const double c2g0 = c12.y * g[a].x, c2g1 = c12.y * g[a].y, c3g0 = c3p.x * g[a].x, c3g1 = c3p.x * g[a].y;
-        const double d0 = c2g0 + c3g0, d1 = c2g1 + c3g1;
-        Kd[a][0] = fma(d0, g[a].x, fma(c1Gx, G[a].x, fma(c1Gy, G[a].y, Kd[a][0])));
-        Kd[a][1] = fma(c2g0, g[a].y, fma(c3g1, g[a].x, Kd[a][1]));
-        Kd[a][2] = fma(c2g1, g[a].x, fma(c3g0, g[a].y, Kd[a][2]));
-        Kd[a][3] = fma(d1, g[a].y, fma(c1Gx, G[a].x, fma(c1Gy, G[a].y, Kd[a][3])));
-#pragma unroll
-        for (int b = a + 1; b < 4; ++b) {
-          const int ob = (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5
-          Ko[ob][0] = fma(d0, g[b].x, fma(c1Gx, G[b].x, fma(c1Gy, G[b].y, Ko[ob][0])));
-          Ko[ob][1] = fma(c2g0, g[b].y, fma(c3g1, g[b].x, Ko[ob][1]));
-          Ko[ob][2] = fma(c2g1, g[b].x, fma(c3g0, g[b].y, Ko[ob][2]));
-          Ko[ob][3] = fma(d1, g[b].y, fma(c1Gx, G[b].x, fma(c1Gy, G[b].y, Ko[ob][3])));
-        }
-      }
-    }
-  }
-  double2 *d2 = reinterpret_cast<double2 *>(el);
-  if (DO_K) {
+  const double c1 = wd * mu, c2 = wd * lam, wcl = c2 * lnJ, c3 = c1 - wcl;
+  if (DO_R) {
+    const double P00 = fma(c1, F[0] - Fi[0], wcl * Fi[0]), P01 = fma(c1, F[1] - Fi[2], wcl * Fi[2]);
+    const double P10 = fma(c1, F[2] - Fi[1], wcl * Fi[1]), P11 = fma(c1, F[3] - Fi[3], wcl * Fi[3]);
+    // f_e is accumulated in the element's own shared-memory record (thread-private, no synchronisation):
+    // 16 registers fewer across the loop than keeping it beside the 40 K accumulators
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      const int bd = (a == 0) ? 0 : (a == 1 ? 4 : (a == 2 ? 7 : 9));
-      d2[bd * 2] = make_double2(Kd[a][0], Kd[a][1]);
-      d2[bd * 2 + 1] = make_double2(Kd[a][2], Kd[a][3]);
-#pragma unroll
-      for (int b = a + 1; b < 4; ++b) {
-        const int ob = (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);
-        const int bo = bd + (b - a);
-        d2[bo * 2] = make_double2(Ko[ob][0], Ko[ob][1]);
-        d2[bo * 2 + 1] = make_double2(Ko[ob][2], Ko[ob][3]);
-      }
+      double2 o = ferec[a];
+      if (first) o = make_double2(0.0, 0.0);
+      o.x = fma(P00, G[a][0], fma(P01, G[a][1], o.x));
+      o.y = fma(P10, G[a][0], fma(P11, G[a][1], o.y));
+      ferec[a] = o;
     }
   }
-  if (DO_R) {
+  if (DO_K) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) d2[20 + a] = make_double2(fe[a * 2], fe[a * 2 + 1]);
+    for (int a = 0; a < 4; ++a) { g[a][0] = fma(G[a][0], Fi[0], G[a][1] * Fi[2]); g[a][1] = fma(G[a][0], Fi[1], G[a][1] * Fi[3]); }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double c1Gx = c1 * G[a][0], c1Gy = c1 * G[a][1];
+      const double c2g0 = c2 * g[a][0], c2g1 = c2 * g[a][1], c3g0 = c3 * g[a][0], c3g1 = c3 * g[a][1];
+      const double d0 = c2g0 + c3g0, d1 = c2g1 + c3g1;
+#pragma unroll
+      for (int b = a; b < 4; ++b) {
+        const int s = ((a == 0) ? 0 : (a == 1 ? 4 : (a == 2 ? 7 : 9))) + (b - a);
+        Kb[s][0] = fma(d0, g[b][0], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Kb[s][0])));
+        Kb[s][1] = fma(c2g0, g[b][1], fma(c3g1, g[b][0], Kb[s][1]));
+        Kb[s][2] = fma(c2g1, g[b][0], fma(c3g0, g[b][1], Kb[s][2]));
+        Kb[s][3] = fma(d1, g[b][1], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Kb[s][3])));
+      }
+    }
   }
 }
 
@@ -164,16 +123,17 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // ---- shared-memory carve-up (all sub-buffers 16-byte aligned) ----
   const int tn_words = 4 + P.maxt;
-  double *Qs = reinterpret_cast<double *>(smem_raw);                                  // [maxe][G2_KS]
-  double *Tsm = Qs + (size_t)P.maxe * G2_KS + 4;                                      // 4 zero doubles (dummy source), then 40 doubles
+  double *Ks = reinterpret_cast<double *>(smem_raw);                                  // [maxe + 1][G2_KS], last record = zeros
+  double *Tsm = Ks + (size_t)(P.maxe + 1) * G2_KS;                                    // 40 doubles: dN[4][4][2], w[4], pad
   int32_t *tnb = reinterpret_cast<int32_t *>(Tsm + 40);                               // [3][tn_words]
   unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [2] stage buffers
   const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NC * 8, b_cn = b_lc + (size_t)P.maxe * 4,
-               b_dg = b_cn + G2_NC * 4, b_ns = b_dg + G2_NC * 4, b_size = b_ns + (size_t)G2_NC * P.ns * 4;
+               b_dg = b_cn + G2_NC * 4, b_rs = b_dg + G2_NC * 4, b_bs = b_rs + G2_NC * G2_MAXSRC * 2,
+               b_size = b_bs + (size_t)(1 + P.nsw) * P.maxb * 4;
   const int tid = threadIdx.x;
   if (tid < 32) Tsm[tid] = T.dN[tid >> 3][(tid >> 1) & 3][tid & 1];
   else if (tid < 36) Tsm[tid] = T.w[tid - 32];
-  else if (tid < 40) Tsm[tid - 40] = 0.0;   // the zero slot just below Tsm
+  else if (tid >= 64 && tid < 64 + G2_KS) Ks[(size_t)P.maxe * G2_KS + tid - 64] = 0.0;
 
   auto issue_A = [&](int64_t c, int k) {          // node list of cluster c -> tnb[k % 3]
     if (c < P.ncl) {
@@ -200,8 +160,9 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
         cp_async16(B + b_cn + w * 4, P.cn + c * G2_NC + w);
         cp_async16(B + b_dg + w * 4, P.deg + c * G2_NC + w);
       }
-      const int nsw = G2_NC * P.ns;   // uint32 entries, multiple of 4
-      for (int w = tid * 4; w < nsw; w += G2_THREADS * 4) cp_async16(B + b_ns + w * 4, P.nsrc + c * nsw + w);
+      for (int w = tid * 8; w < G2_NC * G2_MAXSRC; w += G2_THREADS * 8) cp_async16(B + b_rs + w * 2, P.rsrc + c * (G2_NC * G2_MAXSRC) + w);
+      const int nbw = (1 + P.nsw) * P.maxb;   // uint32 entries, multiple of 4
+      for (int w = tid * 4; w < nbw; w += G2_THREADS * 4) cp_async16(B + b_bs + w * 4, P.bsrc + c * nbw + w);
     }
     cp_async_commit();
   };
@@ -225,70 +186,85 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
 
     const unsigned char *B = bbase + (size_t)(k & 1) * b_size;
     const int ne = tnb[(k % 3) * tn_words + 1];
-    // ---- phase 1a: one thread per (element, quadrature point): the latency-bound geometry chain
-    //      (J, J^-1, F, F^-1, log) gets 4x the thread-level parallelism of a per-element thread ----
+    const int nb = tnb[(k % 3) * tn_words + 2];
+    // ---- phase 1: one thread per element, quadrature loop rolled (the accumulators are the register budget) ----
     {
       const double *xu = reinterpret_cast<const double *>(B + b_xu);
       const unsigned *lcv = reinterpret_cast<const unsigned *>(B + b_lc);
-      for (int w = tid; w < ne * 4; w += G2_THREADS) {
-        const int sl = w >> 2, q = w & 3;
+      for (int sl = tid; sl < ne; sl += G2_THREADS) {
         const unsigned lc = lcv[sl];
-        double X[4][2], u[4][2];
+        double Kb[10][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int t = (lc >> (8 * a)) & 0xff;
-          const double2 x = reinterpret_cast<const double2 *>(xu)[2 * t];
-          const double2 v = reinterpret_cast<const double2 *>(xu)[2 * t + 1];
-          X[a][0] = x.x; X[a][1] = x.y; u[a][0] = v.x; u[a][1] = v.y;
+        for (int s = 0; s < 10; ++s)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Kb[s][j] = 0.0;
+        double2 *dst = reinterpret_cast<double2 *>(Ks + (size_t)sl * G2_KS);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q)
+          q1_2d_qp_accumulate<DO_R, DO_K>(reinterpret_cast<const double2 *>(xu), lc, Tsm + q * 8, Tsm[32 + q], mu, lam, Kb, dst + 20, q == 0);
+        if (DO_K) {
+#pragma unroll
+          for (int s = 0; s < 10; ++s) { dst[2 * s] = make_double2(Kb[s][0], Kb[s][1]); dst[2 * s + 1] = make_double2(Kb[s][2], Kb[s][3]); }
         }
-        q1_2d_qp_record<DO_R, DO_K>(X, u, Tsm + q * 8, Tsm[32 + q], mu, lam,
-                                    reinterpret_cast<double2 *>(Qs + (size_t)sl * G2_KS + q * G2_QS));
       }
     }
     __syncthreads();
     const long long tp2 = P.prof ? clock64() : 0;
-    // ---- phase 1b: one thread per element: pure FMA stream over its 4 records ----
-    if (tid < ne) q1_2d_accumulate_sym<DO_R, DO_K>(Qs + (size_t)tid * G2_KS);
-    __syncthreads();
-    const long long tp3 = P.prof ? clock64() : 0;
-    // ---- phase 2: one thread per (owned node, component) writes its row ----
-    {
-      const int nl = tid >> 1, i = tid & 1;
-      const int node = reinterpret_cast<const int32_t *>(B + b_cn)[nl];
-      if (node >= 0) {
-        const int64_t b0 = reinterpret_cast<const int64_t *>(B + b_b0)[nl];
-        const int deg = reinterpret_cast<const int32_t *>(B + b_dg)[nl];
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(B + b_ns) + (size_t)nl * P.ns;
-        double *row = A.vals + 4 * b0 + (int64_t)i * 2 * deg;
-        double rsum = 0.0;
-        double2 acc = make_double2(0.0, 0.0);
-        // branch-free walk: every list has exactly P.ns entries (padded with sources that point at the
-        // zero slot); bit 14 = block stored transposed, bit 15 = diagonal block (adds f_e), bit 26 = last
-        // source of its column block (flush)
-#pragma unroll 4
-        for (int m = 0; m < P.ns; ++m) {
-          const uint32_t code = src[m];
-          const int off = code & 0x3fff, tr = (code >> 14) & 1;
-          if (DO_K) {
-            const int xo = off + i * (2 - tr);
-            acc.x += Qs[xo]; acc.y += Qs[xo + 1 + tr];
-            if (code & (1u << 26)) {
-              *reinterpret_cast<double2 *>(row + 2 * ((code >> 16) & 0xff)) = acc;
-              acc = make_double2(0.0, 0.0);
-            }
-          }
-          if (DO_R && (code & 0x8000u)) rsum += Qs[(off / G2_KS) * G2_KS + 40 + ((code >> 24) & 3) * 2 + i];
+    // ---- phase 2: one task per CSR block of the cluster's rows: sum the element blocks that land in it, in
+    //      ascending element order (padded list: unused sources read the zero record), and write its two row
+    //      segments (adjacent tasks -> adjacent 16 B). R: one task per node over its f_e list. ----
+    if (DO_K) {
+      const uint32_t *bs = reinterpret_cast<const uint32_t *>(B + b_bs);
+      const int64_t *b0v = reinterpret_cast<const int64_t *>(B + b_b0);
+      const int32_t *dgv = reinterpret_cast<const int32_t *>(B + b_dg);
+      const unsigned ks_s = (unsigned)__cvta_generic_to_shared(Ks);
+      for (int blk = tid; blk < nb; blk += G2_THREADS) {
+        const uint32_t w0 = bs[blk];
+        const int nl = w0 & 0xff, jb = (w0 >> 8) & 0xff;
+        double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
+        for (int sw = 0; sw < P.nsw; ++sw) {
+          const uint32_t cw = bs[(1 + sw) * P.maxb + blk];
+          const unsigned a0 = ks_s + ((cw & 0x7fffu) << 3), a1 = ks_s + ((cw >> 13) & 0x3fff8u);
+          double2 x0, x1, y0, y1;
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0.x), "=d"(x0.y) : "r"(a0));
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(x1.x), "=d"(x1.y) : "r"(a0));
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y0.x), "=d"(y0.y) : "r"(a1));
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(y1.x), "=d"(y1.y) : "r"(a1));
+          const bool tr0 = (cw & 0x8000u) != 0, tr1 = (cw & 0x80000000u) != 0;
+          lo.x += x0.x; lo.y += tr0 ? x1.x : x0.y; hi.x += tr0 ? x0.y : x1.x; hi.y += x1.y;
+          lo.x += y0.x; lo.y += tr1 ? y1.x : y0.y; hi.x += tr1 ? y0.y : y1.x; hi.y += y1.y;
         }
-        if (DO_R) A.R[2 * (int64_t)node + i] = rsum;
+        double *row = A.vals + 4 * b0v[nl] + 2 * jb;
+        *reinterpret_cast<double2 *>(row) = lo;
+        *reinterpret_cast<double2 *>(row + 2 * dgv[nl]) = hi;
       }
     }
-    __syncthreads();             // Qs and stage k & 1 are free again
+    if (DO_R) {
+      const int32_t *cnv = reinterpret_cast<const int32_t *>(B + b_cn);
+      for (int nl = tid; nl < G2_NC; nl += G2_THREADS) {
+        const int node = cnv[nl];
+        if (node < 0) continue;
+        const uint4 rc = *reinterpret_cast<const uint4 *>(B + b_rs + nl * (G2_MAXSRC * 2));
+        const unsigned rw[4] = {rc.x, rc.y, rc.z, rc.w};
+        double2 rs = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int sw = 0; sw < G2_MAXSRC / 2; ++sw) {
+          if (sw < P.nsw) {
+            const double2 f0 = *reinterpret_cast<const double2 *>(Ks + (rw[sw] & 0xffffu));
+            const double2 f1 = *reinterpret_cast<const double2 *>(Ks + (rw[sw] >> 16));
+            rs.x += f0.x; rs.y += f0.y;
+            rs.x += f1.x; rs.y += f1.y;
+          }
+        }
+        *reinterpret_cast<double2 *>(A.R + 2 * (int64_t)node) = rs;
+      }
+    }
+    __syncthreads();             // Ks and stage k & 1 are free again
     if (P.prof && tid == 0) {
-      const long long tp4 = clock64();
+      const long long tp3 = clock64();
       atomicAdd(P.prof + 0, (unsigned long long)(tp1 - tp0));   // staging wait + issue
-      atomicAdd(P.prof + 1, (unsigned long long)(tp2 - tp1));   // phase 1a
-      atomicAdd(P.prof + 2, (unsigned long long)(tp3 - tp2));   // phase 1b
-      atomicAdd(P.prof + 3, (unsigned long long)(tp4 - tp3));   // phase 2
+      atomicAdd(P.prof + 1, (unsigned long long)(tp2 - tp1));   // phase 1
+      atomicAdd(P.prof + 3, (unsigned long long)(tp3 - tp2));   // phase 2
       atomicAdd(P.prof + 4, 1ull);                               // clusters
     }
   }
@@ -296,13 +272,24 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
 }
 
 // ---- host side: pack the cluster plan into fixed-stride device arrays ---------------------------
-bool nls_assembly_overwrites(const nls_context *h) { return h->dim == 2 && h->opt_assembly == 1 && h->have_plan; }
+int nls_assembly_mode(nls_context *h) {
+  if (h->opt_assembly == 0 || h->dim < 2) return NLS_ASM_ATOMIC;
+  if (h->dim == 2 && h->opt_assembly == 1 && h->have_plan) return NLS_ASM_GATHER;
+  TwoPhasePlan &t = h->tplan;
+  if (h->dim == 3 && h->opt_assembly == 1 && !h->opt_twophase_3d) return NLS_ASM_ATOMIC;
+  if (t.ok && !t.scratch) {       // first use: the record scratch; without room for it keep the atomic scatter
+    if (cudaMalloc((void **)&t.scratch, t.scratch_bytes) != cudaSuccess) { cudaGetLastError(); t.scratch = nullptr; t.ok = false; }
+  }
+  if (t.ok) return NLS_ASM_TWOPHASE;
+  return (h->dim == 2 && h->have_plan) ? NLS_ASM_GATHER : NLS_ASM_ATOMIC;
+}
+bool nls_assembly_overwrites(nls_context *h) { return nls_assembly_mode(h) != NLS_ASM_ATOMIC; }
 int nls_gather_nc(void) { return G2_NC; }
 
-static size_t gather_smem(int maxt, int maxe, int ns, int rp) {
-  const size_t bsz = (size_t)maxt * 32 + G2_NC * 8 + (size_t)maxe * 4 + G2_NC * 4 + G2_NC * 4 + (size_t)G2_NC * ns * 4;
-  (void)rp;   // staging the rows in shared memory for coalesced stores was measured slower
-  return (size_t)maxe * G2_KS * 8 + 44 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
+static size_t gather_smem(int maxt, int maxe, int maxb, int nsw) {
+  const size_t bsz = (size_t)maxt * 32 + G2_NC * 8 + (size_t)maxe * 4 + G2_NC * 4 + G2_NC * 4 + G2_NC * G2_MAXSRC * 2 +
+                     (size_t)(1 + nsw) * maxb * 4;
+  return (size_t)(maxe + 1) * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
 }
 
 void nls_gather_free(nls_context *h) {
@@ -312,13 +299,14 @@ void nls_gather_free(nls_context *h) {
   if (g.cn) cudaFree(g.cn);
   if (g.b0) cudaFree(g.b0);
   if (g.deg) cudaFree(g.deg);
-  if (g.nsrc) cudaFree(g.nsrc);
+  if (g.bsrc) cudaFree(g.bsrc);
+  if (g.rsrc) cudaFree(g.rsrc);
   g = GatherPlanDev();
   h->have_plan = false;
 }
 
 // Sets h->have_plan when the mesh fits the kernel's packed formats; otherwise leaves it false and
-// the atomic-scatter kernel is used instead.
+// another scheme is used instead.
 int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   nls_gather_free(h);
   if (h->dim != 2 || plan.ncl == 0) return NLS_OK;
@@ -327,9 +315,9 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   const int32_t *conn = h->h_conn.data();
   int maxdeg = 0;
   for (int64_t a = 0; a < h->n_owned; ++a) maxdeg = std::max<int>(maxdeg, (int)(h->h_browptr[a + 1] - h->h_browptr[a]));
-  if (plan.max_elems > G2_THREADS || (size_t)(plan.max_elems + 4) * G2_KS + 4 > 0x3fff || maxdeg > 255 || plan.max_adj > 8) return NLS_OK;
+  if ((size_t)(plan.max_elems + 5) * G2_KS > 0x7fff || maxdeg > 127 || plan.max_adj > G2_MAXSRC) return NLS_OK;
   std::vector<std::vector<int32_t>> touched((size_t)ncl);
-  int maxt = 0;
+  int maxt = 0, maxb = 0;
   for (int64_t c = 0; c < ncl; ++c) {
     std::vector<int32_t> &t = touched[c];
     for (int32_t s = plan.eptr[c]; s < plan.eptr[c + 1]; ++s)
@@ -337,18 +325,26 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
     std::sort(t.begin(), t.end());
     t.erase(std::unique(t.begin(), t.end()), t.end());
     maxt = std::max<int>(maxt, (int)t.size());
+    int nb = 0;
+    for (int nl = 0; nl < G2_NC; ++nl) {
+      const int32_t a = plan.nodes[c * G2_NC + nl];
+      if (a >= 0) nb += (int)(h->h_browptr[a + 1] - h->h_browptr[a]);
+    }
+    maxb = std::max(maxb, nb);
   }
   if (maxt > 255) return NLS_OK;
-  const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, NS = (plan.max_adj * nen + 3) & ~3;
-  const int RP = 4 * maxdeg + 2;   // doubles per node in the row buffer; (2 maxdeg + 1) x 16 B = odd
-  if (gather_smem(MAXT, MAXE, NS, RP) > (size_t)110 * 1024) return NLS_OK;
-  const int tnw = 4 + MAXT;
+  const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, MAXB = (maxb + 3) & ~3;
+  const int NSW = plan.max_adj <= 4 ? 2 : 4;       // 16-bit source codes, two per word
+  if (gather_smem(MAXT, MAXE, MAXB, NSW) > (size_t)112 * 1024) return NLS_OK;   // two CTAs per SM
+  const int tnw = 4 + MAXT, bw = (1 + NSW) * MAXB;
   std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NC, -1), deg((size_t)ncl * G2_NC, 0);
   std::vector<uint32_t> lconn((size_t)ncl * MAXE, 0);
   std::vector<int64_t> b0((size_t)ncl * G2_NC, 0);
-  const uint32_t dummy = (uint32_t)(MAXE * G2_KS);   // offset of the zero slot, no flags
-  std::vector<uint32_t> nsrc((size_t)ncl * G2_NC * NS, dummy);
-  std::vector<uint32_t> codes;
+  const uint32_t none = (uint32_t)(MAXE * G2_KS);   // the zero record, not transposed
+  std::vector<uint32_t> bsrc((size_t)ncl * bw, none | (none << 16));
+  std::vector<uint16_t> rsrc((size_t)ncl * G2_NC * G2_MAXSRC, (uint16_t)(none + 40));
+  static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
+  std::vector<int> nsrc_of;
   for (int64_t c = 0; c < ncl; ++c) {
     const std::vector<int32_t> &t = touched[c];
     const int32_t e0 = plan.eptr[c], ne = plan.eptr[c + 1] - e0;
@@ -362,42 +358,47 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
       }
       lconn[c * MAXE + s] = packed;
     }
+    uint32_t *bs = bsrc.data() + (size_t)c * bw;
+    int nb = 0;
     for (int nl = 0; nl < G2_NC; ++nl) {
       const int32_t a = plan.nodes[c * G2_NC + nl];
       if (a < 0) continue;
       cn[c * G2_NC + nl] = a;
       b0[c * G2_NC + nl] = h->h_browptr[a];
-      deg[c * G2_NC + nl] = (int32_t)(h->h_browptr[a + 1] - h->h_browptr[a]);
-      const int32_t *lo = h->h_bcol.data() + h->h_browptr[a], *hi = h->h_bcol.data() + h->h_browptr[a + 1];
-      codes.clear();
+      const int dg = (int)(h->h_browptr[a + 1] - h->h_browptr[a]);
+      deg[c * G2_NC + nl] = dg;
+      const int32_t *lo = h->h_bcol.data() + h->h_browptr[a], *hi = lo + dg;
+      const int blk0 = nb;
+      nsrc_of.assign(dg, 0);
+      for (int jb = 0; jb < dg; ++jb)
+        bs[blk0 + jb] = (uint32_t)nl | ((uint32_t)jb << 8);
+      int nrs = 0;
+      nb += dg;
       for (int32_t s = 0; s < ne; ++s) {          // ascending slot = ascending element id
         const int32_t *ce = conn + (int64_t)plan.elems[e0 + s] * nen;
         int al = -1;
         for (int q = 0; q < nen; ++q) if (ce[q] == a) al = q;
         if (al < 0) continue;
+        rsrc[((size_t)c * G2_NC + nl) * G2_MAXSRC + nrs++] = (uint16_t)(s * G2_KS + 40 + al * 2);
         for (int b = 0; b < nen; ++b) {
-          const uint32_t jb = (uint32_t)(std::lower_bound(lo, hi, ce[b]) - lo);
-          codes.push_back((jb << 16) | ((uint32_t)s << 4) | ((uint32_t)al << 2) | (uint32_t)b);   // sort key: (jb, slot)
+          const int jb = (int)(std::lower_bound(lo, hi, ce[b]) - lo);
+          const int k = nsrc_of[jb]++;
+          if (k >= 2 * NSW) return NLS_OK;        // more elements on one block than the packed list holds
+          const int lo_ = std::min(al, b), hi_ = std::max(al, b);
+          const uint32_t code = (uint32_t)(s * G2_KS + (bd[lo_] + (hi_ - lo_)) * 4) | (al > b ? 0x8000u : 0u);
+          uint32_t &wsrc = bs[(size_t)(1 + k / 2) * MAXB + blk0 + jb];
+          wsrc = (k & 1) ? ((wsrc & 0x0000ffffu) | (code << 16)) : ((wsrc & 0xffff0000u) | code);
         }
       }
-      std::sort(codes.begin(), codes.end());
-      if ((int)codes.size() > NS) return NLS_OK;   // cannot happen: NS >= max_adj * nen
-      for (size_t m = 0; m < codes.size(); ++m) {
-        const uint32_t kk = codes[m], jb = kk >> 16, s = (kk >> 4) & 0xfff, al = (kk >> 2) & 3, b = kk & 3;
-        static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
-        const uint32_t lo_ = std::min(al, b), hi_ = std::max(al, b);
-        const uint32_t off = s * G2_KS + (uint32_t)(bd[lo_] + (hi_ - lo_)) * 4;
-        const bool last = (m + 1 == codes.size()) || ((codes[m + 1] >> 16) != jb);
-        nsrc[((size_t)c * G2_NC + nl) * NS + m] = off | (al > b ? 0x4000u : 0u) | (al == b ? 0x8000u : 0u) | (jb << 16) | (al << 24) |
-                                                   (last ? (1u << 26) : 0u);
-      }
     }
+    tn[c * tnw + 2] = nb;
+    for (int j = nb; j < MAXB; ++j) bs[j] = 0;    // unused tail (never read: tasks stop at nb)
   }
   GatherPlanDev &g = h->gplan;
-  g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.ns = NS; g.rp = RP;
+  g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.maxb = MAXB; g.nsw = NSW;
 #define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&g.field, sizeof(vec[0]) * vec.size())); \
   NLS_CUDA(h, cudaMemcpyAsync(g.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
-  UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(nsrc, nsrc);
+  UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(bsrc, bsrc); UP(rsrc, rsrc);
 #undef UP
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_plan = true;
@@ -409,9 +410,9 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
   a.nel = h->nel; a.n_owned = h->n_owned; a.conn = h->d_conn; a.coords = h->d_coords; a.U = h->d_U;
   a.R = h->d_R; a.vals = h->d_vals; a.browptr = h->d_browptr; a.pos = h->d_pos;
   const GatherPlanDev &g = h->gplan;
-  GatherArgs p{g.ncl, g.maxt, g.maxe, g.ns, g.rp, g.tn, g.lconn, g.cn, g.b0, g.deg, g.nsrc,
+  GatherArgs p{g.ncl, g.maxt, g.maxe, g.maxb, g.nsw, g.tn, g.lconn, g.cn, g.b0, g.deg, g.bsrc, g.rsrc,
                h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr};
-  const size_t shm = gather_smem(g.maxt, g.maxe, g.ns, g.rp);
+  const size_t shm = gather_smem(g.maxt, g.maxe, g.maxb, g.nsw);
   static size_t shm_set = 0;
   if (shm > shm_set) {
     cudaFuncSetAttribute(k_asm_q1_2d_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);

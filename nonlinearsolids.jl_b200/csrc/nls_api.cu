@@ -45,6 +45,7 @@ static void free_pattern(nls_context *h) {
   dev_free(&h->d_browptr); dev_free(&h->d_bcol); dev_free(&h->d_rowptr); dev_free(&h->d_colind);
   dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
   nls_gather_free(h);
+  nls_twophase_free(h);
   h->h_browptr.clear(); h->h_bcol.clear();
   h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
 }
@@ -358,6 +359,7 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
     nls_host_cluster_plan(h->dim, h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_coords.data(), nls_gather_nc(), plan);
     NLS_TRY(nls_gather_build(h, plan));
   }
+  NLS_TRY(nls_twophase_build(h));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_pattern = true;
   return NLS_OK;
@@ -682,6 +684,12 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
+  if (!std::strcmp(key, "twophase_3d")) { h->opt_twophase_3d = value; return NLS_OK; }
+  if (!std::strcmp(key, "scratch_mb")) {   // takes effect at the next nls_build_pattern
+    h->opt_scratch_mb = value;
+    if (h->have_pattern) { NLS_TRY(nls_twophase_build(h)); }
+    return NLS_OK;
+  }
   if (!std::strcmp(key, "gather_ctas")) { h->opt_gather_ctas = value; return NLS_OK; }
   if (!std::strcmp(key, "profile_phases")) {
     if (!h->d_prof) NLS_CUDA(h, cudaMalloc((void **)&h->d_prof, 8 * sizeof(uint64_t)));

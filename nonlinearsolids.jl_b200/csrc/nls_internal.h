@@ -58,13 +58,27 @@ void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, i
 // packed, fixed-stride device copy of the plan (kernels_gather.cu)
 struct GatherPlanDev {
   int64_t ncl = 0;
-  int maxt = 0, maxe = 0, ns = 0, rp = 0;
+  int maxt = 0, maxe = 0, maxb = 0, nsw = 0;
   int32_t *tn = nullptr;
   uint32_t *lconn = nullptr;
   int32_t *cn = nullptr;
   int64_t *b0 = nullptr;
   int32_t *deg = nullptr;
-  uint32_t *nsrc = nullptr;
+  uint32_t *bsrc = nullptr;
+  uint16_t *rsrc = nullptr;
+};
+
+// plan of the two-phase (element records -> row owners) assembly (kernels_twophase.cu)
+struct TwoPhaseChunk { int64_t n0, n1, e_lo, e_hi; };
+struct TwoPhasePlan {
+  bool ok = false;                // plan built and the mesh fits the packed formats
+  int64_t estride = 0, np = 0;
+  int maxadj = 0, rs = 0, nent = 0;
+  int32_t *esrc = nullptr;
+  uint64_t *asrc = nullptr;
+  double *scratch = nullptr;      // allocated on first use
+  size_t scratch_bytes = 0;
+  std::vector<TwoPhaseChunk> chunks;
 };
 
 // ---- device control block of the PCG loop (lives in device memory) ----
@@ -134,6 +148,7 @@ struct nls_context {
   // gather-assembly plan (device copy)
   bool have_plan = false;
   GatherPlanDev gplan;
+  TwoPhasePlan tplan;
   std::vector<double> h_coords;
 
   // vectors (ndof_local unless noted)
@@ -160,7 +175,10 @@ struct nls_context {
   int opt_profile_phases = 0; // debug: per-phase cycle counters of the gather kernel
   uint64_t *d_prof = nullptr;
   int opt_gather_ctas = 0; // persistent CTAs per SM of the gather kernel (0 = default)
-  int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: gather (row-owner) kernel where available
+  int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: best row-owner scheme available (2-D: shared-memory
+                          // gather, 3-D: element records + row owners); 2: element records + row owners everywhere
+  int opt_twophase_3d = 0; // 1: the 3-D default becomes element records + row owners instead of the atomic scatter
+  int opt_scratch_mb = 0; // byte budget of the element-record scratch in MiB (0 = default 8192)
 
   // distributed
   bool distributed = false;
@@ -183,7 +201,12 @@ struct nls_context {
 
 // ---- kernel launchers (kernels_assembly.cu / kernels_krylov.cu) ----
 int nls_launch_assembly(nls_context *h, bool want_r, bool want_k);
-bool nls_assembly_overwrites(const nls_context *h);
+enum { NLS_ASM_ATOMIC = 0, NLS_ASM_GATHER = 1, NLS_ASM_TWOPHASE = 2 };
+int nls_assembly_mode(nls_context *h);          // which scheme the next assembly uses (allocates the record scratch if needed)
+bool nls_assembly_overwrites(nls_context *h);   // true when the scheme writes every row itself (no zero-fill)
+int nls_twophase_build(nls_context *h);
+void nls_twophase_free(nls_context *h);
+int nls_launch_twophase(nls_context *h, bool want_r, bool want_k);
 int nls_gather_nc(void);
 int nls_gather_build(nls_context *h, const AsmPlan &plan);
 void nls_gather_free(nls_context *h);

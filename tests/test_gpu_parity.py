@@ -300,6 +300,51 @@ def test_gather_vs_atomic_assembly_2d(nls, orc, n, kind):
         assert rel_err(out[opt][0], Ro) <= RTOL and rel_err(out[opt][1], Ko) <= RTOL, opt
 
 
+@pytest.mark.parametrize("dim,n,kind,scratch_mb", [(2, 37, "distorted", 0), (2, 66, "shuffled", 1), (3, 9, "distorted", 0),
+                                                     (3, 13, "affine", 1), (3, 12, "shuffled", 1)])
+def test_assembly_schemes_agree(nls, orc, dim, n, kind, scratch_mb):
+    """Every assembly scheme (0 = atomic scatter, 1 = default row-owner scheme of the dimension, 2 = element
+    records + row owners) against the oracle and against each other, on structured, distorted and randomly
+    renumbered meshes; scratch_mb = 1 forces the record scratch into several node chunks. The row-owner
+    schemes sum in element order, so they are bit-reproducible and residual-only / Jacobian-only passes
+    reproduce the fused pass exactly."""
+    mat = nls.NeoHookean(E=1.0, nu=0.3)
+    mesh = nls.grid_mesh(n, dim)
+    if kind == "distorted":
+        mesh.coords[:] = distorted(mesh)
+    if kind == "shuffled":
+        rng = np.random.default_rng(5)
+        perm = rng.permutation(mesh.nn)
+        conn = perm[mesh.conn][rng.permutation(mesh.nel)].astype(np.int32)
+        coords = np.zeros_like(mesh.coords); coords[perm] = mesh.coords
+        mesh = nls.Mesh(dim, conn, coords=coords)
+    fem = nls.FEMModel(mesh)
+    fem.addboundary(nls.Dirichlet([0, 1, 7], [0.0, 0.001, -0.002]))
+    fem.addboundary(nls.Neumann([5, 9], [0.25, -0.5]))
+    om = orc.OracleModel(dim, mesh.conn, mesh.coords, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mat.mu, mat.lam))
+    om.set_dirichlet([0, 1, 7], [0.0, 0.001, -0.002]); om.set_neumann([5, 9], [0.25, -0.5])
+    U = nls.smooth_field(mesh.coords, amp=0.2 / (n - 1))
+    H = fem.handle(mat)
+    if scratch_mb:
+        H.call("nls_set_option", b"scratch_mb", scratch_mb)
+    _, Ro = om.residual(U); Ko = om.jacobian_csr(U)
+    out = {}
+    for opt in (2, 0, 1, 2):
+        H.call("nls_set_option", b"assembly", opt)
+        R, K = np.full(fem.ndof, np.nan), nls.CSRMatrix(fem)
+        K.vals[:] = np.nan
+        nls.residual_jacobian(mat, fem, U.copy(), R, K)
+        assert rel_err(R, Ro) <= RTOL and rel_err(K.vals, Ko) <= RTOL, opt
+        if opt == 2 and 2 in out:
+            assert np.array_equal(out[2][0], R) and np.array_equal(out[2][1], K.vals)   # deterministic
+        out[opt] = (R, K.vals.copy())
+        R1, K1 = np.full(fem.ndof, np.nan), nls.CSRMatrix(fem)
+        K1.vals[:] = np.nan
+        nls.Residual(mat)(fem, U.copy(), R1); nls.Jacobian(mat)(fem, U.copy(), K1)
+        assert rel_err(R1, R) <= 1e-13 and rel_err(K1.vals, K.vals) <= 1e-13
+    assert rel_err(out[2][1], out[0][1]) <= 1e-13 and rel_err(out[2][1], out[1][1]) <= 1e-13
+
+
 def test_distributed_force(nls, orc):
     """DistributedForce on the device (distributedforce.jl:7-27, residual.jl:19-25): 1-D with a function of
     time evaluated through the timestepper context, and constant 2-D / 3-D body loads."""
