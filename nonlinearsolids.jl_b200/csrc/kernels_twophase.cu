@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstring>
 #include "asm_common.cuh"
+#include "hex_element.cuh"
 
 // ---- record layout ---------------------------------------------------------------------------
 // 2-D: blocks (a,b), a <= b, slot = {0,4,7,9}[a] + (b-a); entry = slot*4 + i*2 + k; f_e at 40 + a*2 + i.
@@ -161,8 +162,6 @@ k_elem_q1_2d_store(const AsmArgs A, const TwoPhaseArgs P, const __grid_constant_
 //   store  : 45 + 3 values per lane, 4 consecutive elements per 32-byte sector
 // ------------------------------------------------------------------------------------
 #define T8_EPB 16
-#define T8_QSTRIDE 62
-#define T8_ESTRIDE (8 * T8_QSTRIDE + 48)
 
 template <bool DO_R, bool DO_K>
 __global__ void __launch_bounds__(128, 3)
@@ -170,122 +169,13 @@ k_elem_q1_3d_store(const AsmArgs A, const TwoPhaseArgs P, const __grid_constant_
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int le = tid >> 3;
-  const int ln = tid & 7;
+  const int a = tid & 7;
   const int64_t ec = blockIdx.x * (int64_t)T8_EPB + le;
   const int64_t e = P.e_lo + ec;
-  const bool active = e < P.e_hi;
-  double *S = smem + le * T8_ESTRIDE;
-  double *Xu = S + 8 * T8_QSTRIDE;
+  if (e >= P.e_hi) return;                  // whole 8-lane groups leave together
   const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));
-
-  if (active) {
-    const int node = A.conn[e * 8 + ln];
-    const double *xc = A.coords + 3 * (int64_t)node;
-    const double *uc = A.U + 3 * (int64_t)node;
-    Xu[ln * 6 + 0] = xc[0]; Xu[ln * 6 + 1] = xc[1]; Xu[ln * 6 + 2] = xc[2];
-    Xu[ln * 6 + 3] = uc[0]; Xu[ln * 6 + 4] = uc[1]; Xu[ln * 6 + 5] = uc[2];
-  }
-  __syncwarp(gmask);
-
-  const double mu = mp.p[0], lam = mp.p[1];
-  if (active) {
-    const int q = ln;
-    double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Ji[9], F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Fi[9];
-    double G[8][3];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const double dn0 = T.dN[q][a][0], dn1 = T.dN[q][a][1], dn2 = T.dN[q][a][2];
-      G[a][0] = dn0; G[a][1] = dn1; G[a][2] = dn2;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const double x = Xu[a * 6 + d];
-        J[d * 3 + 0] = fma(x, dn0, J[d * 3 + 0]); J[d * 3 + 1] = fma(x, dn1, J[d * 3 + 1]); J[d * 3 + 2] = fma(x, dn2, J[d * 3 + 2]);
-      }
-    }
-    const double detJ = inv3(J, Ji);
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const double d0 = G[a][0], d1 = G[a][1], d2 = G[a][2];
-#pragma unroll
-      for (int D = 0; D < 3; ++D) G[a][D] = fma(d0, Ji[D], fma(d1, Ji[3 + D], d2 * Ji[6 + D]));
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double ui = Xu[a * 6 + 3 + i];
-        F[i * 3 + 0] = fma(ui, G[a][0], F[i * 3 + 0]); F[i * 3 + 1] = fma(ui, G[a][1], F[i * 3 + 1]); F[i * 3 + 2] = fma(ui, G[a][2], F[i * 3 + 2]);
-      }
-    }
-    const double detF = inv3(F, Fi);
-    const double lnJ = log(detF);
-    const double wd = T.w[q] * detJ;
-    double *Q = S + q * T8_QSTRIDE;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      double2 *dst = reinterpret_cast<double2 *>(Q + a * 6);
-      const double g0 = fma(G[a][0], Fi[0], fma(G[a][1], Fi[3], G[a][2] * Fi[6]));
-      const double g1 = fma(G[a][0], Fi[1], fma(G[a][1], Fi[4], G[a][2] * Fi[7]));
-      const double g2 = fma(G[a][0], Fi[2], fma(G[a][1], Fi[5], G[a][2] * Fi[8]));
-      dst[0] = make_double2(G[a][0], G[a][1]);
-      dst[1] = make_double2(G[a][2], g0);
-      dst[2] = make_double2(g1, g2);
-    }
-    const double c1 = wd * mu, cl = wd * lam * lnJ;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int Jc = 0; Jc < 3; ++Jc)
-        Q[48 + i * 3 + Jc] = fma(c1, F[i * 3 + Jc] - Fi[Jc * 3 + i], cl * Fi[Jc * 3 + i]);
-    Q[57] = c1; Q[58] = wd * lam; Q[59] = c1 - cl;
-  }
-  __syncwarp(gmask);
-  if (!active) return;
-
-  const int a = ln;
-  double fe[3] = {0, 0, 0};
-  double Kr[5][3][3];
-#pragma unroll
-  for (int d = 0; d < 5; ++d)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) Kr[d][i][k] = 0.0;
-#pragma unroll 1
-  for (int q = 0; q < 8; ++q) {
-    const double *Q = S + q * T8_QSTRIDE;
-    const double2 t0 = reinterpret_cast<const double2 *>(Q + a * 6)[0];
-    const double2 t1 = reinterpret_cast<const double2 *>(Q + a * 6)[1];
-    const double2 t2 = reinterpret_cast<const double2 *>(Q + a * 6)[2];
-    const double Ga[3] = {t0.x, t0.y, t1.x}, ga[3] = {t1.y, t2.x, t2.y};
-    if (DO_R) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        fe[i] = fma(Q[48 + i * 3], Ga[0], fma(Q[48 + i * 3 + 1], Ga[1], fma(Q[48 + i * 3 + 2], Ga[2], fe[i])));
-    }
-    if (DO_K) {
-      const double c1 = Q[57], c2 = Q[58], c3 = Q[59];
-      const double c1G[3] = {c1 * Ga[0], c1 * Ga[1], c1 * Ga[2]};
-      const double c2g[3] = {c2 * ga[0], c2 * ga[1], c2 * ga[2]};
-      const double c3g[3] = {c3 * ga[0], c3 * ga[1], c3 * ga[2]};
-#pragma unroll
-      for (int d = 0; d < 5; ++d) {
-        const int b = (a + d) & 7;
-        double Gb[3], gb[3];
-        if (d == 0) {
-          Gb[0] = Ga[0]; Gb[1] = Ga[1]; Gb[2] = Ga[2]; gb[0] = ga[0]; gb[1] = ga[1]; gb[2] = ga[2];
-        } else {
-          const double2 s0 = reinterpret_cast<const double2 *>(Q + b * 6)[0];
-          const double2 s1 = reinterpret_cast<const double2 *>(Q + b * 6)[1];
-          const double2 s2 = reinterpret_cast<const double2 *>(Q + b * 6)[2];
-          Gb[0] = s0.x; Gb[1] = s0.y; Gb[2] = s1.x; gb[0] = s1.y; gb[1] = s2.x; gb[2] = s2.y;
-        }
-        const double dab = fma(c1G[0], Gb[0], fma(c1G[1], Gb[1], c1G[2] * Gb[2]));
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            Kr[d][i][k] += fma(c2g[i], gb[k], fma(c3g[k], gb[i], (i == k ? dab : 0.0)));
-      }
-    }
-  }
+  double fe[3], Kr[5][3][3];
+  hex_element_circulant<DO_R, DO_K>(smem + le * HEX_REC, a, gmask, A.conn[e * 8 + a], A.coords, A.U, T, mp.p[0], mp.p[1], Kr, fe);
   double *sc = P.scratch + ec;
   if (DO_K) {
 #pragma unroll
@@ -473,7 +363,7 @@ template <int DIM, bool DO_R, bool DO_K>
 static int launch_twophase(nls_context *h, const AsmArgs &a) {
   const TwoPhasePlan &t = h->tplan;
   static bool attr_set = false;
-  const size_t shm1 = sizeof(double) * T8_EPB * T8_ESTRIDE;
+  const size_t shm1 = sizeof(double) * T8_EPB * HEX_REC;
   const size_t shm2 = sizeof(double) * DIM * 32 * (size_t)t.rs;
   if (DIM == 3 && !attr_set) {
     cudaFuncSetAttribute(k_elem_q1_3d_store<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm1);
