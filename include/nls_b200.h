@@ -160,6 +160,28 @@ int32_t nls_linear_solve(nls_handle h, double rtol, int32_t maxits, const double
 int32_t nls_newton_solve(nls_handle h, const nls_newton_opts *opts, const double *U0, double *U, double *R,
                          double *norm_hist /*maxits+1 or NULL*/, nls_newton_result *res);
 
+/* ---- dynamics: consistent mass, dynamic operators, Newmark step -- */
+/* Builds the consistent mass once (assemblemass!, src/gallery/mass.jl:2-17): rho = density(material),
+ * area = get(fem.data, :A, 1.0) of mass.jl:9,27 (1-D only; ignored for Q1). Needs the pattern. */
+int32_t nls_set_mass(nls_handle h, double rho, double area);
+/* assemblemass!(material, fem, K) into zeroed CSR values (K = M) */
+int32_t nls_get_mass(nls_handle h, double *vals);
+/* applymass!(material, fem, a, R) (mass.jl:26-37): y += M x; y in/out, nrows entries */
+int32_t nls_apply_mass(nls_handle h, const double *x, double *y);
+/* Residual dynamic method (gallery/residual.jl:48-54): static residual of U (Dirichlet overwrite, in/out) + M Udd */
+int32_t nls_dynamic_residual(nls_handle h, double *U, const double *Udd, double *R);
+/* Jacobian dynamic method (gallery/jacobian.jl:42-51): K(U) * scale + M, scale = dUdd/dU(ctx) = dt^2 beta */
+int32_t nls_dynamic_jacobian(nls_handle h, double *U, double scale, double *vals);
+/* M x = b on all DoFs (initial acceleration, timesteppers/newmark.jl:136-140; Jacobi-PCG in place of `\`) */
+int32_t nls_mass_solve(nls_handle h, double rtol, int32_t maxits, const double *b, double *x, int32_t *its, int32_t *status_out);
+/* One step of solve!(ts::NewmarkTimeStepper) (newmark.jl:142-155): Newton on the acceleration with the closures
+ * of newmark.jl:75-107 (update_state! -> static operators -> inertia terms), device-resident, from the
+ * predictors Ut, Udt (update_predictors!, :109-112) and the initial guess Udd0 (previous acceleration).
+ * Returns the converged acceleration and U, Ud = update_state!(Udd) (:114-117). */
+int32_t nls_newmark_solve(nls_handle h, const nls_newton_opts *opts, double beta, double gamma, double dt,
+                          const double *Ut, const double *Udt, const double *Udd0,
+                          double *Udd, double *U, double *Ud, double *R, double *norm_hist, nls_newton_result *res);
+
 /* ---- device-resident variants (no host<->device copies; U/R/vals stay in HBM) ---- */
 int32_t nls_dev_upload_u(nls_handle h, const double *U);
 int32_t nls_dev_download_u(nls_handle h, double *U);
@@ -178,7 +200,9 @@ int64_t nls_kernel_launches(nls_handle h);   /* kernels launched by this handle 
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
  * {staging wait, phase 1a, phase 1b, phase 2, clusters, 0, 0, 0}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);
-/* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 gather/row-owner (2-D);
+/* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 the default row-owner scheme
+ * (2-D: shared-memory gather; 3-D: atomic scatter unless "twophase_3d" = 1), 2 element records + row owners;
+ * "scratch_mb" -> byte budget of the element-record scratch; "gather_ctas" -> persistent CTAs per SM;
  * "spmv" -> 0 scalar CSR, 1 block-aware; "spmv_lanes" -> lanes per node (0 = default) */
 int32_t nls_set_option(nls_handle h, const char *key, int32_t value);
 

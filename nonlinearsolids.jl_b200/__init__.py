@@ -9,10 +9,10 @@ from . import _lib, distributed
 from ._lib import Handle, NLSError, lib
 from .fem import (Dirichlet, Element, ElementBoundary, FEMModel, Lagrange, Mesh, N, Neumann, Quadrature,
                   TimeDependent, dN, gauss_quadrature, getstate, integrate, interpolate, lagrange)
-from .gallery import CSRMatrix, DistributedForce, Jacobian, Residual, residual_jacobian
+from .gallery import CSRMatrix, DistributedForce, Jacobian, Residual, applymass, assemblemass, residual_jacobian
 from .materials import (ExponentialMaterial, LinearElasticity1D, LinearElastoPlasticity1D, NeoHookean,
                         initialize_state, save_state)
 from .meshes import bar_mesh, face_nodes, grid_mesh, slab_local_mesh, slab_planes, smooth_field
 from .solvers import (REASON_CONVERGED_ABSOLUTE, REASON_CONVERGED_RELATIVE, REASON_DIVERGED_LINEAR_SOLVE,
                       REASON_DIVERGED_MAXITS, REASON_DIVERGED_STEP, REASON_NOT_YET_CONVERGED, NewtonSolver,
-                      PseudoTimeStepper, is_converged, set_ctx, set_jacobian_fn, set_residual_fn)
+                      NewmarkTimeStepper, PseudoTimeStepper, is_converged, set_ctx, set_jacobian_fn, set_residual_fn)

@@ -71,6 +71,14 @@ PROTOTYPES = {
     "nls_axpy": (C.c_int32, [_H, C.c_int64, C.c_double, _dp, _dp]),
     "nls_linear_solve": (C.c_int32, [_H, C.c_double, C.c_int32, _dp, _dp, _ip, _dp, _ip]),
     "nls_newton_solve": (C.c_int32, [_H, C.POINTER(NewtonOpts), _dp, _dp, _dp, _dp, C.POINTER(NewtonResult)]),
+    "nls_set_mass": (C.c_int32, [_H, C.c_double, C.c_double]),
+    "nls_get_mass": (C.c_int32, [_H, _dp]),
+    "nls_apply_mass": (C.c_int32, [_H, _dp, _dp]),
+    "nls_dynamic_residual": (C.c_int32, [_H, _dp, _dp, _dp]),
+    "nls_dynamic_jacobian": (C.c_int32, [_H, _dp, C.c_double, _dp]),
+    "nls_mass_solve": (C.c_int32, [_H, C.c_double, C.c_int32, _dp, _dp, _ip, _ip]),
+    "nls_newmark_solve": (C.c_int32, [_H, C.POINTER(NewtonOpts), C.c_double, C.c_double, C.c_double, _dp, _dp, _dp,
+                                      _dp, _dp, _dp, _dp, _dp, C.POINTER(NewtonResult)]),
     "nls_dev_upload_u": (C.c_int32, [_H, _dp]),
     "nls_dev_download_u": (C.c_int32, [_H, _dp]),
     "nls_dev_download_r": (C.c_int32, [_H, _dp]),

@@ -46,6 +46,7 @@ static void free_pattern(nls_context *h) {
   dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
   nls_gather_free(h);
   nls_twophase_free(h);
+  dev_free(&h->d_mass); h->have_mass = false;
   h->h_browptr.clear(); h->h_bcol.clear();
   h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
 }
@@ -112,6 +113,7 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
   dev_free(&h->d_u_n);
   dev_free(&h->d_send_nodes); dev_free(&h->d_recv_nodes); dev_free(&h->d_sendbuf); dev_free(&h->d_recvbuf);
+  dev_free(&h->d_Ut); dev_free(&h->d_Udt); dev_free(&h->d_Udd); dev_free(&h->d_Ud); dev_free(&h->d_con_zero);
   if (h->d_flush) cudaFree(h->d_flush);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -151,6 +153,7 @@ extern "C" int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64
   NLS_CUDA(h, cudaMemsetAsync(h->d_p, 0, nd * sizeof(double), h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->ndir = h->ndir_user = 0; h->nneu = 0; h->have_body = false;
+  dev_free(&h->d_Ut); dev_free(&h->d_Udt); dev_free(&h->d_Udd); dev_free(&h->d_Ud); dev_free(&h->d_con_zero);
   h->dir_user_dofs.clear(); h->dir_slot.clear();
   for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
   dev_free(&h->d_u_n);
@@ -409,6 +412,18 @@ static int assemble(nls_context *h, bool want_r, bool want_k) {
   return NLS_OK;
 }
 
+// Newton on the acceleration (newmark.jl:75-107): U, Ud follow from the unknown Udd (update_state!), the static
+// operators act on that U, then the inertia terms: R += M Udd (residual.jl:53), K = (dt^2 beta) K + M (jacobian.jl:46-50).
+static int assemble_any(nls_context *h, bool want_r, bool want_k) {
+  if (!h->dyn_on) return assemble(h, want_r, want_k);
+  NLS_TRY(nls_halo_exchange(h, h->d_Udd));
+  NLS_TRY(nls_launch_newmark_state(h, h->dyn_cu, h->dyn_cv));
+  NLS_TRY(assemble(h, want_r, want_k));
+  if (want_r) NLS_TRY(nls_launch_apply_mass(h, h->d_Udd, h->d_R, true));
+  if (want_k) NLS_TRY(nls_launch_scale_add_mass(h, h->dyn_cu, true));
+  return NLS_OK;
+}
+
 static int host_assemble(nls_context *h, double *U, double *R, double *vals) {
   NLS_TRY(check_ready(h, "assemble"));
   if (!U) NLS_FAIL(h, NLS_ERR_ARG, "assemble: null U");
@@ -514,7 +529,7 @@ static int newton_loop(nls_context *h, const nls_newton_opts *o, double *hist, n
   int rc = NLS_OK, nh = 0, its = 0, lin_total = 0;
   NLS_CUDA(h, cudaEventRecord(h->ev0, h->stream));
   NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
-  NLS_TRY(assemble(h, true, true));                                        // :137-138
+  NLS_TRY(assemble_any(h, true, true));                                    // :137-138
   NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
   double norm_r = nls_dev_masked_norm2(h, h->d_R, true, &rc);              // :140-141
   if (rc) return rc;
@@ -540,9 +555,9 @@ static int newton_loop(nls_context *h, const nls_newton_opts *o, double *hist, n
     res->ms_linear += elapsed(h->ev2, h->ev3);
     if (finished) break;
     if (nd > o->dtol) { reason = NLS_REASON_DIVERGED_STEP; finished = true; break; }     // :168-172
-    NLS_TRY(nls_launch_axpy(h, h->nrows, 1.0, h->d_dU, h->d_U));           // :173
+    NLS_TRY(nls_launch_axpy(h, h->nrows, 1.0, h->d_dU, h->dyn_on ? h->d_Udd : h->d_U));   // :173
     NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
-    NLS_TRY(assemble(h, true, !o->type_modified));                         // :174-179
+    NLS_TRY(assemble_any(h, true, !o->type_modified));                     // :174-179
     NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
     norm_r = nls_dev_masked_norm2(h, h->d_R, true, &rc);                   // :180
     if (rc) return rc;
@@ -568,6 +583,135 @@ extern "C" int32_t nls_newton_solve(nls_handle h, const nls_newton_opts *opts, c
   NLS_TRY(newton_loop(h, opts, norm_hist, res));
   NLS_TRY(nls_halo_exchange(h, h->d_U));
   NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, sizeof(double) * h->ndof_local(), cudaMemcpyDeviceToHost, h->stream));
+  if (R) NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+// ---- dynamics: consistent mass, dynamic operators, Newmark step ---------------------
+static int ensure_dyn(nls_context *h) {
+  if (h->d_Udd) return NLS_OK;
+  const size_t nd = (size_t)h->ndof_local();
+  NLS_TRY(dev_alloc(h, &h->d_Ut, nd)); NLS_TRY(dev_alloc(h, &h->d_Udt, nd));
+  NLS_TRY(dev_alloc(h, &h->d_Udd, nd)); NLS_TRY(dev_alloc(h, &h->d_Ud, nd));
+  NLS_TRY(dev_alloc(h, &h->d_con_zero, nd));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_Ut, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_Udt, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_Udd, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_Ud, 0, nd * sizeof(double), h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(h->d_con_zero, 0, nd, h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_set_mass(nls_handle h, double rho, double area) {
+  NLS_ENTER(h);
+  if (!h->have_pattern || !h->have_disc) NLS_FAIL(h, NLS_ERR_STATE, "nls_set_mass: call nls_build_pattern first");
+  if (!(rho > 0.0) || !(area > 0.0)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mass: density and area must be positive");
+  NLS_TRY(ensure_dyn(h));
+  NLS_TRY(dev_alloc(h, &h->d_mass, (size_t)h->nnzb));
+  NLS_TRY(nls_launch_mass_build(h, rho, h->dim == 1 ? area : 1.0));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->mass_rho = rho; h->mass_area = area; h->have_mass = true;
+  return NLS_OK;
+}
+
+#define NEED_MASS(h, who) do { if (!(h)->have_mass) NLS_FAIL(h, NLS_ERR_STATE, who ": call nls_set_mass first"); } while (0)
+
+extern "C" int32_t nls_get_mass(nls_handle h, double *vals) {
+  NLS_ENTER(h);
+  NEED_MASS(h, "nls_get_mass");
+  if (!vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_get_mass: null vals");
+  NLS_TRY(nls_launch_scale_add_mass(h, 0.0, false));
+  NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_apply_mass(nls_handle h, const double *x, double *y) {
+  NLS_ENTER(h);
+  NEED_MASS(h, "nls_apply_mass");
+  if (!x || !y) NLS_FAIL(h, NLS_ERR_ARG, "nls_apply_mass: null vector");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_tmp, x, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_b, y, sizeof(double) * h->nrows, cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(nls_halo_exchange(h, h->d_tmp));
+  NLS_TRY(nls_launch_apply_mass(h, h->d_tmp, h->d_b, true));
+  NLS_CUDA(h, cudaMemcpyAsync(y, h->d_b, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_dynamic_residual(nls_handle h, double *U, const double *Udd, double *R) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_dynamic_residual"));
+  NEED_MASS(h, "nls_dynamic_residual");
+  if (!U || !Udd || !R) NLS_FAIL(h, NLS_ERR_ARG, "nls_dynamic_residual: null argument");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_Udd, Udd, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(assemble(h, true, false));
+  NLS_TRY(nls_halo_exchange(h, h->d_Udd));
+  NLS_TRY(nls_launch_apply_mass(h, h->d_Udd, h->d_R, true));
+  NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, sizeof(double) * h->ndof_local(), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+extern "C" int32_t nls_dynamic_jacobian(nls_handle h, double *U, double scale, double *vals) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_dynamic_jacobian"));
+  NEED_MASS(h, "nls_dynamic_jacobian");
+  if (!U || !vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_dynamic_jacobian: null argument");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(assemble(h, false, true));
+  NLS_TRY(nls_launch_scale_add_mass(h, scale, true));
+  NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, sizeof(double) * h->ndof_local(), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+
+// M x = b on ALL DoFs (newmark.jl:136-140 solves with the full mass matrix, no constraints): Jacobi-PCG
+extern "C" int32_t nls_mass_solve(nls_handle h, double rtol, int32_t maxits, const double *b, double *x, int32_t *its, int32_t *status_out) {
+  NLS_ENTER(h);
+  NEED_MASS(h, "nls_mass_solve");
+  if (!b || !x || maxits < 0) NLS_FAIL(h, NLS_ERR_ARG, "nls_mass_solve: bad arguments");
+  NLS_TRY(nls_launch_scale_add_mass(h, 0.0, false));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_b, b, sizeof(double) * h->nrows, cudaMemcpyHostToDevice, h->stream));
+  std::swap(h->d_con, h->d_con_zero);
+  int li = 0, st = 0; double rr = 0.0;
+  const int rc = nls_pcg_solve(h, rtol, maxits, 0, &li, &rr, &st);
+  std::swap(h->d_con, h->d_con_zero);
+  if (rc) return rc;
+  NLS_CUDA(h, cudaMemcpyAsync(x, h->d_dU, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (its) *its = li;
+  if (status_out) *status_out = st;
+  return NLS_OK;
+}
+
+// One Newmark step: solve!(ts.solver, Udd_prev) with the closures of newmark.jl:75-107 installed, then
+// update_state! (newmark.jl:114-117). Inputs: predictors Ut, Udt (update_predictors!, newmark.jl:109-112) and the
+// initial guess Udd0; outputs: the converged acceleration and U, Ud = update_state!(Udd) (without the Dirichlet
+// overwrite: the reference applies it to a temporary copy, newmark.jl:78,103).
+extern "C" int32_t nls_newmark_solve(nls_handle h, const nls_newton_opts *opts, double beta, double gamma, double dt,
+                                     const double *Ut, const double *Udt, const double *Udd0,
+                                     double *Udd, double *U, double *Ud, double *R, double *norm_hist, nls_newton_result *res) {
+  NLS_ENTER(h);
+  NEED_MASS(h, "nls_newmark_solve");
+  if (!Ut || !Udt || !Udd0 || !Udd || !U || !Ud) NLS_FAIL(h, NLS_ERR_ARG, "nls_newmark_solve: null vector");
+  const size_t nb = sizeof(double) * h->ndof_local();
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_Ut, Ut, nb, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_Udt, Udt, nb, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_Udd, Udd0, nb, cudaMemcpyHostToDevice, h->stream));
+  h->dyn_on = true; h->dyn_cu = dt * dt * beta; h->dyn_cv = dt * gamma;
+  const int rc = newton_loop(h, opts, norm_hist, res);
+  h->dyn_on = false;
+  if (rc) return rc;
+  NLS_TRY(nls_halo_exchange(h, h->d_Udd));
+  NLS_TRY(nls_launch_newmark_state(h, h->dyn_cu, h->dyn_cv));
+  NLS_CUDA(h, cudaMemcpyAsync(Udd, h->d_Udd, nb, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(U, h->d_U, nb, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(Ud, h->d_Ud, nb, cudaMemcpyDeviceToHost, h->stream));
   if (R) NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   return NLS_OK;

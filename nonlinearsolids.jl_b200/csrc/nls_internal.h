@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/nls_b200.h"
@@ -161,6 +162,15 @@ struct nls_context {
   double *d_scal = nullptr;             // small scalar scratch (8 doubles)
   double *h_scal = nullptr;             // pinned
 
+  // dynamics: node-level consistent mass [nnzb], Newmark vectors
+  double *d_mass = nullptr;
+  bool have_mass = false;
+  double mass_rho = 0.0, mass_area = 1.0;
+  double *d_Ut = nullptr, *d_Udt = nullptr, *d_Udd = nullptr, *d_Ud = nullptr;   // predictors, acceleration, velocity
+  bool dyn_on = false;                  // the Newton unknown is the acceleration (newmark.jl:75-107)
+  double dyn_cu = 0.0, dyn_cv = 0.0;    // dt^2 beta, dt gamma
+  uint8_t *d_con_zero = nullptr;        // all-free mask for the unconstrained mass solve
+
   // plastic state [nel][nq]
   double *d_state[9] = {nullptr};       // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
   double *d_u_n = nullptr;              // [nel][nen]
@@ -224,6 +234,11 @@ double nls_dev_masked_norm2(nls_context *h, const double *v, bool masked, int *r
 int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, double *out);
 int nls_launch_axpy(nls_context *h, int64_t n, double a, const double *x, double *y);
 int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int *its, double *relres, int *status);
+
+int nls_launch_mass_build(nls_context *h, double rho, double area);
+int nls_launch_apply_mass(nls_context *h, const double *x, double *y, bool accumulate);
+int nls_launch_scale_add_mass(nls_context *h, double scale, bool scale_existing);
+int nls_launch_newmark_state(nls_context *h, double c_u, double c_v);
 
 int nls_halo_exchange(nls_context *h, double *v);
 int nls_allreduce_sum(nls_context *h, double *dptr, int count);

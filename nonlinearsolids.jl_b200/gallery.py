@@ -59,12 +59,22 @@ class Residual:
         self.material = material
         self.externalforces = list(externalforces)
 
-    def __call__(self, fem, U, R, ctx=None):
+    def __call__(self, fem, U, *args):
+        """(fem, U, R, ctx) static (residual.jl:12-26); (fem, U, Ud, R, ctx) rate form (:29-45, no shipped material
+        is velocity dependent, so it equals the static one); (fem, U, Ud, Udd, R, ctx) dynamic (:48-54)."""
         if not (isinstance(U, np.ndarray) and U.dtype == np.float64 and U.flags.c_contiguous):
             raise TypeError("U must be a contiguous float64 array (it is updated in place)")
+        arrs = [a for a in args if isinstance(a, np.ndarray)]
+        ctx = args[len(arrs)] if len(args) > len(arrs) else None
+        if len(arrs) not in (1, 2, 3):
+            raise TypeError("Residual(fem, U, [Ud, [Udd,]] R, ctx)")
         H = fem.handle(self.material)
         _sync_external_forces(H, fem, self.externalforces, ctx)
-        H.call("nls_residual", dptr(U), dptr(R))
+        if len(arrs) == 3:
+            _ensure_mass(H, fem, self.material)
+            H.call("nls_dynamic_residual", dptr(U), dptr(np.ascontiguousarray(arrs[1], dtype=np.float64)), dptr(arrs[2]))
+        else:
+            H.call("nls_residual", dptr(U), dptr(arrs[-1]))
 
 
 class Jacobian:
@@ -76,11 +86,46 @@ class Jacobian:
         self.material = material
         self.dexternalforces = list(dexternalforces)
 
-    def __call__(self, fem, U, K, ctx=None):
+    def __call__(self, fem, U, *args):
+        """(fem, U, K, ctx) static (jacobian.jl:10-22); (fem, U, Ud, K, ctx) rate form (:25-38); (fem, U, Ud, Udd, K, ctx)
+        dynamic (:42-51): K(U) * dUdd_dU(ctx) + M, ctx a NewmarkTimeStepper."""
         if not (isinstance(U, np.ndarray) and U.dtype == np.float64 and U.flags.c_contiguous):
             raise TypeError("U must be a contiguous float64 array (it is updated in place)")
+        mats = [a for a in args if isinstance(a, (np.ndarray, CSRMatrix))]
+        ctx = args[len(mats)] if len(args) > len(mats) else None
+        if len(mats) not in (1, 2, 3):
+            raise TypeError("Jacobian(fem, U, [Ud, [Udd,]] K, ctx)")
+        K = mats[-1]
         vals = K.vals if isinstance(K, CSRMatrix) else K
-        fem.handle(self.material).call("nls_jacobian", dptr(U), dptr(vals))
+        H = fem.handle(self.material)
+        if len(mats) == 3:
+            if ctx is None or not hasattr(ctx, "dUdd_dU"):
+                raise TypeError("the dynamic Jacobian needs a timestepper context (jacobian.jl:42)")
+            _ensure_mass(H, fem, self.material)
+            H.call("nls_dynamic_jacobian", dptr(U), float(ctx.dUdd_dU()), dptr(vals))
+        else:
+            H.call("nls_jacobian", dptr(U), dptr(vals))
+
+
+def _ensure_mass(H, fem, material):
+    key = (float(material.density()), float(fem.data.get("A", 1.0)))     # mass.jl:9,27: A defaults to 1.0 here
+    if getattr(H, "_mass_key", None) != key:
+        H.call("nls_set_mass", key[0], key[1])
+        H._mass_key = key
+
+
+def assemblemass(material, fem, K):
+    """assemblemass!(material, fem, K) (mass.jl:8-17) for a zeroed K: K = M in CSR."""
+    H = fem.handle(material)
+    _ensure_mass(H, fem, material)
+    H.call("nls_get_mass", dptr(K.vals if isinstance(K, CSRMatrix) else K))
+
+
+def applymass(material, fem, Udd, R):
+    """applymass!(material, fem, U̇̇, R) (mass.jl:26-37): R += M U̇̇."""
+    H = fem.handle(material)
+    _ensure_mass(H, fem, material)
+    H.call("nls_apply_mass", dptr(np.ascontiguousarray(Udd, dtype=np.float64)), dptr(R))
 
 
 def residual_jacobian(material, fem, U, R, K):

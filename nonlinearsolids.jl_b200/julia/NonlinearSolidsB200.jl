@@ -223,4 +223,51 @@ function save_state!(mat::LinearElastoPlasticity1D, fem::FEMModel, U, ts::Abstra
     end
 end
 
+# ---- dynamics (SURVEY 8f-3): gallery/mass.jl, the dynamic Residual/Jacobian methods, NewmarkTimeStepper ----------
+"""Build the device mass once per (density, area): assemblemass! (mass.jl:8-17); `A` defaults to 1.0 there."""
+function sync_mass!(m::B200Model, mat)
+    check(m.h, ccall((:nls_set_mass, libnls), Int32, (Ptr{Cvoid}, Float64, Float64), m.h,
+                     Float64(density(mat)), Float64(get(m.fem.data, :A, 1.0))))
+end
+
+"""assemblemass!(material, model, vals): CSR values of M over the model's pattern (K must be zero on entry)."""
+function assemblemass!(mat, m::B200Model, vals::Vector{Float64})
+    sync_mass!(m, mat)
+    check(m.h, ccall((:nls_get_mass, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}), m.h, vals))
+end
+
+"""applymass!(material, model, U̇̇, R): R += M U̇̇ (mass.jl:26-37)."""
+function applymass!(mat, m::B200Model, Udd::Vector{Float64}, R::Vector{Float64})
+    sync_mass!(m, mat)
+    check(m.h, ccall((:nls_apply_mass, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, Udd, R))
+end
+
+"""One Newmark step on the device: the Newton solve on the acceleration with the closures of newmark.jl:75-107,
+then update_state! (newmark.jl:114-117). Call from a `solve!(ts::NewmarkTimeStepper)` whose solver is a
+B200NewtonSolver, in place of `solve!(ts.solver, ts.U̇̇[step(ts)-1, :])` + `update_state!`:
+
+    a, U, U̇ = newmark_step!(ts.solver, ts.material, ts.β, ts.γ, ts.Δt, ts.Ũ, ts.Ũ̇, ts.U̇̇[step(ts)-1, :])
+"""
+function newmark_step!(s::B200NewtonSolver, mat, β, γ, Δt, Ut::Vector{Float64}, Udt::Vector{Float64}, Udd0::Vector{Float64})
+    sync_material!(s.dev, mat)
+    sync_mass!(s.dev, mat)
+    sync_external_forces!(s.dev, s.residual_fn!.externalforces, s.ctx)
+    sync_boundaries!(s.dev)
+    opts = NewtonOpts(s.type == :modified, s.atol, s.rtol, s.dtol, s.maxits, s.lin_rtol, s.lin_maxits)
+    res = NewtonResult()
+    hist = zeros(s.maxits + 2)
+    n = numdof(s.fem)
+    a, U, Ud = zeros(n), zeros(n), zeros(n)
+    check(s.dev.h, ccall((:nls_newmark_solve, libnls), Int32,
+        (Ptr{Cvoid}, Ref{NewtonOpts}, Float64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{NewtonResult}),
+        s.dev.h, opts, Float64(β), Float64(γ), Float64(Δt), Ut, Udt, Udd0, a, U, Ud, s.R, hist, res))
+    s.converged_reason = REASONS[res.reason + 1]
+    s.iterations = res.iterations
+    s.lin_iterations = res.lin_its_total
+    s.norm_history = hist[1:res.nhist]
+    s.U .= a                                  # solution(solver) is the acceleration, as in the reference
+    return a, U, Ud
+end
+
 end # module

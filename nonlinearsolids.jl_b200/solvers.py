@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import dptr
-from .gallery import Jacobian, Residual, _sync_external_forces
+from .gallery import Jacobian, Residual, _ensure_mass, _sync_external_forces
 from .materials import save_state
 
 
@@ -120,11 +120,11 @@ class NewtonSolver:
 
 
 def set_residual_fn(solver, fn):
-    (solver.solver if isinstance(solver, PseudoTimeStepper) else solver).residual_fn = fn
+    (solver.solver if isinstance(solver, (PseudoTimeStepper, NewmarkTimeStepper)) else solver).residual_fn = fn
 
 
 def set_jacobian_fn(solver, fn):
-    (solver.solver if isinstance(solver, PseudoTimeStepper) else solver).jacobian_fn = fn
+    (solver.solver if isinstance(solver, (PseudoTimeStepper, NewmarkTimeStepper)) else solver).jacobian_fn = fn
 
 
 def set_ctx(solver, ctx):
@@ -216,6 +216,109 @@ class PseudoTimeStepper:
             self.U[self.step, :] = self.solver.solution()
             r[self.step, :] = self.solver.residual()
             num_its[self.step] = self.solver.iterations
+            self.poststep(self.U[self.step, :])
+            for f in self.postprocess:
+                f(self, self.U[self.step, :])
+
+
+class NewmarkTimeStepper(PseudoTimeStepper):
+    """NewmarkTimeStepper(solver, material; beta, gamma, dt, maxtime) (timesteppers/newmark.jl:5-53): implicit
+    dynamics. Newton runs on the acceleration: the closures of newmark.jl:75-107 (update_state! -> static
+    Residual/Jacobian of U -> inertia terms M a and dt^2 beta K + M) and the Newton loop all stay on the device
+    (nls_newmark_solve); the host keeps the histories U, Ud, Udd (maxsteps x ndof) like the reference.
+
+    Kept from the reference: the solve is restricted to the free DoFs, so constrained entries of the acceleration
+    keep their initial-guess values, and Dirichlet values only enter through the copy of U the operators act on
+    (newmark.jl:78,103 apply them to a temporary). Two deviations from the text of solve! (newmark.jl:124-141),
+    which as written discards its own results: U0 and Ud0 are kept (the reference's first residual call runs
+    update_state! with zero predictors over them), and with consistent_a0 (default) the initial acceleration
+    solves M a0 = -R(U0) -- the reference writes that residual into a temporary and so always starts from a0 = 0,
+    which consistent_a0=False reproduces."""
+
+    def __init__(self, solver, material, beta=0.25, gamma=0.5, dt=0.01, t=0.0, maxtime=1.0, maxsteps=None,
+                 consistent_a0=True):
+        ms = int(round((maxtime - t) / dt + 1)) if maxsteps is None else maxsteps     # newmark.jl:21 uses round
+        super().__init__(solver, dt=dt, t=t, maxtime=maxtime, maxsteps=ms)
+        self._material = material
+        self.beta, self.gamma = float(beta), float(gamma)
+        self.consistent_a0 = consistent_a0
+        n = solver.fem.ndof
+        self.Ut, self.Udt = np.zeros(n), np.zeros(n)
+        self.Ud = np.zeros((self.maxsteps, n))
+        self.Udd = np.zeros((self.maxsteps, n))
+
+    @property
+    def material(self):
+        return self._material
+
+    def dUdd_dU(self):
+        """∂U̇̇∂U(ts) (newmark.jl:56-58)."""
+        return self.dt ** 2 * self.beta
+
+    def update_predictors(self, n=None):
+        """update_predictors!(ts, n) (newmark.jl:109-112)."""
+        n = self.step if n is None else n
+        self.Ut[:] = self.U[n] + self.dt * self.Ud[n] + self.dt ** 2 * (0.5 - self.beta) * self.Udd[n]
+        self.Udt[:] = self.Ud[n] + self.dt * (1 - self.gamma) * self.Udd[n]
+
+    def velocity(self):
+        return self.Ud
+
+    def acceleration(self):
+        return self.Udd
+
+    def _handle(self):
+        fem, mat = self.solver.fem, self._material
+        H = fem.handle(mat)
+        _ensure_mass(H, fem, mat)
+        return H
+
+    def solve(self, U0=None, Ud0=None, Udd0=None):
+        """solve!(ts, U0, U̇0, U̇̇0) (newmark.jl:124-156). Steps are 0-based: row 0 holds the initial state."""
+        sv = self.solver
+        fem = sv.fem
+        n = fem.ndof
+        if not isinstance(sv.residual_fn, Residual) or not isinstance(sv.jacobian_fn, Jacobian):
+            raise RuntimeError("set_residual_fn/set_jacobian_fn with gallery Residual/Jacobian functors first")
+        H = self._handle()
+        r = self.getoutputarray("residual")
+        num_its = self.getoutputarray("num_its", 1)
+        self.U[self.step] = 0.0 if U0 is None else U0
+        self.Ud[self.step] = 0.0 if Ud0 is None else Ud0
+        self.Udd[self.step] = 0.0 if Udd0 is None else Udd0
+        self.t0 = self.t
+        num_its[self.step] = 0
+        if self.consistent_a0:      # M a0 = Fext(t0) - Fint(U0)  (newmark.jl:133-140)
+            _sync_external_forces(H, fem, sv.residual_fn.externalforces, self)
+            R0, Uc = np.zeros(fem.nrows), np.ascontiguousarray(self.U[self.step].copy())
+            H.call("nls_residual", dptr(Uc), dptr(R0))
+            a0, its, st = np.zeros(n), C.c_int32(0), C.c_int32(0)
+            H.call("nls_mass_solve", 1e-14, 100000, dptr(np.ascontiguousarray(-R0)), dptr(a0), C.byref(its), C.byref(st))
+            if st.value != 0:
+                raise RuntimeError("mass solve for the initial acceleration did not converge")
+            self.Udd[self.step] = a0
+        opts = _lib.NewtonOpts(int(sv.type == "modified"), sv.atol, sv.rtol, sv.dtol, sv.maxits, sv.lin_rtol, sv.lin_maxits)
+        while self.t < self.maxtime and self.step < self.maxsteps - 1:
+            self.update_predictors(self.step)
+            self.step_(self.dt)
+            H = self._handle()                  # pushes the boundary values updateboundaries! just changed
+            _sync_external_forces(H, fem, sv.residual_fn.externalforces, self)
+            res = _lib.NewtonResult()
+            hist = np.zeros(sv.maxits + 2)
+            a, U, Ud, R = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(fem.nrows)
+            H.call("nls_newmark_solve", C.byref(opts), self.beta, self.gamma, self.dt, dptr(self.Ut), dptr(self.Udt),
+                   dptr(np.ascontiguousarray(self.Udd[self.step - 1])), dptr(a), dptr(U), dptr(Ud), dptr(R), dptr(hist), C.byref(res))
+            sv.converged_reason = _REASONS[res.reason]
+            sv.iterations, sv.lin_iterations = res.iterations, res.lin_its_total
+            sv.norm_history = hist[:res.nhist].copy()
+            sv.U[:], sv.R[:] = a, R
+            if not is_converged(sv, sv.allow_maxits):
+                self.trim()
+                return
+            self.Udd[self.step] = a
+            r[self.step, :] = R
+            num_its[self.step] = sv.iterations
+            self.U[self.step], self.Ud[self.step] = U, Ud          # update_state!(ts, Udd) (newmark.jl:114-117)
             self.poststep(self.U[self.step, :])
             for f in self.postprocess:
                 f(self, self.U[self.step, :])

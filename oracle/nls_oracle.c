@@ -493,6 +493,56 @@ static void orc_body_force(const orc_model *mo, double *Fext) {
   }
 }
 
+/* Consistent mass: gallery/mass.jl:2-17 (assemblemass!) and :19-37 (applymass!).
+ * 1-D: m_e = integrate(Q, xi -> N N' * A * rho * J), J = length(e)/2, product order ((N_a N_b) A) rho) J, then * w_q,
+ * summed over q ascending; M[nodes,nodes] += m_e in element order. `area` is the caller's fem.data[:A] for the
+ * mass (mass.jl:9,27 default 1.0 -- not the 3e-4 default of the internal force).
+ * Q1 (builder-defined, same structure): m_ab = sum_q ((N_a N_b) rho) (w_q det(dX/dxi)), M_{ai,bk} = delta_ik m_ab.
+ * Output: node-level dense matrix Mn[nn][nn] (the dim x dim expansion is the caller's). */
+void orc_mass_nodes(const orc_model *mo, double rho, double area, double *Mn) {
+  int dim = mo->dim, nen = mo->nen;
+  int64_t nn = mo->nn;
+  for (int64_t i = 0; i < nn * nn; ++i) Mn[i] = 0.0;
+  if (dim == 1) {
+    double nodes[ORC_MAXN], w[ORC_MAXN], xq[ORC_MAXQ], wq[ORC_MAXQ], N[ORC_MAXQ][ORC_MAXN];
+    orc_lagrange_nodes(mo->p, 0, nodes); orc_lagrange_weights(nen, nodes, w); orc_gauss(mo->nq, xq, wq);
+    for (int q = 0; q < mo->nq; ++q) orc_shape_N(nen, nodes, w, xq[q], N[q]);
+    for (int64_t e = 0; e < mo->nel; ++e) {
+      double J = orc_el_dxdxi(mo, e);
+      for (int a = 0; a < nen; ++a)
+        for (int b = 0; b < nen; ++b) {
+          double s = 0.0;
+          for (int q = 0; q < mo->nq; ++q) { double v = ((((N[q][a] * N[q][b]) * area) * rho) * J) * wq[q]; s = (q == 0) ? v : s + v; }
+          Mn[(int64_t)mo->conn[e * nen + a] * nn + mo->conn[e * nen + b]] += s;
+        }
+    }
+    return;
+  }
+  orc_tabq1 t; orc_tabq1_init(mo, &t);
+  double nodes[2], bw[2], xq[ORC_MAXQ], wq[ORC_MAXQ], N1[2][2];
+  orc_lagrange_nodes(1, 0, nodes); orc_lagrange_weights(2, nodes, bw); orc_gauss(2, xq, wq);
+  for (int q = 0; q < 2; ++q) orc_shape_N(2, nodes, bw, xq[q], N1[q]);
+  for (int64_t e = 0; e < mo->nel; ++e) {
+    const int32_t *c = mo->conn + e * nen;
+    double me[8][8];
+    for (int a = 0; a < nen; ++a) for (int b = 0; b < nen; ++b) me[a][b] = 0.0;
+    for (int q = 0; q < t.nqp; ++q) {
+      double J[9] = {0}, Ji[9], Nq[8];
+      for (int a = 0; a < nen; ++a)
+        for (int d = 0; d < dim; ++d)
+          for (int D = 0; D < dim; ++D) J[d * dim + D] += mo->coords[(int64_t)c[a] * dim + d] * t.dN[q][a][D];
+      double wd = t.w[q] * orc_inv(dim, J, Ji);
+      for (int a = 0; a < nen; ++a) {
+        double Na = 1.0;
+        for (int d = 0; d < dim; ++d) Na = (d == 0) ? N1[(q >> d) & 1][(a >> d) & 1] : Na * N1[(q >> d) & 1][(a >> d) & 1];
+        Nq[a] = Na;
+      }
+      for (int a = 0; a < nen; ++a) for (int b = 0; b < nen; ++b) me[a][b] += ((Nq[a] * Nq[b]) * rho) * wd;
+    }
+    for (int a = 0; a < nen; ++a) for (int b = 0; b < nen; ++b) Mn[(int64_t)c[a] * nn + c[b]] += me[a][b];
+  }
+}
+
 typedef struct { orc_model *mo; double *U, *R; const orc_sink *K; const orc_tab1d *t1; const orc_tabq1 *tq; int nth; } orc_asm_ctx;
 
 static void orc_assemble_range(void *vc, int64_t lo, int64_t hi, int tid) {

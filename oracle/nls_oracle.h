@@ -112,6 +112,8 @@ void orc_element(const orc_model *m, int64_t e, const double *ue, double *fe, do
 
 /* ---- linear algebra ---- */
 int32_t orc_dense_solve(int64_t n, double *A /*row-major, destroyed*/, double *b /*in: rhs, out: x*/);
+/* consistent mass at node level, gallery/mass.jl:2-17 (dense nn x nn; small cases only) */
+void orc_mass_nodes(const orc_model *mo, double rho, double area, double *Mn);
 void orc_spmv(int64_t n, const int64_t *rowptr, const int32_t *colind, const double *vals, const double *x, double *y, int32_t nthreads);
 int32_t orc_pcg(int64_t n, const int64_t *rowptr, const int32_t *colind, const double *vals,
                 const uint8_t *constrained, const double *b, double *x, double rtol, int32_t maxits,

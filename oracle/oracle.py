@@ -262,6 +262,92 @@ class OracleModel:
                     lin_its=res.lin_its_total, hist=hist[:res.nhist].copy(),
                     norm_r=res.norm_r, norm_r0=res.norm_r0)
 
+    # ---- dynamics: gallery/mass.jl, gallery/residual.jl:48-54, gallery/jacobian.jl:42-51, timesteppers/newmark.jl ----
+    def mass_dense(self, rho, area=1.0):
+        """assemblemass! into a zero matrix (mass.jl:8-17): dense ndof x ndof, M_{ai,bk} = delta_ik m_ab."""
+        Mn = np.zeros((self.nn, self.nn))
+        lib().orc_mass_nodes(C.byref(self.m), C.c_double(rho), C.c_double(area), _d(Mn))
+        return np.kron(Mn, np.eye(self.dim))
+
+    def mass_csr(self, rho, area=1.0):
+        rowptr, colind = self.pattern()
+        M = self.mass_dense(rho, area)
+        vals = np.zeros(len(colind))
+        for i in range(self.ndof):
+            vals[rowptr[i]:rowptr[i + 1]] = M[i, colind[rowptr[i]:rowptr[i + 1]]]
+        return vals
+
+    def dynamic_residual(self, U, Udd, rho, area=1.0):
+        """Residual dynamic method (residual.jl:48-54): static residual, then applymass!(U̇̇) added to R."""
+        Ud, R = self.residual(U)
+        return Ud, R + self.mass_dense(rho, area) @ np.asarray(Udd, dtype=np.float64)
+
+    def dynamic_jacobian_dense(self, U, scale, rho, area=1.0):
+        """Jacobian dynamic method (jacobian.jl:42-51): K .*= dUdd/dU scale, then assemblemass! added."""
+        return self.jacobian_dense(U) * scale + self.mass_dense(rho, area)
+
+    def newmark(self, rho, dt, maxtime, beta=0.25, gamma=0.5, area=1.0, U0=None, Ud0=None, bc_update=None,
+                rtol=1e-16, atol=1e-16, dtol=1e6, maxits=100, consistent_a0=True):
+        """solve!(ts::NewmarkTimeStepper, U0, U̇0, U̇̇0) (newmark.jl:124-156) with dense linear algebra (small cases).
+        Newton runs on the acceleration (closures of newmark.jl:75-107, loop of newton_fem.jl:132-190).
+        Semantics kept from the reference: the solve is on the free DoFs only, so constrained entries of U̇̇ keep
+        their initial-guess values; Dirichlet values enter through the copy of U the operators work on.
+        Deviations from the text of newmark.jl, both documented in DESIGN.md: U0/U̇0 are kept (the reference's first
+        residual call runs update_state! with zero predictors and overwrites them), and with consistent_a0 the
+        initial acceleration solves M a0 = -R(U0) (the reference writes that residual into a temporary and ends up
+        with a0 = 0; consistent_a0=False reproduces that).
+        bc_update(t) -> (dir_vals, neu_vals) or None updates the time-dependent boundaries (step!, types.jl:68-72)."""
+        n = self.ndof
+        nsteps = int(round((maxtime - 0.0) / dt + 1))
+        U = np.zeros((nsteps, n)); Ud = np.zeros((nsteps, n)); Udd = np.zeros((nsteps, n))
+        its = np.zeros(nsteps, dtype=int); res = np.zeros((nsteps, n))
+        if U0 is not None: U[0] = U0
+        if Ud0 is not None: Ud[0] = Ud0
+        M = self.mass_dense(rho, area)
+        con = self.constrained_mask().astype(bool)
+        free = ~con
+        if consistent_a0:
+            _, R0 = self.residual(U[0])
+            Udd[0] = np.linalg.solve(M, -R0)
+        t, step = 0.0, 0
+        s = dt * dt * beta
+        while t < maxtime and step < nsteps - 1:
+            Ut = U[step] + dt * Ud[step] + dt * dt * (0.5 - beta) * Udd[step]
+            Udt = Ud[step] + dt * (1 - gamma) * Udd[step]
+            t += dt; step += 1
+            if bc_update is not None:
+                dv, nv = bc_update(t)
+                if dv is not None: self.dir_vals[:] = dv
+                if nv is not None: self.neu_vals[:] = nv
+            a = Udd[step - 1].copy()
+            def resid(a):
+                Uc, R = self.residual(Ut + s * a)
+                return R + M @ a
+            R = resid(a)
+            nr = np.linalg.norm(R[free]); nr0 = nr if nr > np.finfo(float).eps else 1.0
+            k = 0; reason = "NOT_YET_CONVERGED"
+            while k < maxits:
+                if nr / nr0 < rtol: reason = "CONVERGED_RELATIVE"; break
+                if nr < atol: reason = "CONVERGED_ABSOLUTE"; break
+                K = self.jacobian_dense(Ut + s * a) * s + M
+                d = np.zeros(n)
+                d[free] = np.linalg.solve(K[np.ix_(free, free)], -R[free])
+                if np.linalg.norm(d) > dtol: reason = "DIVERGED_STEP"; break
+                a = a + d
+                R = resid(a)
+                nr = np.linalg.norm(R[free]); k += 1
+            else:
+                reason = "DIVERGED_MAXITS"
+            if k >= maxits and not reason.startswith("CONV") and reason != "DIVERGED_STEP": reason = "DIVERGED_MAXITS"
+            if not reason.startswith("CONVERGED"):
+                return dict(U=U[:step + 1], Ud=Ud[:step + 1], Udd=Udd[:step + 1], num_its=its[:step + 1], residual=res[:step + 1],
+                            reason=reason, steps=step)
+            Udd[step] = a; res[step] = R; its[step] = k
+            U[step] = Ut + s * a
+            Ud[step] = Udt + dt * gamma * a
+        return dict(U=U[:step + 1], Ud=Ud[:step + 1], Udd=Udd[:step + 1], num_its=its[:step + 1], residual=res[:step + 1],
+                    reason="CONVERGED", steps=step)
+
     def partition(self, nranks, node_off, rank):
         off = np.ascontiguousarray(node_off, dtype=np.int64)
         ne, ng = C.c_int64(0), C.c_int64(0)

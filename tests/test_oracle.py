@@ -384,3 +384,50 @@ def test_distributed_force_oracle(orc, nls):
     om.set_body_force([0.5, -2.0, 0.25])
     _, R = om.residual(np.zeros(m2.nn * 3))
     assert np.allclose(-R.reshape(-1, 3).sum(axis=0), [0.5, -2.0, 0.25], rtol=1e-13)   # unit cube volume
+
+
+# ---- dynamics: consistent mass and Newmark restatement ---------------------------------------
+def test_mass_known_answers(orc):
+    """mass.jl:2-17 on one 2-node element: rho A L / 6 [[2,1],[1,2]]; any p with exact quadrature: entries sum to
+    rho A L (partition of unity); Q1: sum of the node-level mass = rho |Omega|."""
+    conn = np.array([[0, 1]], dtype=np.int32)
+    om = orc.OracleModel(1, conn, np.array([0.0, 2.0]), p=1, nq=2, mat_kind=orc.MAT_LINEAR, mat=(1.0,), area=1.0)
+    assert np.allclose(om.mass_dense(3.0, 0.5), 3.0 * 0.5 * 2.0 / 6.0 * np.array([[2, 1], [1, 2]]), rtol=1e-15, atol=0)
+    for p, q in [(2, 3), (3, 4), (4, 5)]:
+        nel = 3
+        nn = nel * p + 1
+        conn = np.array([[e * p + a for a in range(p + 1)] for e in range(nel)], dtype=np.int32)
+        X = np.linspace(0.0, 1.5, nn)
+        om = orc.OracleModel(1, conn, X, p=p, nq=q, mat_kind=orc.MAT_LINEAR, mat=(1.0,), area=1.0)
+        M = om.mass_dense(2.0, 0.25)
+        assert abs(M.sum() - 2.0 * 0.25 * 1.5) <= 1e-14 and np.allclose(M, M.T, atol=1e-16)
+    n = 4
+    g = np.arange(n * n).reshape(n, n)
+    conn = np.array([[g[j, i], g[j, i + 1], g[j + 1, i], g[j + 1, i + 1]] for j in range(n - 1) for i in range(n - 1)], dtype=np.int32)
+    xs = np.linspace(0, 1, n)
+    X = np.array([[x, y] for y in xs for x in xs])
+    om = orc.OracleModel(2, conn, X, mat_kind=orc.MAT_NEOHOOKEAN, mat=(1.0, 1.0))
+    M = om.mass_dense(1.5)
+    assert abs(M.sum() - 1.5 * 2) <= 1e-14 and np.allclose(M, M.T, atol=1e-16)
+
+
+def test_newmark_linear_energy_conservation(orc):
+    """Average-acceleration Newmark (beta = 1/4, gamma = 1/2) conserves 1/2 v'Mv + 1/2 u'Ku exactly for a linear
+    undamped system; the restated stepper (newmark.jl:109-155) must too, and the first Newton iteration must
+    converge the linear problem (1 iteration per step)."""
+    nel, E, rho, A = 5, 4.0, 1.5, 1.0
+    conn = np.array([[e, e + 1] for e in range(nel)], dtype=np.int32)
+    X = np.linspace(0.0, 1.0, nel + 1)
+    om = orc.OracleModel(1, conn, X, p=1, nq=2, mat_kind=orc.MAT_LINEAR, mat=(E,), area=A)
+    om.set_dirichlet([0], [0.0])
+    # released from rest position with an initial velocity (zero at the clamp): R(U0) = 0, so a0 = 0 on every DoF and the
+    # clamped entry of the acceleration, which the reference never solves for, stays zero
+    out = om.newmark(rho, 0.01, 0.2, area=A, Ud0=0.01 * X, rtol=1e-9, atol=1e-14, maxits=5)
+    assert out["reason"] == "CONVERGED" and out["steps"] == 20
+    assert np.all(out["num_its"][1:] == 1)
+    M = om.mass_dense(rho, A)
+    K = om.jacobian_dense(np.zeros(nel + 1))
+    free = np.arange(1, nel + 1)
+    en = [0.5 * v[free] @ M[np.ix_(free, free)] @ v[free] + 0.5 * u[free] @ K[np.ix_(free, free)] @ u[free]
+          for u, v in zip(out["U"], out["Ud"])]
+    assert max(en) - min(en) <= 1e-12 * en[0] and en[0] > 0
