@@ -177,6 +177,8 @@ def run_ours(args):
         H.call("nls_set_option", b"assembly", args.assembly)
     if args.gather_ctas:
         H.call("nls_set_option", b"gather_ctas", args.gather_ctas)
+    scheme = L.nls_assembly_scheme(H.h)
+    sys.stderr.write("rank %d: assembly scheme %d (0 atomic, 1 gather, 2 element records)\n" % (rank, scheme))
     nrows, nnz = C.c_int64(0), C.c_int64(0)
     H.call("nls_pattern_size", C.byref(nrows), C.byref(nnz))
     nrows, nnz = nrows.value, nnz.value

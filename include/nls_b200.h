@@ -197,6 +197,9 @@ int32_t nls_timer_start(nls_handle h);       /* CUDA event on the library's stre
 int32_t nls_timer_stop(nls_handle h, float *ms);
 int32_t nls_flush_l2(nls_handle h);          /* overwrite a >L2-sized scratch buffer */
 int64_t nls_kernel_launches(nls_handle h);   /* kernels launched by this handle so far */
+/* which assembly scheme the next nls_*assemble / residual / jacobian call uses for this model:
+ * 0 atomic scatter, 1 shared-memory gather (2-D), 2 element records + row owners; -1 without a pattern */
+int32_t nls_assembly_scheme(nls_handle h);
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
  * {staging wait, phase 1a, phase 1b, phase 2, clusters, 0, 0, 0}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "nls_kernel_launches": (C.c_int64, [_H]),
     "nls_set_option": (C.c_int32, [_H, C.c_char_p, C.c_int32]),
     "nls_debug_counters": (C.c_int32, [_H, _lp]),
+    "nls_assembly_scheme": (C.c_int32, [_H]),
     "nls_partition": (C.c_int32, [C.c_int32, C.c_int64, _ip, C.c_int32, _lp, C.c_int32,
                                   _lp, _lp, _lp, _lp, _lp, _lp]),
     "nls_set_halo": (C.c_int32, [_H, C.c_int64, C.c_int32, _ip, _lp, _ip, _lp, _ip]),

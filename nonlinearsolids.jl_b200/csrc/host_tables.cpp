@@ -289,13 +289,16 @@ static inline uint64_t spread_bits(uint64_t v, int dim) {
 }
 
 void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
-                           const double *coords, int nc, AsmPlan &plan) {
+                           const double *coords, int nc, AsmPlan &plan, const int *tile) {
   plan = AsmPlan();
   plan.nc = nc;
   if (n_owned == 0) { plan.eptr.assign(1, 0); return; }
-  // Morton keys of the owned nodes. Coordinates are binned on a grid with about one node per
-  // bin (bins per axis = nodes^(1/dim) scaled by the aspect ratio), so on a structured mesh the
-  // bin index is the grid index and a Morton tile (key >> tile_bits) is an 8x8 (4x4x4) node tile.
+  // Keys of the owned nodes. Coordinates are binned on a grid with about one node per bin (bins per
+  // axis = nodes^(1/dim) scaled by the aspect ratio), so on a structured mesh the bin index is the grid
+  // index. Without `tile`, keys are Morton codes and a tile (key >> tile_bits) is an 8x8 (4x4x4) node
+  // tile for nc = 64. With `tile` = {tx, ty, tz} the tiles are tx x ty (x tz) bins, ordered
+  // lexicographically: the 2-D kernel asks for 15 x 7 nodes, whose 16 x 8 = 128 touching elements fill
+  // its 128 threads exactly.
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int64_t a = 0; a < n_owned; ++a)
     for (int d = 0; d < dim; ++d) { lo[d] = std::min(lo[d], coords[a * dim + d]); hi[d] = std::max(hi[d], coords[a * dim + d]); }
@@ -304,15 +307,27 @@ void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, i
   const double hbin = std::pow(vol / (double)n_owned, 1.0 / dim);   // ~ node spacing
   int tile_bits = 0;
   while ((1 << tile_bits) < nc) ++tile_bits;                        // nc = 64 -> 6 bits: 8x8 or 4x4x4
+  uint64_t ntile[3] = {1, 1, 1};
+  if (tile) {
+    tile_bits = 24;                                                 // key = tile id << 24 | position inside the tile
+    for (int d = 0; d < dim; ++d) ntile[d] = (uint64_t)std::floor((hi[d] - lo[d]) / hbin + 0.5) / (uint64_t)tile[d] + 1;
+  }
   std::vector<std::pair<uint64_t, int32_t>> keyed((size_t)n_owned);
   for (int64_t a = 0; a < n_owned; ++a) {
-    uint64_t key = 0;
+    uint64_t key = 0, tid_ = 0, within = 0, tmul = 1, wmul = 1;
     for (int d = 0; d < dim; ++d) {
       double b = std::floor((coords[a * dim + d] - lo[d]) / hbin + 0.5);
       if (b < 0) b = 0;
       if (b > 2097151.0) b = 2097151.0;
-      key |= spread_bits((uint64_t)b, dim) << d;
+      if (tile) {
+        const uint64_t bi = (uint64_t)b, t = bi / (uint64_t)tile[d];
+        tid_ += std::min<uint64_t>(t, ntile[d] - 1) * tmul; tmul *= ntile[d];
+        within += (bi % (uint64_t)tile[d]) * wmul; wmul *= (uint64_t)tile[d];
+      } else {
+        key |= spread_bits((uint64_t)b, dim) << d;
+      }
     }
+    if (tile) key = (tid_ << 24) | std::min<uint64_t>(within, (1u << 24) - 1);
     keyed[a] = {key, (int32_t)a};
   }
   std::sort(keyed.begin(), keyed.end());
@@ -361,7 +376,8 @@ extern "C" int32_t nls_plan_stats(int32_t dim, int32_t nen, int64_t nelem, const
   if (dim < 1 || dim > 3 || nen < 1 || nelem < 0 || nnodes < 1 || n_owned_nodes < 0 || n_owned_nodes > nnodes || !coords ||
       !out4 || nc < 1 || (nelem > 0 && !conn0)) return NLS_ERR_ARG;
   AsmPlan plan;
-  nls_host_cluster_plan(dim, nen, nelem, conn0, nnodes, n_owned_nodes, coords, nc, plan);
+  const int tile2d[3] = {15, 7, 1};
+  nls_host_cluster_plan(dim, nen, nelem, conn0, nnodes, n_owned_nodes, coords, nc, plan, (dim == 2 && nc == 105) ? tile2d : nullptr);
   out4[0] = plan.ncl; out4[1] = plan.max_elems; out4[2] = (int64_t)plan.elems.size(); out4[3] = plan.max_adj;
   return NLS_OK;
 }

@@ -21,8 +21,12 @@
 #include <cstring>
 #include "asm_common.cuh"
 
-#define G2_NC 128         // owned nodes per cluster (16 x 8 tile -> 17 x 9 = 153 elements, 19.5 % evaluated twice)
-#define G2_THREADS 160
+#define G2_TX 15
+#define G2_TY 7
+#define G2_NC (G2_TX * G2_TY)   // owned nodes per cluster: a 15 x 7 tile is touched by 16 x 8 = 128 elements -- one per thread,
+                                // four full warps (one per SM sub-partition), 22 % of the elements evaluated twice
+#define G2_NCP 112              // padded stride of the per-node plan arrays (16-byte rows)
+#define G2_THREADS 128
 #define G2_KS 50          // doubles per element in shared memory: 10 symmetric 2x2 blocks (40) + f_e (8) + 2 pad;
                           // 25 x 16 B (odd) -> the reduce-scatter's STS.128 are conflict-free
 #define G2_MAXSRC 8       // most elements around one node the packed block lists can hold
@@ -32,13 +36,13 @@ struct GatherArgs {
   int maxt, maxe, maxb, nsw;  // padded strides: touched nodes, elements, CSR blocks; source words per block (2 or 4)
   const int32_t *tn;      // [ncl][4 + maxt]: {nt, ne, nb, 0}, node ids
   const uint32_t *lconn;  // [ncl][maxe]: 4 local node indices (bytes) into the touched-node list
-  const int32_t *cn;      // [ncl][G2_NC] owned node ids (-1 = none)
-  const int64_t *b0;      // [ncl][G2_NC] block-row start of the node
-  const int32_t *deg;     // [ncl][G2_NC] block-row length
+  const int32_t *cn;      // [ncl][G2_NCP] owned node ids (-1 = none)
+  const int64_t *b0;      // [ncl][G2_NCP] block-row start of the node
+  const int32_t *deg;     // [ncl][G2_NCP] block-row length
   const uint32_t *bsrc;   // [ncl][1 + nsw][maxb]: word 0 = nl | jb << 8; then 16-bit source codes, two per word:
                           //   offset of the 2x2 block in Ks (15 bits) | transposed << 15; unused sources point at the
                           //   zero record Ks[maxe]
-  const uint16_t *rsrc;   // [ncl][G2_NC][G2_MAXSRC]: offsets in Ks of the node's f_e pairs, ascending element; unused -> zero record
+  const uint16_t *rsrc;   // [ncl][G2_NCP][G2_MAXSRC]: offsets in Ks of the node's f_e pairs, ascending element; unused -> zero record
   unsigned long long *prof; // optional per-phase cycle counters (nls_set_option "profile_phases"), else NULL
 };
 
@@ -127,8 +131,8 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   double *Tsm = Ks + (size_t)(P.maxe + 1) * G2_KS;                                    // 40 doubles: dN[4][4][2], w[4], pad
   int32_t *tnb = reinterpret_cast<int32_t *>(Tsm + 40);                               // [3][tn_words]
   unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [2] stage buffers
-  const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NC * 8, b_cn = b_lc + (size_t)P.maxe * 4,
-               b_dg = b_cn + G2_NC * 4, b_rs = b_dg + G2_NC * 4, b_bs = b_rs + G2_NC * G2_MAXSRC * 2,
+  const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NCP * 8, b_cn = b_lc + (size_t)P.maxe * 4,
+               b_dg = b_cn + G2_NCP * 4, b_rs = b_dg + G2_NCP * 4, b_bs = b_rs + G2_NCP * G2_MAXSRC * 2,
                b_size = b_bs + (size_t)(1 + P.nsw) * P.maxb * 4;
   const int tid = threadIdx.x;
   if (tid < 32) Tsm[tid] = T.dN[tid >> 3][(tid >> 1) & 3][tid & 1];
@@ -154,13 +158,13 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
         cp_async16(xu + 4 * t, A.coords + 2 * (int64_t)id);
         cp_async16(xu + 4 * t + 2, A.U + 2 * (int64_t)id);
       }
-      for (int w = tid * 2; w < G2_NC; w += G2_THREADS * 2) cp_async16(B + b_b0 + w * 8, P.b0 + c * G2_NC + w);
+      for (int w = tid * 2; w < G2_NCP; w += G2_THREADS * 2) cp_async16(B + b_b0 + w * 8, P.b0 + c * G2_NCP + w);
       for (int w = tid * 4; w < P.maxe; w += G2_THREADS * 4) cp_async16(B + b_lc + w * 4, P.lconn + c * P.maxe + w);
-      for (int w = tid * 4; w < G2_NC; w += G2_THREADS * 4) {
-        cp_async16(B + b_cn + w * 4, P.cn + c * G2_NC + w);
-        cp_async16(B + b_dg + w * 4, P.deg + c * G2_NC + w);
+      for (int w = tid * 4; w < G2_NCP; w += G2_THREADS * 4) {
+        cp_async16(B + b_cn + w * 4, P.cn + c * G2_NCP + w);
+        cp_async16(B + b_dg + w * 4, P.deg + c * G2_NCP + w);
       }
-      for (int w = tid * 8; w < G2_NC * G2_MAXSRC; w += G2_THREADS * 8) cp_async16(B + b_rs + w * 2, P.rsrc + c * (G2_NC * G2_MAXSRC) + w);
+      for (int w = tid * 8; w < G2_NCP * G2_MAXSRC; w += G2_THREADS * 8) cp_async16(B + b_rs + w * 2, P.rsrc + c * (G2_NCP * G2_MAXSRC) + w);
       const int nbw = (1 + P.nsw) * P.maxb;   // uint32 entries, multiple of 4
       for (int w = tid * 4; w < nbw; w += G2_THREADS * 4) cp_async16(B + b_bs + w * 4, P.bsrc + c * nbw + w);
     }
@@ -179,8 +183,11 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   for (int64_t c = c0; c < P.ncl; c += cstep, ++k) {
     const long long tp0 = P.prof ? clock64() : 0;
     issue_A(c + 2 * cstep, k + 2);
+    const long long tq0 = P.prof ? clock64() : 0;
     cp_async_wait<1>();          // everything but A(k+2): A(k+1) and B(k) have landed
+    const long long tq1 = P.prof ? clock64() : 0;
     __syncthreads();
+    const long long tq2 = P.prof ? clock64() : 0;
     issue_B(c + cstep, k + 1);   // flies while cluster k is computed
     const long long tp1 = P.prof ? clock64() : 0;
 
@@ -218,25 +225,51 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
       const int64_t *b0v = reinterpret_cast<const int64_t *>(B + b_b0);
       const int32_t *dgv = reinterpret_cast<const int32_t *>(B + b_dg);
       const unsigned ks_s = (unsigned)__cvta_generic_to_shared(Ks);
-      for (int blk = tid; blk < nb; blk += G2_THREADS) {
-        const uint32_t w0 = bs[blk];
-        const int nl = w0 & 0xff, jb = (w0 >> 8) & 0xff;
-        double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
-        for (int sw = 0; sw < P.nsw; ++sw) {
-          const uint32_t cw = bs[(1 + sw) * P.maxb + blk];
-          const unsigned a0 = ks_s + ((cw & 0x7fffu) << 3), a1 = ks_s + ((cw >> 13) & 0x3fff8u);
-          double2 x0, x1, y0, y1;
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0.x), "=d"(x0.y) : "r"(a0));
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(x1.x), "=d"(x1.y) : "r"(a0));
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y0.x), "=d"(y0.y) : "r"(a1));
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(y1.x), "=d"(y1.y) : "r"(a1));
-          const bool tr0 = (cw & 0x8000u) != 0, tr1 = (cw & 0x80000000u) != 0;
-          lo.x += x0.x; lo.y += tr0 ? x1.x : x0.y; hi.x += tr0 ? x0.y : x1.x; hi.y += x1.y;
-          lo.x += y0.x; lo.y += tr1 ? y1.x : y0.y; hi.x += tr1 ? y0.y : y1.x; hi.y += y1.y;
+      auto ld2 = [](unsigned addr, double2 &lo_, double2 &hi_) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(lo_.x), "=d"(lo_.y) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(hi_.x), "=d"(hi_.y) : "r"(addr));
+      };
+      if (P.nsw == 2) {
+        // structured-like meshes (<= 4 elements around a node): all four sources of a task are loaded up front and
+        // two tasks are interleaved, so 16 LDS.128 are in flight per thread instead of a dependent chain
+#pragma unroll 2
+        for (int blk = tid; blk < nb; blk += G2_THREADS) {
+          const uint32_t w0 = bs[blk], c0w = bs[P.maxb + blk], c1w = bs[2 * P.maxb + blk];
+          double2 x[4][2];
+          ld2(ks_s + ((c0w & 0x7fffu) << 3), x[0][0], x[0][1]);
+          ld2(ks_s + ((c0w >> 13) & 0x3fff8u), x[1][0], x[1][1]);
+          ld2(ks_s + ((c1w & 0x7fffu) << 3), x[2][0], x[2][1]);
+          ld2(ks_s + ((c1w >> 13) & 0x3fff8u), x[3][0], x[3][1]);
+          const bool tr[4] = {(c0w & 0x8000u) != 0, (c0w & 0x80000000u) != 0, (c1w & 0x8000u) != 0, (c1w & 0x80000000u) != 0};
+          double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {      // ascending element order
+            lo.x += x[s4][0].x; lo.y += tr[s4] ? x[s4][1].x : x[s4][0].y;
+            hi.x += tr[s4] ? x[s4][0].y : x[s4][1].x; hi.y += x[s4][1].y;
+          }
+          const int nl = w0 & 0xff, jb = (w0 >> 8) & 0xff;
+          double *row = A.vals + 4 * b0v[nl] + 2 * jb;
+          *reinterpret_cast<double2 *>(row) = lo;
+          *reinterpret_cast<double2 *>(row + 2 * dgv[nl]) = hi;
         }
-        double *row = A.vals + 4 * b0v[nl] + 2 * jb;
-        *reinterpret_cast<double2 *>(row) = lo;
-        *reinterpret_cast<double2 *>(row + 2 * dgv[nl]) = hi;
+      } else {
+        for (int blk = tid; blk < nb; blk += G2_THREADS) {
+          const uint32_t w0 = bs[blk];
+          const int nl = w0 & 0xff, jb = (w0 >> 8) & 0xff;
+          double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
+          for (int sw = 0; sw < P.nsw; ++sw) {
+            const uint32_t cw = bs[(1 + sw) * P.maxb + blk];
+            double2 x0, x1, y0, y1;
+            ld2(ks_s + ((cw & 0x7fffu) << 3), x0, x1);
+            ld2(ks_s + ((cw >> 13) & 0x3fff8u), y0, y1);
+            const bool tr0 = (cw & 0x8000u) != 0, tr1 = (cw & 0x80000000u) != 0;
+            lo.x += x0.x; lo.y += tr0 ? x1.x : x0.y; hi.x += tr0 ? x0.y : x1.x; hi.y += x1.y;
+            lo.x += y0.x; lo.y += tr1 ? y1.x : y0.y; hi.x += tr1 ? y0.y : y1.x; hi.y += y1.y;
+          }
+          double *row = A.vals + 4 * b0v[nl] + 2 * jb;
+          *reinterpret_cast<double2 *>(row) = lo;
+          *reinterpret_cast<double2 *>(row + 2 * dgv[nl]) = hi;
+        }
       }
     }
     if (DO_R) {
@@ -266,6 +299,9 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
       atomicAdd(P.prof + 1, (unsigned long long)(tp2 - tp1));   // phase 1
       atomicAdd(P.prof + 3, (unsigned long long)(tp3 - tp2));   // phase 2
       atomicAdd(P.prof + 4, 1ull);                               // clusters
+      atomicAdd(P.prof + 5, (unsigned long long)(tq1 - tq0));   // cp.async wait
+      atomicAdd(P.prof + 6, (unsigned long long)(tq2 - tq1));   // barrier after the wait
+      atomicAdd(P.prof + 7, (unsigned long long)(tp1 - tq2));   // issue of the next cluster's stage
     }
   }
   cp_async_wait<0>();
@@ -285,9 +321,10 @@ int nls_assembly_mode(nls_context *h) {
 }
 bool nls_assembly_overwrites(nls_context *h) { return nls_assembly_mode(h) != NLS_ASM_ATOMIC; }
 int nls_gather_nc(void) { return G2_NC; }
+void nls_gather_tile(int *t) { t[0] = G2_TX; t[1] = G2_TY; t[2] = 1; }
 
 static size_t gather_smem(int maxt, int maxe, int maxb, int nsw) {
-  const size_t bsz = (size_t)maxt * 32 + G2_NC * 8 + (size_t)maxe * 4 + G2_NC * 4 + G2_NC * 4 + G2_NC * G2_MAXSRC * 2 +
+  const size_t bsz = (size_t)maxt * 32 + G2_NCP * 8 + (size_t)maxe * 4 + G2_NCP * 4 + G2_NCP * 4 + G2_NCP * G2_MAXSRC * 2 +
                      (size_t)(1 + nsw) * maxb * 4;
   return (size_t)(maxe + 1) * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
 }
@@ -335,14 +372,14 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   if (maxt > 255) return NLS_OK;
   const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, MAXB = (maxb + 3) & ~3;
   const int NSW = plan.max_adj <= 4 ? 2 : 4;       // 16-bit source codes, two per word
-  if (gather_smem(MAXT, MAXE, MAXB, NSW) > (size_t)112 * 1024) return NLS_OK;   // two CTAs per SM
+  if (gather_smem(MAXT, MAXE, MAXB, NSW) > (size_t)110 * 1024) return NLS_OK;   // two CTAs per SM
   const int tnw = 4 + MAXT, bw = (1 + NSW) * MAXB;
-  std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NC, -1), deg((size_t)ncl * G2_NC, 0);
+  std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NCP, -1), deg((size_t)ncl * G2_NCP, 0);
   std::vector<uint32_t> lconn((size_t)ncl * MAXE, 0);
-  std::vector<int64_t> b0((size_t)ncl * G2_NC, 0);
+  std::vector<int64_t> b0((size_t)ncl * G2_NCP, 0);
   const uint32_t none = (uint32_t)(MAXE * G2_KS);   // the zero record, not transposed
   std::vector<uint32_t> bsrc((size_t)ncl * bw, none | (none << 16));
-  std::vector<uint16_t> rsrc((size_t)ncl * G2_NC * G2_MAXSRC, (uint16_t)(none + 40));
+  std::vector<uint16_t> rsrc((size_t)ncl * G2_NCP * G2_MAXSRC, (uint16_t)(none + 40));
   static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
   std::vector<int> nsrc_of;
   for (int64_t c = 0; c < ncl; ++c) {
@@ -363,10 +400,10 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
     for (int nl = 0; nl < G2_NC; ++nl) {
       const int32_t a = plan.nodes[c * G2_NC + nl];
       if (a < 0) continue;
-      cn[c * G2_NC + nl] = a;
-      b0[c * G2_NC + nl] = h->h_browptr[a];
+      cn[c * G2_NCP + nl] = a;
+      b0[c * G2_NCP + nl] = h->h_browptr[a];
       const int dg = (int)(h->h_browptr[a + 1] - h->h_browptr[a]);
-      deg[c * G2_NC + nl] = dg;
+      deg[c * G2_NCP + nl] = dg;
       const int32_t *lo = h->h_bcol.data() + h->h_browptr[a], *hi = lo + dg;
       const int blk0 = nb;
       nsrc_of.assign(dg, 0);
@@ -379,7 +416,7 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
         int al = -1;
         for (int q = 0; q < nen; ++q) if (ce[q] == a) al = q;
         if (al < 0) continue;
-        rsrc[((size_t)c * G2_NC + nl) * G2_MAXSRC + nrs++] = (uint16_t)(s * G2_KS + 40 + al * 2);
+        rsrc[((size_t)c * G2_NCP + nl) * G2_MAXSRC + nrs++] = (uint16_t)(s * G2_KS + 40 + al * 2);
         for (int b = 0; b < nen; ++b) {
           const int jb = (int)(std::lower_bound(lo, hi, ce[b]) - lo);
           const int k = nsrc_of[jb]++;

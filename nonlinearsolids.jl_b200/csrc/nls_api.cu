@@ -359,7 +359,9 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
   // when a cluster would not fit in shared memory
   if (h->dim == 2 && h->n_owned > 0 && h->nel > 0) {
     AsmPlan plan;
-    nls_host_cluster_plan(h->dim, h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_coords.data(), nls_gather_nc(), plan);
+    int tile[3];
+    nls_gather_tile(tile);
+    nls_host_cluster_plan(h->dim, h->nen, h->nel, h->h_conn.data(), h->nn, h->n_owned, h->h_coords.data(), nls_gather_nc(), plan, tile);
     NLS_TRY(nls_gather_build(h, plan));
   }
   NLS_TRY(nls_twophase_build(h));
@@ -811,6 +813,12 @@ extern "C" int32_t nls_flush_l2(nls_handle h) {
   return NLS_OK;
 }
 extern "C" int64_t nls_kernel_launches(nls_handle h) { return h ? h->launches : 0; }
+
+extern "C" int32_t nls_assembly_scheme(nls_handle h) {
+  if (!h || !h->have_pattern) return -1;
+  cudaSetDevice(h->device);
+  return nls_assembly_mode(h);
+}
 
 extern "C" int32_t nls_debug_counters(nls_handle h, int64_t *out8) {
   NLS_ENTER(h);

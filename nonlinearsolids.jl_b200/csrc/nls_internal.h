@@ -54,7 +54,8 @@ struct AsmPlan {
   std::vector<int32_t> elems;     // element ids touching the cluster, ascending per cluster
 };
 void nls_host_cluster_plan(int dim, int nen, int64_t nel, const int32_t *conn, int64_t nn, int64_t n_owned,
-                           const double *coords, int nc, AsmPlan &plan);
+                           const double *coords, int nc, AsmPlan &plan, const int *tile = nullptr);
+void nls_gather_tile(int *tile3);
 
 // packed, fixed-stride device copy of the plan (kernels_gather.cu)
 struct GatherPlanDev {
