@@ -178,7 +178,14 @@ def run_ours(args):
     if args.gather_ctas:
         H.call("nls_set_option", b"gather_ctas", args.gather_ctas)
     scheme = L.nls_assembly_scheme(H.h)
-    sys.stderr.write("rank %d: assembly scheme %d (0 atomic, 1 gather, 2 element records)\n" % (rank, scheme))
+    comm_path = L.nls_comm_path(H.h)
+    comm_us = None
+    if world > 1:
+        uh, ua = C.c_float(0), C.c_float(0)
+        H.call("nls_dev_comm_probe", 200, C.byref(uh), C.byref(ua))
+        comm_us = {"halo_exchange_us": uh.value, "allreduce_us": ua.value}
+    sys.stderr.write("rank %d: assembly scheme %d (0 atomic, 1 gather, 2 element records), comm path %d (1 NCCL, 2 peer memory) %s\n"
+                     % (rank, scheme, comm_path, comm_us))
     nrows, nnz = C.c_int64(0), C.c_int64(0)
     H.call("nls_pattern_size", C.byref(nrows), C.byref(nnz))
     nrows, nnz = nrows.value, nnz.value
@@ -283,6 +290,8 @@ def run_ours(args):
             "e2e": {"value": total_dof / e2e_s, "unit": "DoF/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": 8 * fem.ndof, "d2h_bytes_per_step": 8 * (fem.ndof + nrows + nnz)},
             "gpu_launches": int(launches), "clocks": clk, "newton_step": newton,
+            "comm": {"path": {0: "single GPU", 1: "NCCL send/recv + allreduce", 2: "peer-memory windows over NVLink (CUDA IPC)"}[comm_path],
+                     "latency": comm_us},
             "wall_s_timed_region": t_wall,
         }
     # ---- CPU baseline beside it (rank 0, N=1 only) ----

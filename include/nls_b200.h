@@ -226,6 +226,12 @@ int32_t nls_set_halo(nls_handle h, int64_t n_owned_nodes, int32_t nneigh, const 
 int32_t nls_comm_unique_id(const char *nccl_lib_path, uint8_t *id128);
 int32_t nls_comm_init(nls_handle h, const char *nccl_lib_path, int32_t rank, int32_t nranks, const uint8_t *id128);
 int32_t nls_dev_halo_exchange_u(nls_handle h); /* test hook: fill ghost entries of U */
+/* Data path of the halo exchange / reductions: 0 single GPU, 1 NCCL (ncclSend/Recv, ncclAllReduce), 2 peer memory
+ * (CUDA IPC windows over NVLink, kernels_p2p.cu; chosen at nls_set_halo when every rank can open every window;
+ * NLS_B200_P2P=0 in the environment keeps NCCL) */
+int32_t nls_comm_path(nls_handle h);
+/* average device time (us) of one halo exchange of U and of one 2-double allreduce over `iters` back-to-back calls */
+int32_t nls_dev_comm_probe(nls_handle h, int32_t iters, float *us_halo, float *us_allreduce);
 
 #ifdef __cplusplus
 }

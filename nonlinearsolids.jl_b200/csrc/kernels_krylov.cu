@@ -394,6 +394,7 @@ int nls_launch_axpy(nls_context *h, int64_t n, double a, const double *x, double
 // ---- communication: neighbour halo (ghost-DoF) exchange + scalar allreduce over NCCL ----
 int nls_halo_exchange(nls_context *h, double *v) {
   if (!h->distributed || h->nneigh == 0) return NLS_OK;
+  if (h->p2p.on) return nls_p2p_halo_exchange(h, v);
   const int dim = h->dim;
   const int64_t nsend = h->send_ptr[h->nneigh], nrecv = h->recv_ptr[h->nneigh];
   if (nsend > 0) {
@@ -421,6 +422,7 @@ int nls_halo_exchange(nls_context *h, double *v) {
 
 int nls_allreduce_sum(nls_context *h, double *dptr, int count) {
   if (!h->distributed) return NLS_OK;
+  if (h->p2p.on) return nls_p2p_allreduce(h, dptr, count);
   int e = h->nccl->AllReduce(dptr, dptr, (size_t)count, NCCL_DYN_FLOAT64, NCCL_DYN_SUM, h->comm, h->stream);
   if (e != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclAllReduce: ") + h->nccl->GetErrorString(e));
   return NLS_OK;

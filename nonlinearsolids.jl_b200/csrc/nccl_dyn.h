@@ -20,6 +20,7 @@ struct NcclApi {
   int (*CommInitRank)(void **comm, int nranks, NcclDynId id, int rank) = nullptr;
   int (*CommDestroy)(void *comm) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t sendcount, int, void *comm, cudaStream_t) = nullptr;
   int (*Send)(const void *, size_t, int, int peer, void *comm, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int peer, void *comm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -43,6 +44,7 @@ struct NcclApi {
     NLS_SYM(CommInitRank, "ncclCommInitRank")
     NLS_SYM(CommDestroy, "ncclCommDestroy")
     NLS_SYM(AllReduce, "ncclAllReduce")
+    NLS_SYM(AllGather, "ncclAllGather")
     NLS_SYM(Send, "ncclSend")
     NLS_SYM(Recv, "ncclRecv")
     NLS_SYM(GroupStart, "ncclGroupStart")

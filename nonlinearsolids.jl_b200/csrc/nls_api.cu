@@ -102,6 +102,7 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   if (!h) return NLS_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  nls_p2p_free(h);
   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
   free_pattern(h);
   dev_free(&h->d_conn); dev_free(&h->d_coords);
@@ -789,7 +790,7 @@ extern "C" int32_t nls_dev_newton_solve(nls_handle h, const nls_newton_opts *opt
 extern "C" int32_t nls_sync(nls_handle h) {
   NLS_ENTER(h);
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
-  return NLS_OK;
+  return nls_p2p_check(h);
 }
 extern "C" int32_t nls_timer_start(nls_handle h) {
   NLS_ENTER(h);
@@ -875,7 +876,7 @@ extern "C" int32_t nls_set_halo(nls_handle h, int64_t n_owned_nodes, int32_t nne
   if (ns) NLS_CUDA(h, cudaMemcpyAsync(h->d_send_nodes, send_nodes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, h->stream));
   if (nr) NLS_CUDA(h, cudaMemcpyAsync(h->d_recv_nodes, recv_nodes, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
-  return NLS_OK;
+  return nls_p2p_setup(h);      // collective: every rank of the communicator sets its halo
 }
 
 extern "C" int32_t nls_comm_unique_id(const char *nccl_lib_path, uint8_t *id128) {
@@ -902,6 +903,35 @@ extern "C" int32_t nls_comm_init(nls_handle h, const char *nccl_lib_path, int32_
   if (rc != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
   h->comm = comm; h->rank = rank; h->nranks = nranks; h->distributed = true;
   return NLS_OK;
+}
+
+extern "C" int32_t nls_comm_path(nls_handle h) {
+  if (!h || !h->distributed) return 0;
+  return h->p2p.on ? 2 : 1;
+}
+
+extern "C" int32_t nls_dev_comm_probe(nls_handle h, int32_t iters, float *us_halo, float *us_allreduce) {
+  NLS_ENTER(h);
+  if (!h->have_mesh || iters < 1) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_comm_probe: no mesh or iters < 1");
+  float ms = 0.f;
+  for (int rep = 0; rep < 2; ++rep) {          // first round warms the connections up
+    NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    for (int i = 0; i < iters; ++i) NLS_TRY(nls_halo_exchange(h, h->d_U));
+    NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
+    NLS_CUDA(h, cudaEventSynchronize(h->ev3));
+    ms = elapsed(h->ev2, h->ev3);
+  }
+  if (us_halo) *us_halo = ms * 1e3f / iters;
+  NLS_CUDA(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), h->stream));
+  for (int rep = 0; rep < 2; ++rep) {
+    NLS_CUDA(h, cudaEventRecord(h->ev2, h->stream));
+    for (int i = 0; i < iters; ++i) NLS_TRY(nls_allreduce_sum(h, h->d_scal, 2));
+    NLS_CUDA(h, cudaEventRecord(h->ev3, h->stream));
+    NLS_CUDA(h, cudaEventSynchronize(h->ev3));
+    ms = elapsed(h->ev2, h->ev3);
+  }
+  if (us_allreduce) *us_allreduce = ms * 1e3f / iters;
+  return nls_p2p_check(h);
 }
 
 extern "C" int32_t nls_dev_halo_exchange_u(nls_handle h) {

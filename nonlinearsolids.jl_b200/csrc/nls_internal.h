@@ -97,6 +97,24 @@ struct PcgCtl {
 
 struct NcclApi;                     // nccl_dyn.h
 
+// peer-memory (CUDA IPC over NVLink) data path of the halo exchange and the Krylov reductions (kernels_p2p.cu)
+struct P2PState {
+  bool on = false;
+  double *win = nullptr;                       // my window: [2][H] halo areas, then [2][nranks][4] reduction slots
+  unsigned long long *flags = nullptr;         // my flags: [0][src] halo epochs, [1][src] reduction epochs
+  int64_t H = 0;
+  double *dst[2][8] = {};                      // per parity, per neighbour: where my planes go in its window
+  unsigned long long *dst_flag[8] = {};
+  const unsigned long long *my_flag[8] = {};
+  double **d_peer_red[2] = {nullptr, nullptr}; // device arrays [nranks]
+  unsigned long long **d_peer_rflag = nullptr;
+  const double *my_red[2] = {nullptr, nullptr};
+  unsigned long long halo_epoch = 0, red_epoch = 0;
+  unsigned int *d_done = nullptr;
+  int *d_err = nullptr;
+  std::vector<void *> opened;
+};
+
 struct nls_context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -201,6 +219,7 @@ struct nls_context {
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
   NcclApi *nccl = nullptr;
   void *comm = nullptr;
+  P2PState p2p;
 
   int64_t ndof_local() const { return nn * (int64_t)dim; }
 };
@@ -242,4 +261,9 @@ int nls_launch_scale_add_mass(nls_context *h, double scale, bool scale_existing)
 int nls_launch_newmark_state(nls_context *h, double c_u, double c_v);
 
 int nls_halo_exchange(nls_context *h, double *v);
+int nls_p2p_setup(nls_context *h);
+void nls_p2p_free(nls_context *h);
+int nls_p2p_halo_exchange(nls_context *h, double *v);
+int nls_p2p_allreduce(nls_context *h, double *dptr, int count);
+int nls_p2p_check(nls_context *h);
 int nls_allreduce_sum(nls_context *h, double *dptr, int count);

@@ -4,7 +4,7 @@
     python tools/run_config.py --config C1                       # 1-D KAT-3 bar, 100 p=3 elements, Newton to convergence
     python tools/run_config.py --config C3 [--lin-rtol 1e-8]     # 3-D n=150 (10.1 M DoF): assembly, PCG iteration, full Newton
     torchrun --nproc-per-node 8 ... tools/run_config.py --config C4 --steps 3   # 3-D n=216 (30.2 M DoF), load stepping
-    python tools/run_config.py --dim 3 --n 70 --mode assembly    # one point of the C5 assembly sweep (also --strong under torchrun)
+    python tools/run_config.py --dim 3 --side 70 --mode assembly    # one point of the C5 assembly sweep (also --strong under torchrun)
 
 Multi-GPU runs partition the structured mesh in slabs along the slowest axis; timings are CUDA events on
 the library stream, max over ranks. --weak stacks one n^dim block per rank instead of splitting one."""
@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default=None, choices=[None, "C1", "C3", "C4"])
     ap.add_argument("--dim", type=int, default=3)
-    ap.add_argument("--n", type=int, default=70)
+    ap.add_argument("--side", dest="n", type=int, default=70, help="nodes per side")
     ap.add_argument("--mode", default="newton", choices=["assembly", "newton", "steps"])
     ap.add_argument("--weak", action="store_true")
     ap.add_argument("--steps", type=int, default=2, help="load steps (mode steps)")
