@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SIDE = 708          # C2: 708^2 nodes = 1 002 528 DoF
-NCU_TRAFFIC_BYTES = 195.0e6   # measured DRAM traffic of the assembly kernel at C2 (see roofline.traffic_source)
+NCU_TRAFFIC_BYTES = 194.3e6   # measured DRAM traffic of the assembly kernel at C2 (see roofline.traffic_source)
 DIM = 2
 E_MOD, NU = 1.0, 0.3
 
@@ -281,7 +281,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": NCU_TRAFFIC_BYTES if args.assembly in (None, 1) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r1h_ncu_asm2d_gather_v9.txt): 93.5 MB read + 101.5 MB written; the 19 MB above the algorithmic "
+                                           "(profiles/r1j_ncu_asm2d_gather_v10.txt): 95.0 MB read + 99.2 MB written; the 18 MB above the algorithmic "
                                            "bytes are the staged cluster plan (node lists, per-block source lists), part of the freshly "
                                            "written CSR values is still in the 126 MB L2 when the kernel ends",
                          "kernel": "k_asm_q1_2d_gather<R,K> (one launch = one fused assembly pass; no zero-fill needed)"
