@@ -197,6 +197,7 @@ def run_ours(args):
     # ---- value: device-resident fused R+K assembly ----
     def step_dev():
         H.call("nls_flush_l2")
+        H.call("nls_dev_barrier")        # N > 1: line the ranks' streams up, so the halo wait inside the step is not host jitter
         H.call("nls_timer_start")
         H.call("nls_dev_assemble", 1, 1)
         H.call("nls_timer_stop", C.byref(ms))

@@ -230,6 +230,9 @@ int32_t nls_dev_halo_exchange_u(nls_handle h); /* test hook: fill ghost entries 
  * (CUDA IPC windows over NVLink, kernels_p2p.cu; chosen at nls_set_halo when every rank can open every window;
  * NLS_B200_P2P=0 in the environment keeps NCCL) */
 int32_t nls_comm_path(nls_handle h);
+/* device-side barrier: one reduction over all ranks enqueued on the library stream (no host sync); lines the ranks'
+ * streams up before a timed region */
+int32_t nls_dev_barrier(nls_handle h);
 /* average device time (us) of one halo exchange of U and of one 2-double allreduce over `iters` back-to-back calls */
 int32_t nls_dev_comm_probe(nls_handle h, int32_t iters, float *us_halo, float *us_allreduce);
 

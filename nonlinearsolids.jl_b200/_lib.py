@@ -103,6 +103,7 @@ PROTOTYPES = {
     "nls_comm_init": (C.c_int32, [_H, C.c_char_p, C.c_int32, C.c_int32, _bp]),
     "nls_dev_halo_exchange_u": (C.c_int32, [_H]),
     "nls_comm_path": (C.c_int32, [_H]),
+    "nls_dev_barrier": (C.c_int32, [_H]),
     "nls_dev_comm_probe": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 

@@ -483,9 +483,9 @@ int nls_launch_assembly(nls_context *h, bool want_r, bool want_k) {
   }
   const unsigned g = nblk(h->nel, H8_EPB);
   const size_t shm = sizeof(double) * H8_EPB * (want_k ? H8_ESTRIDE : HEX_REC);
-  static bool attr_set = false;
+  bool &attr_set = h->attr_asm3d;   // the attribute is per device: one handle = one device
   if (!attr_set) {
-    const int shm_max = (int)(sizeof(double) * H8_EPB * H8_ESTRIDE);
+    const int shm_max = h->max_optin_smem;
     cudaFuncSetAttribute(k_asm_q1_3d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
     cudaFuncSetAttribute(k_asm_q1_3d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
     cudaFuncSetAttribute(k_asm_q1_3d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);

@@ -450,12 +450,11 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
   GatherArgs p{g.ncl, g.maxt, g.maxe, g.maxb, g.nsw, g.tn, g.lconn, g.cn, g.b0, g.deg, g.bsrc, g.rsrc,
                h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr};
   const size_t shm = gather_smem(g.maxt, g.maxe, g.maxb, g.nsw);
-  static size_t shm_set = 0;
-  if (shm > shm_set) {
-    cudaFuncSetAttribute(k_asm_q1_2d_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-    cudaFuncSetAttribute(k_asm_q1_2d_gather<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-    cudaFuncSetAttribute(k_asm_q1_2d_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-    shm_set = shm;
+  if (!h->attr_gather) {       // per device: raised once per handle to the opt-in maximum
+    cudaFuncSetAttribute(k_asm_q1_2d_gather<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
+    cudaFuncSetAttribute(k_asm_q1_2d_gather<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
+    cudaFuncSetAttribute(k_asm_q1_2d_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
+    h->attr_gather = true;
   }
   const int per_sm = h->opt_gather_ctas > 0 ? h->opt_gather_ctas : 2;
   const unsigned grid = (unsigned)std::min<int64_t>(g.ncl, (int64_t)h->sm_count * per_sm);

@@ -362,19 +362,19 @@ int nls_twophase_build(nls_context *h) {
 template <int DIM, bool DO_R, bool DO_K>
 static int launch_twophase(nls_context *h, const AsmArgs &a) {
   const TwoPhasePlan &t = h->tplan;
-  static bool attr_set = false;
+  bool &attr_set = h->attr_tp3d;
   const size_t shm1 = sizeof(double) * T8_EPB * HEX_REC;
   const size_t shm2 = sizeof(double) * DIM * 32 * (size_t)t.rs;
   if (DIM == 3 && !attr_set) {
-    cudaFuncSetAttribute(k_elem_q1_3d_store<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm1);
-    cudaFuncSetAttribute(k_elem_q1_3d_store<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm1);
-    cudaFuncSetAttribute(k_elem_q1_3d_store<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm1);
+    cudaFuncSetAttribute(k_elem_q1_3d_store<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
+    cudaFuncSetAttribute(k_elem_q1_3d_store<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
+    cudaFuncSetAttribute(k_elem_q1_3d_store<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
     attr_set = true;
   }
-  static size_t shm2_set = 48 * 1024;
-  if (DO_K && shm2 > shm2_set) {
-    cudaFuncSetAttribute(k_rows_from_records<DIM, DO_R, DO_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm2);
-    shm2_set = shm2;
+  bool &rows_set = h->attr_rows[DIM - 2][DO_R ? 1 : 0][DO_K ? 1 : 0];
+  if (DO_K && !rows_set) {
+    cudaFuncSetAttribute(k_rows_from_records<DIM, DO_R, DO_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
+    rows_set = true;
   }
   for (const TwoPhaseChunk &c : t.chunks) {
     TwoPhaseArgs p{c.n0, c.n1, c.e_lo, c.e_hi, t.estride, t.np, t.maxadj, t.rs, t.esrc, t.asrc, t.scratch};

@@ -85,6 +85,7 @@ extern "C" int32_t nls_create(int32_t device, nls_handle *out) {
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   CK(cudaEventCreate(&h->ev2)); CK(cudaEventCreate(&h->ev3));
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CK(cudaDeviceGetAttribute(&h->max_optin_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   CK(cudaMalloc((void **)&h->d_ctl, sizeof(PcgCtl)));
   CK(cudaMemset(h->d_ctl, 0, sizeof(PcgCtl)));
   CK(cudaMallocHost((void **)&h->h_ctl, sizeof(PcgCtl)));
@@ -903,6 +904,15 @@ extern "C" int32_t nls_comm_init(nls_handle h, const char *nccl_lib_path, int32_
   if (rc != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
   h->comm = comm; h->rank = rank; h->nranks = nranks; h->distributed = true;
   return NLS_OK;
+}
+
+// Enqueues one reduction over all ranks on the library stream (no host synchronisation): a device-side barrier that
+// lines the ranks' streams up, e.g. right before a timed region.
+extern "C" int32_t nls_dev_barrier(nls_handle h) {
+  NLS_ENTER(h);
+  if (!h->distributed) return NLS_OK;
+  NLS_CUDA(h, cudaMemsetAsync(h->d_scal + 4, 0, 2 * sizeof(double), h->stream));
+  return nls_allreduce_sum(h, h->d_scal + 4, 1);
 }
 
 extern "C" int32_t nls_comm_path(nls_handle h) {

@@ -194,6 +194,11 @@ struct nls_context {
   double *d_state[9] = {nullptr};       // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
   double *d_u_n = nullptr;              // [nel][nen]
 
+  // per-handle (= per-device) record of the dynamic shared-memory limits already raised with cudaFuncSetAttribute
+  // (always raised to the device's opt-in maximum, so handles sharing a device cannot lower each other's limit)
+  bool attr_asm3d = false, attr_tp3d = false, attr_gather = false, attr_rows[2][2][2] = {};   // rows: [dim-2][DO_R][DO_K]
+  int max_optin_smem = 227 * 1024;
+
   // L2 flush scratch
   void *d_flush = nullptr;
   size_t flush_bytes = 0;

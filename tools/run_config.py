@@ -126,7 +126,8 @@ def main():
     H.call("nls_dev_upload_u", dp(U0))
     ts = []
     for rep in range(a.reps + 2):
-        H.call("nls_flush_l2"); H.call("nls_timer_start"); H.call("nls_dev_assemble", 1, 1); H.call("nls_timer_stop", C.byref(ms))
+        H.call("nls_flush_l2"); H.call("nls_dev_barrier")
+        H.call("nls_timer_start"); H.call("nls_dev_assemble", 1, 1); H.call("nls_timer_stop", C.byref(ms))
         ts.append(ms.value)
     asm_ms = allmax(float(np.median(ts[2:])))
     abytes = 4 * mesh.nen * mesh.nel + 8 * dim * mesh.nn + 16 * nrows + 8 * nnz
