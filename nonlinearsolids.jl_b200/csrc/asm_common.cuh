@@ -13,6 +13,8 @@ struct AsmArgs {
   const uint16_t *pos;
   double *st[9];   // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
   const double *u_n;
+  const double *lap;       // 3-D: [40][lap_stride] precomputed sum_q w detJ (G_a . G_b) per lane slot (a*5+d), or NULL
+  int64_t lap_stride;
 };
 
 __device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }

@@ -242,7 +242,21 @@ k_asm_q1_2d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_const
 #define H8_TS 25                        // row stride of the K_e tile (24 entries + 1: conflict-free)
 #define H8_ESTRIDE (24 * H8_TS + 32)    // per element: max(HEX_REC = 544, K_e tile 600 + scatter meta 28) doubles
 
-template <bool DO_R, bool DO_K>
+// one-time: lap[(a*5+d)][e] = sum_q w detJ (G_a . G_b), b = (a+d)&7 -- the lane/slot layout the assembly kernel reads back
+__global__ void __launch_bounds__(8 * H8_EPB)
+k_lap_build_3d(const AsmArgs A, const __grid_constant__ TabQ1 T, double *lap, int64_t stride) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, le = tid >> 3, a = tid & 7;
+  const int64_t e = blockIdx.x * (int64_t)H8_EPB + le;
+  if (e >= A.nel) return;
+  const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));
+  double fe[3], Kr[5][3][3];
+  hex_element_circulant<false, true, false, true>(smem + le * HEX_REC, a, gmask, A.conn[e * 8 + a], A.coords, A.coords, T, 1.0, 0.0, Kr, fe);
+#pragma unroll
+  for (int d = 0; d < 5; ++d) lap[(int64_t)(a * 5 + d) * stride + e] = Kr[d][0][0];
+}
+
+template <bool DO_R, bool DO_K, bool USE_LAP>
 __global__ void __launch_bounds__(8 * H8_EPB, 5)
 k_asm_q1_3d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
   extern __shared__ __align__(16) double smem[];
@@ -255,8 +269,12 @@ k_asm_q1_3d(const AsmArgs A, const __grid_constant__ TabQ1 T, const __grid_const
   double *S = smem + le * ES;
   const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));
   const int node = A.conn[e * 8 + a];
-  double fe[3], Kr[5][3][3];
-  hex_element_circulant<DO_R, DO_K>(S, a, gmask, node, A.coords, A.U, T, mp.p[0], mp.p[1], Kr, fe);
+  double fe[3], Kr[5][3][3], lap5[5];
+  if (DO_K && USE_LAP) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) lap5[d] = A.lap[(int64_t)(a * 5 + d) * A.lap_stride + e];
+  }
+  hex_element_circulant<DO_R, DO_K, USE_LAP>(S, a, gmask, node, A.coords, A.U, T, mp.p[0], mp.p[1], Kr, fe, lap5);
 
   const bool owned = node < A.n_owned;
   if (DO_R && owned) {
@@ -486,14 +504,35 @@ int nls_launch_assembly(nls_context *h, bool want_r, bool want_k) {
   bool &attr_set = h->attr_asm3d;   // the attribute is per device: one handle = one device
   if (!attr_set) {
     const int shm_max = h->max_optin_smem;
-    cudaFuncSetAttribute(k_asm_q1_3d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
-    cudaFuncSetAttribute(k_asm_q1_3d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
-    cudaFuncSetAttribute(k_asm_q1_3d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
+    cudaFuncSetAttribute(k_asm_q1_3d<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
+    cudaFuncSetAttribute(k_asm_q1_3d<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
+    cudaFuncSetAttribute(k_asm_q1_3d<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
+    cudaFuncSetAttribute(k_asm_q1_3d<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
+    cudaFuncSetAttribute(k_asm_q1_3d<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
+    cudaFuncSetAttribute(k_lap_build_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, shm_max);
     attr_set = true;
   }
-  if (want_r && want_k) k_asm_q1_3d<true, true><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
-  else if (want_r)      k_asm_q1_3d<true, false><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
-  else                  k_asm_q1_3d<false, true><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
+  // the Laplacian part of the tangent: once per mesh (coordinates and connectivity only), if its 320 B/element fit
+  if (want_k && h->opt_lap3d && !h->lap_valid && !h->d_lap) {
+    h->lap_stride = (h->nel + 31) & ~(int64_t)31;
+    if (cudaMalloc((void **)&h->d_lap, sizeof(double) * 40 * (size_t)h->lap_stride) != cudaSuccess) { cudaGetLastError(); h->d_lap = nullptr; h->opt_lap3d = 0; }
+  }
+  if (want_k && h->opt_lap3d && h->d_lap && !h->lap_valid) {
+    k_lap_build_3d<<<g, 8 * H8_EPB, sizeof(double) * H8_EPB * HEX_REC, h->stream>>>(a, h->tabq, h->d_lap, h->lap_stride);
+    NLS_KCHECK(h);
+    h->lap_valid = true;
+  }
+  const bool lap = want_k && h->opt_lap3d && h->lap_valid;
+  a.lap = lap ? h->d_lap : nullptr; a.lap_stride = h->lap_stride;
+  if (want_r && want_k) {
+    if (lap) k_asm_q1_3d<true, true, true><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
+    else     k_asm_q1_3d<true, true, false><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
+  } else if (want_r) {
+    k_asm_q1_3d<true, false, false><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
+  } else {
+    if (lap) k_asm_q1_3d<false, true, true><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
+    else     k_asm_q1_3d<false, true, false><<<g, 8 * H8_EPB, shm, h->stream>>>(a, h->tabq, h->mat);
+  }
   NLS_KCHECK(h);
   return NLS_OK;
 }

@@ -116,6 +116,7 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   dev_free(&h->d_u_n);
   dev_free(&h->d_send_nodes); dev_free(&h->d_recv_nodes); dev_free(&h->d_sendbuf); dev_free(&h->d_recvbuf);
   dev_free(&h->d_Ut); dev_free(&h->d_Udt); dev_free(&h->d_Udd); dev_free(&h->d_Ud); dev_free(&h->d_con_zero);
+  dev_free(&h->d_lap);
   if (h->d_flush) cudaFree(h->d_flush);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -137,6 +138,7 @@ extern "C" int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64
   for (int64_t k = 0; k < nelem * nen; ++k)
     if (conn0[k] < 0 || conn0[k] >= nnodes) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: connectivity entry out of range (expects 0-based node ids)");
   free_pattern(h);
+  dev_free(&h->d_lap); h->lap_valid = false;
   h->dim = dim; h->nen = nen; h->nn = nnodes; h->nel = nelem; h->n_owned = nnodes;
   h->h_conn.assign(conn0, conn0 + nelem * nen);
   h->h_coords.assign(coords, coords + nnodes * dim);
@@ -839,6 +841,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
   if (!std::strcmp(key, "twophase_3d")) { h->opt_twophase_3d = value; return NLS_OK; }
+  if (!std::strcmp(key, "lap3d")) { h->opt_lap3d = value; return NLS_OK; }
   if (!std::strcmp(key, "scratch_mb")) {   // takes effect at the next nls_build_pattern
     h->opt_scratch_mb = value;
     if (h->have_pattern) { NLS_TRY(nls_twophase_build(h)); }

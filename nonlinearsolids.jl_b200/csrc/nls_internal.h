@@ -165,6 +165,12 @@ struct nls_context {
   uint16_t *d_pos = nullptr;            // [nel][nen][nen] position of node b in block row of node a
   int32_t *d_diag = nullptr;            // [nrows] offset of the diagonal entry within its row
 
+  // 3-D: deformation-independent (Laplacian) part of the tangent per element, built once per mesh (hex_element.cuh)
+  double *d_lap = nullptr;
+  int64_t lap_stride = 0;
+  bool lap_valid = false;
+  int opt_lap3d = 1;      // 1: use it when the 320 B/element fit in HBM
+
   // gather-assembly plan (device copy)
   bool have_plan = false;
   GatherPlanDev gplan;
