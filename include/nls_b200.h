@@ -201,7 +201,7 @@ int64_t nls_kernel_launches(nls_handle h);   /* kernels launched by this handle 
  * 0 atomic scatter, 1 shared-memory gather (2-D), 2 element records + row owners; -1 without a pattern */
 int32_t nls_assembly_scheme(nls_handle h);
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
- * {staging wait, phase 1a, phase 1b, phase 2, clusters, 0, 0, 0}, summed over CTAs */
+ * {staging, element phase, 0, block-task phase, clusters, cp.async wait, barrier, issue of the next stage}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);
 /* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 the default row-owner scheme
  * (2-D: shared-memory gather; 3-D: atomic scatter unless "twophase_3d" = 1), 2 element records + row owners;

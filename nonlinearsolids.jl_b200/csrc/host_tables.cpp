@@ -278,7 +278,7 @@ extern "C" int32_t nls_pattern_host(int32_t dim, int32_t nen, int64_t nelem, con
 
 // ---- cluster plan for the gather (row-owner) assembly ----------------------------------------
 // Owned nodes are grouped into spatially compact clusters of <= nc nodes (Morton order of the
-// quantised coordinates; works for any mesh, gives 8x8 tiles on a structured 2-D grid). A CTA
+// quantised coordinates, or rectangular tiles of bins when the caller asks for them; works for any mesh). A CTA
 // computes every element touching its cluster once into shared memory, then each cluster node
 // gathers its rows from there: no atomics, no zero-fill, rows written once, contributions summed
 // in ascending element order (the order of the reference's serial element loop, defaults.jl:77-81).

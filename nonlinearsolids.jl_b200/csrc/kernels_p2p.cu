@@ -14,13 +14,13 @@
 // Windows are double buffered by epoch parity: a rank can only be one exchange ahead of a neighbour (its own
 // receive waits for the neighbour's send of the same epoch, which follows the neighbour's previous receive in
 // stream order), so the slot being overwritten has always been consumed.
-// Spins are bounded (about 2 s): a lost peer raises an error flag instead of hanging the GPU.
+// Spins are bounded (about 60 s): a lost peer raises an error flag instead of hanging the GPU.
 #include <cstdlib>
 #include <cstring>
 #include "nls_internal.h"
 #include "nccl_dyn.h"
 
-#define P2P_SPIN_CYCLES (4000000000ll)
+#define P2P_SPIN_CYCLES (120000000000ll)   // ~60 s at 2 GHz: ranks may reach an exchange seconds apart (host-side setup)
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
@@ -34,7 +34,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsig
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < epoch) {
     if (clock64() - t0 > P2P_SPIN_CYCLES) { atomicExch(err, 1); return false; }
-    __nanosleep(20);
+    __nanosleep(40);
   }
   return true;
 }

@@ -33,8 +33,8 @@ if dim == 2:
     cnt = np.zeros(8, dtype=np.int64)
     H.call("nls_debug_counters", cnt.ctypes.data_as(C.POINTER(C.c_int64)))
     ncl = max(1, cnt[4])
-    print("gather phases, cycles per cluster: staging %.0f, 1a %.0f, 1b %.0f, 2 %.0f (clusters %d)" % (
-        cnt[0] / ncl, cnt[1] / ncl, cnt[2] / ncl, cnt[3] / ncl, ncl))
+    print("gather phases, cycles per cluster: staging %.0f, elements %.0f, block tasks %.0f (clusters %d)" % (
+        cnt[0] / ncl, cnt[1] / ncl, cnt[3] / ncl, ncl))
     print("  staging split: cp.async wait %.0f, barrier %.0f, issue_B %.0f" % (cnt[5] / ncl, cnt[6] / ncl, cnt[7] / ncl))
     H.call("nls_set_option", b"profile_phases", 0)
 H.call("nls_dev_pcg_iterations", 20)
