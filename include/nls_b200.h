@@ -156,6 +156,11 @@ int32_t nls_axpy(nls_handle h, int64_t n, double a, const double *x, double *y);
 int32_t nls_linear_solve(nls_handle h, double rtol, int32_t maxits, const double *b, double *x,
                          int32_t *its, double *relres, int32_t *status_out);
 
+/* Same contract for a symmetric INDEFINITE matrix (the tangent past a limit point, arc-length continuation,
+ * nonlinearsolvers/newtonarclength_fem.jl:104): Jacobi-preconditioned MINRES. status_out: 0 ok, 1 maxits, 2 breakdown */
+int32_t nls_linear_solve_indefinite(nls_handle h, double rtol, int32_t maxits, const double *b, double *x,
+                                    int32_t *its, double *relres, int32_t *status_out);
+
 /* ---- Newton (solve!(::NewtonSolver, U0), newton_fem.jl:132-190) ------------- */
 int32_t nls_newton_solve(nls_handle h, const nls_newton_opts *opts, const double *U0, double *U, double *R,
                          double *norm_hist /*maxits+1 or NULL*/, nls_newton_result *res);

@@ -6,6 +6,7 @@ materials, Residual/Jacobian functors, NewtonSolver, PseudoTimeStepper -- callin
 through ctypes exactly as the Julia `ccall` shim in julia/NonlinearSolidsB200.jl does.
 """
 from . import _lib, distributed
+from .arclength import ArcLength, ArcLengthResult, newtonarclength
 from ._lib import Handle, NLSError, lib
 from .fem import (Dirichlet, Element, ElementBoundary, FEMModel, Lagrange, Mesh, N, Neumann, Quadrature,
                   TimeDependent, dN, gauss_quadrature, getstate, integrate, interpolate, lagrange)

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "nls_dot": (C.c_int32, [_H, C.c_int64, _dp, _dp, _dp]),
     "nls_axpy": (C.c_int32, [_H, C.c_int64, C.c_double, _dp, _dp]),
     "nls_linear_solve": (C.c_int32, [_H, C.c_double, C.c_int32, _dp, _dp, _ip, _dp, _ip]),
+    "nls_linear_solve_indefinite": (C.c_int32, [_H, C.c_double, C.c_int32, _dp, _dp, _ip, _dp, _ip]),
     "nls_newton_solve": (C.c_int32, [_H, C.POINTER(NewtonOpts), _dp, _dp, _dp, _dp, C.POINTER(NewtonResult)]),
     "nls_set_mass": (C.c_int32, [_H, C.c_double, C.c_double]),
     "nls_get_mass": (C.c_int32, [_H, _dp]),

@@ -473,3 +473,90 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
   if (status) *status = (c.done == 1) ? 0 : (c.done == 3 ? 2 : (fixed_iters > 0 ? 0 : 1));
   return NLS_OK;
 }
+
+
+// ------------------------------------------------------------------------------------
+// Jacobi-preconditioned MINRES (Paige & Saunders) on the free block of the handle's current CSR values: the
+// symmetric-INDEFINITE solve the arc-length continuation needs past a limit point (the reference's
+// bordered dense `\` of newtonarclength_fem.jl:104 becomes two of these). Vectors stay on the device; the
+// Lanczos / Givens scalars are 3 doubles per iteration on the host (one synchronisation per dot product): this
+// solver serves continuation runs, not the throughput path. rhs = h->d_b (masked inside), solution -> h->d_dU.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lincomb3(int64_t n, double *y, double a, const double *x1, double b, const double *x2, double c, const double *x3) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = a * x1[i];
+    if (x2) v = fma(b, x2[i], v);
+    if (x3) v = fma(c, x3[i], v);
+    y[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_prec_abs(int64_t n, const double *__restrict__ dinv, const uint8_t *__restrict__ con, const double *__restrict__ r, double *__restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = con[i] ? 0.0 : fabs(dinv[i]) * r[i];
+}
+
+int nls_minres_solve(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status) {
+  int rc;
+  const int64_t n = h->nrows, nl = h->ndof_local();
+  for (int i = 0; i < 7; ++i)
+    if (!h->d_mr[i]) {
+      NLS_CUDA(h, cudaMalloc((void **)&h->d_mr[i], sizeof(double) * (size_t)std::max<int64_t>(1, nl)));
+      NLS_CUDA(h, cudaMemsetAsync(h->d_mr[i], 0, sizeof(double) * (size_t)std::max<int64_t>(1, nl), h->stream));
+    }
+  double *r1 = h->d_mr[0], *r2 = h->d_mr[1], *y = h->d_mr[2], *v = h->d_mr[3], *w = h->d_mr[4], *w1 = h->d_mr[5], *w2 = h->d_mr[6];
+  double *x = h->d_dU;
+  const unsigned g = vec_grid(h, n);
+  if ((rc = nls_launch_extract_dinv(h))) return rc;
+  NLS_CUDA(h, cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(w, 0, sizeof(double) * n, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(w2, 0, sizeof(double) * n, h->stream));
+  // r1 = masked b (constrained rows carry no equation)
+  k_prec_abs<<<g, 256, 0, h->stream>>>(n, h->d_dinv, h->d_con, h->d_b, y); NLS_KCHECK(h);          // y = M^-1 b (0 on constrained)
+  k_lincomb3<<<g, 256, 0, h->stream>>>(n, r1, 1.0, h->d_b, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
+  double beta1sq = 0.0;
+  if ((rc = nls_dev_dot(h, n, r1, y, &beta1sq))) return rc;     // y is zero on constrained rows, so the mask is implied
+  if (its) *its = 0;
+  if (relres) *relres = 0.0;
+  if (status) *status = 0;
+  if (!(beta1sq > 0.0)) { if (status) *status = (beta1sq == 0.0) ? 0 : 2; return NLS_OK; }   // b = 0 -> x = 0; NaN/negative -> breakdown
+  const double beta1 = sqrt(beta1sq);
+  k_lincomb3<<<g, 256, 0, h->stream>>>(n, r2, 1.0, r1, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
+  double oldb = 0.0, beta = beta1, dbar = 0.0, epsln = 0.0, phibar = beta1, cs = -1.0, sn = 0.0;
+  int itn = 0, st = 1;
+  while (itn < maxits) {
+    ++itn;
+    k_lincomb3<<<g, 256, 0, h->stream>>>(n, v, 1.0 / beta, y, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
+    if (h->distributed) { NLS_CUDA(h, cudaMemcpyAsync(h->d_p, v, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream)); if ((rc = nls_halo_exchange(h, h->d_p))) return rc; }
+    if ((rc = nls_launch_spmv(h, h->distributed ? h->d_p : v, y, true, false))) return rc;      // y = A v on the free block
+    if (itn >= 2) { k_lincomb3<<<g, 256, 0, h->stream>>>(n, y, 1.0, y, -beta / oldb, r1, 0.0, nullptr); NLS_KCHECK(h); }
+    double alfa = 0.0;
+    if ((rc = nls_dev_dot(h, n, v, y, &alfa))) return rc;
+    k_lincomb3<<<g, 256, 0, h->stream>>>(n, y, 1.0, y, -alfa / beta, r2, 0.0, nullptr); NLS_KCHECK(h);
+    std::swap(r1, r2);                                   // r1 <- r2
+    k_lincomb3<<<g, 256, 0, h->stream>>>(n, r2, 1.0, y, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);   // r2 <- y
+    k_prec_abs<<<g, 256, 0, h->stream>>>(n, h->d_dinv, h->d_con, r2, y); NLS_KCHECK(h);
+    oldb = beta;
+    double b2 = 0.0;
+    if ((rc = nls_dev_dot(h, n, r2, y, &b2))) return rc;
+    if (!(b2 >= 0.0)) { st = 2; break; }                 // NaN or an indefinite preconditioner
+    beta = sqrt(b2);
+    const double oldeps = epsln, delta = cs * dbar + sn * alfa, gbar = sn * dbar - cs * alfa;
+    epsln = sn * beta; dbar = -cs * beta;
+    const double gamma = std::max(sqrt(gbar * gbar + beta * beta), 2.220446049250313e-16);
+    cs = gbar / gamma; sn = beta / gamma;
+    const double phi = cs * phibar;
+    phibar = sn * phibar;
+    std::swap(w1, w2); std::swap(w2, w);                 // w1 <- w2, w2 <- w (old w is recycled as the new one)
+    k_lincomb3<<<g, 256, 0, h->stream>>>(n, w, 1.0 / gamma, v, -oldeps / gamma, w1, -delta / gamma, w2); NLS_KCHECK(h);
+    if ((rc = nls_launch_axpy(h, n, phi, w, x))) return rc;
+    if (fabs(phibar) <= rtol * beta1) { st = 0; break; }
+    if (beta == 0.0) { st = 0; break; }                  // exact Krylov subspace
+  }
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (its) *its = itn;
+  if (relres) *relres = fabs(phibar) / beta1;
+  if (status) *status = st;
+  return NLS_OK;
+}

@@ -112,6 +112,7 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   dev_free(&h->d_U); dev_free(&h->d_R); dev_free(&h->d_dU); dev_free(&h->d_r); dev_free(&h->d_p);
   dev_free(&h->d_Ap); dev_free(&h->d_dinv); dev_free(&h->d_b); dev_free(&h->d_tmp);
   dev_free(&h->d_partial); dev_free(&h->d_ctl); dev_free(&h->d_scal); dev_free(&h->d_prof);
+  for (int i = 0; i < 7; ++i) dev_free(&h->d_mr[i]);
   for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
   dev_free(&h->d_u_n);
   dev_free(&h->d_send_nodes); dev_free(&h->d_recv_nodes); dev_free(&h->d_sendbuf); dev_free(&h->d_recvbuf);
@@ -139,6 +140,7 @@ extern "C" int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64
     if (conn0[k] < 0 || conn0[k] >= nnodes) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_mesh: connectivity entry out of range (expects 0-based node ids)");
   free_pattern(h);
   dev_free(&h->d_lap); h->lap_valid = false;
+  for (int i = 0; i < 7; ++i) dev_free(&h->d_mr[i]);
   h->dim = dim; h->nen = nen; h->nn = nnodes; h->nel = nelem; h->n_owned = nnodes;
   h->h_conn.assign(conn0, conn0 + nelem * nen);
   h->h_coords.assign(coords, coords + nnodes * dim);
@@ -507,6 +509,23 @@ extern "C" int32_t nls_linear_solve(nls_handle h, double rtol, int32_t maxits, c
   NLS_CUDA(h, cudaMemcpyAsync(h->d_b, b, sizeof(double) * h->nrows, cudaMemcpyHostToDevice, h->stream));
   int li = 0, st = 0; double rr = 0.0;
   NLS_TRY(nls_pcg_solve(h, rtol, maxits, 0, &li, &rr, &st));
+  NLS_CUDA(h, cudaMemcpyAsync(x, h->d_dU, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (its) *its = li;
+  if (relres) *relres = rr;
+  if (status_out) *status_out = st;
+  return NLS_OK;
+}
+
+// symmetric indefinite variant (arc-length continuation past limit points): Jacobi-preconditioned MINRES
+extern "C" int32_t nls_linear_solve_indefinite(nls_handle h, double rtol, int32_t maxits, const double *b, double *x,
+                                               int32_t *its, double *relres, int32_t *status_out) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_linear_solve_indefinite: call nls_build_pattern first");
+  if (!b || !x || maxits < 0) NLS_FAIL(h, NLS_ERR_ARG, "nls_linear_solve_indefinite: bad arguments");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_b, b, sizeof(double) * h->nrows, cudaMemcpyHostToDevice, h->stream));
+  int li = 0, st = 0; double rr = 0.0;
+  NLS_TRY(nls_minres_solve(h, rtol, maxits, &li, &rr, &st));
   NLS_CUDA(h, cudaMemcpyAsync(x, h->d_dU, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   if (its) *its = li;

@@ -181,6 +181,7 @@ struct nls_context {
   double *d_U = nullptr, *d_R = nullptr, *d_dU = nullptr;
   double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr, *d_b = nullptr;
   double *d_tmp = nullptr;
+  double *d_mr[7] = {nullptr};          // MINRES work vectors (allocated on first use)
   double *d_partial = nullptr;          // block partial sums
   PcgCtl *d_ctl = nullptr;
   PcgCtl *h_ctl = nullptr;              // pinned mirror
@@ -265,6 +266,7 @@ double nls_dev_masked_norm2(nls_context *h, const double *v, bool masked, int *r
 int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, double *out);
 int nls_launch_axpy(nls_context *h, int64_t n, double a, const double *x, double *y);
 int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int *its, double *relres, int *status);
+int nls_minres_solve(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status);
 
 int nls_launch_mass_build(nls_context *h, double rho, double area);
 int nls_launch_apply_mass(nls_context *h, const double *x, double *y, bool accumulate);

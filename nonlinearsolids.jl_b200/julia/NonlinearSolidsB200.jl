@@ -270,4 +270,31 @@ function newmark_step!(s::B200NewtonSolver, mat, β, γ, Δt, Ut::Vector{Float64
     return a, U, Ud
 end
 
+# ---- arc-length continuation (SURVEY 8f-4): the bordered solve of newtonarclength_fem.jl:103-104 on the device -------
+"""Assemble the tangent at `d` on the device (CSR values stay there) -- the `dFint(fem, d, Kd)` of newtonarclength_fem.jl."""
+function tangent!(m::B200Model, mat, d::Vector{Float64})
+    sync_material!(m, mat); sync_boundaries!(m)
+    check(m.h, ccall((:nls_dev_upload_u, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}), m.h, d))
+    check(m.h, ccall((:nls_dev_assemble, libnls), Int32, (Ptr{Cvoid}, Int32, Int32), m.h, 0, 1))
+end
+
+"""`dofs(fem, Kd) \\ dofs(fem, rhs)` on the tangent assembled last; Jacobi-MINRES, valid past limit points where the tangent
+is indefinite. `rhs`, result: full-length vectors (zero on constrained DoFs, = expand())."""
+function tangent_solve(m::B200Model, rhs::Vector{Float64}; rtol=1e-12, maxits=200_000)
+    x = zeros(length(rhs)); its = Ref{Int32}(0); st = Ref{Int32}(0); rr = Ref{Float64}(0.0)
+    check(m.h, ccall((:nls_linear_solve_indefinite, libnls), Int32,
+        (Ptr{Cvoid}, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Int32}, Ref{Float64}, Ref{Int32}),
+        m.h, rtol, maxits, rhs, x, its, rr, st))
+    st[] == 0 || throw(LinearAlgebra.SingularException(Int(st[])))    # the branch newtonarclength_fem.jl:105-113 catches
+    return x
+end
+
+"""The bordered update `[Kd -Fext; g_d g_l] \\ [r_d; r_l]` (newtonarclength_fem.jl:103-104) by block elimination:
+two solves with the same tangent. All vectors full length; returns (dd, dlambda)."""
+function bordered_solve(m::B200Model, r_d, F_ext, g_d, g_l, r_l; kwargs...)
+    v1 = tangent_solve(m, r_d; kwargs...); v2 = tangent_solve(m, F_ext; kwargs...)
+    dl = (r_l - dot(g_d, v1)) / (g_l + dot(g_d, v2))
+    return v1 .+ dl .* v2, dl
+end
+
 end # module

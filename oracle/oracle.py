@@ -361,3 +361,80 @@ class OracleModel:
                             C.byref(ne), le.ctypes.data_as(_lp), C.byref(ng), gn.ctypes.data_as(_lp),
                             sp.ctypes.data_as(_lp), sn.ctypes.data_as(_lp))
         return dict(loc_elems=le, ghost_nodes=gn, send_ptr=sp, send_nodes=sn)
+
+
+# ---- arc-length continuation: nonlinearsolvers/newtonarclength_fem.jl:2-169, dense restatement ----------
+def newtonarclength(om, F_ext, b=0.5, da=0.1, rtol=1e-16, ftol=1e-16, stol=0.0, maxsteps=20, maxits=100, stop=None,
+                    sign_rule="det"):
+    """newtonarclength(fem, Fint, dFint, Fext; ...) restated with dense linear algebra for small models.
+    `om`: OracleModel without Neumann boundaries (Fint = its residual), F_ext: load vector (what Fext(fem, F_ext) fills).
+    The ArcLength functor and its gradient are newtonarclength.jl:6-22; the bordered system is solved as written
+    (newtonarclength_fem.jl:103-104). Calls the reference makes to functions that do not exist (updateboundaries!(fem),
+    step!(fem, dlambda), postprocess!(fem, d, res): newtonarclength_fem.jl:49,155-156) are dropped.
+    sign_rule: "det" = sign change of det(K) as in the reference (:64-70); "stiffness" = sign of dtilde . F_ext (what the
+    device path uses, which has no determinant)."""
+    n = om.ndof
+    free = ~om.constrained_mask().astype(bool)
+    F_ext = np.asarray(F_ext, dtype=np.float64)
+    d_hist = np.zeros((maxsteps, n)); lam = np.zeros(maxsteps); num_its = np.zeros(maxsteps, dtype=int)
+    res_d = np.zeros((maxsteps, maxits + 1)); res_l = np.zeros((maxsteps, maxits + 1))
+    Kf = lambda d: om.jacobian_dense(d)[np.ix_(free, free)]
+    Fint = lambda d: om.residual(d)        # (d with Dirichlet values, F_int)
+    K0 = Kf(d_hist[0])
+    Ff = F_ext[free]
+    dt0 = np.linalg.solve(K0, Ff)
+    kdiag = np.diag(K0).copy()
+    den = dt0 @ (kdiag * dt0)
+    f_arc = lambda dd, dl: np.sqrt((1 - b) * (dd @ (kdiag * dd)) / den + b * dl ** 2)
+    ind = lambda K, dt: (np.linalg.slogdet(K)[0] if sign_rule == "det" else np.sign(dt @ Ff))
+    ind_last, sign_last = ind(K0, dt0), 1.0
+    expand = lambda v: (lambda o: (o.__setitem__(free, v), o)[1])(np.zeros(n))
+    nsteps = 1
+    for s in range(maxsteps - 1):                          # Julia: for n in 1:maxsteps-1, n = s + 1
+        d = d_hist[s]
+        if s + 1 < 3:                                      # procedure 1
+            Kd = Kf(d)
+            dtn = np.linalg.solve(Kd, Ff)
+            dl = da / f_arc(dtn, 1.0)
+            ind_n = ind(Kd, dtn)
+            sgn = -sign_last if ind_n == -ind_last else sign_last
+            dl = sgn * abs(dl)
+            sign_last, ind_last = sgn, ind_n
+            dd = dl * dtn
+            dk = d + expand(dd)
+            lk = lam[s] + dl
+        else:                                              # procedure 2: quadratic extrapolation
+            lk = lam[s - 2] - 3 * lam[s - 1] + 3 * lam[s]
+            dk = d_hist[s - 2] - 3 * d_hist[s - 1] + 3 * d_hist[s]
+            dl = lk - lam[s]
+            dd = (dk - d_hist[s])[free]
+        dk, Fi = Fint(dk)
+        r_d = (lk * F_ext - Fi)[free]; r_l = da - f_arc(dd, dl)
+        norm_r0 = np.linalg.norm(r_d)
+        if norm_r0 < np.finfo(float).eps:
+            norm_r0 = 1.0
+        res_d[s + 1, 0], res_l[s + 1, 0] = norm_r0, r_l
+        k = 1
+        while k < maxits:
+            if res_d[s + 1, k - 1] < rtol * norm_r0 and res_l[s + 1, k - 1] / da < ftol:
+                break
+            Kd = Kf(dk)
+            f = f_arc(dd, dl)
+            g_d = (1 - b) * (dd * kdiag) / (f * den); g_l = b / f * dl
+            Kb = np.block([[Kd, -Ff[:, None]], [g_d[None, :], np.array([[g_l]])]])
+            delta = np.linalg.solve(Kb, np.concatenate([r_d, [r_l]]))
+            if np.linalg.norm(delta[:-1]) < stol and abs(delta[-1]) < stol:
+                break
+            dk = dk + expand(delta[:-1]); dd = dd + delta[:-1]
+            lk += delta[-1]; dl += delta[-1]
+            dk, Fi = Fint(dk)
+            r_d = (lk * F_ext - Fi)[free]; r_l = da - f_arc(dd, dl)
+            res_d[s + 1, k], res_l[s + 1, k] = np.linalg.norm(r_d), r_l
+            k += 1
+        num_its[s + 1] = k
+        d_hist[s + 1] = dk; lam[s + 1] = lk
+        nsteps = s + 2
+        if stop is not None and stop(d_hist[s + 1], lam[s + 1]):
+            break
+    return dict(d=d_hist[:nsteps], lam=lam[:nsteps], num_its=num_its[:nsteps], res_d=res_d[:nsteps], res_l=res_l[:nsteps],
+                num_steps=nsteps)

@@ -431,3 +431,35 @@ def test_newmark_linear_energy_conservation(orc):
     en = [0.5 * v[free] @ M[np.ix_(free, free)] @ v[free] + 0.5 * u[free] @ K[np.ix_(free, free)] @ u[free]
           for u, v in zip(out["U"], out["Ud"])]
     assert max(en) - min(en) <= 1e-12 * en[0] and en[0] > 0
+
+
+def test_arclength_restatement_snap_through(orc):
+    """newtonarclength_fem.jl restated: on a shallow arch the load factor passes a limit point, decreases on the unstable
+    branch and rises again; the reference's det(K) sign rule and the stiffness-parameter rule (what the device path uses)
+    give the same path; every converged state satisfies lambda F_ext = F_int(d) on the free DoFs."""
+    import __graft_entry__ as g
+    nls = g.load_package()
+    nx, ny, R, th0, t = 25, 3, 10.0, 0.25, 0.08
+    m = nls.grid_mesh((nx, ny), 2)
+    s, yy = m.coords[:, 0], m.coords[:, 1] * (nx - 1) / (ny - 1)
+    th, r = (2 * s - 1) * th0, R + (yy - 0.5) * t
+    X = np.stack([r * np.sin(th), r * np.cos(th) - R * np.cos(th0)], axis=1)
+    E, nu = 1000.0, 0.3
+    om = orc.OracleModel(2, m.conn, X, mat_kind=orc.MAT_NEOHOOKEAN, mat=(E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))))
+    ends = np.concatenate([np.arange(ny) * nx, np.arange(ny) * nx + nx - 1])
+    dofs = (ends[:, None] * 2 + np.arange(2)[None, :]).ravel()
+    om.set_dirichlet(dofs, np.zeros(len(dofs)))
+    apex = (ny - 1) * nx + nx // 2
+    F = np.zeros(om.ndof); F[2 * apex + 1] = -0.05
+    kw = dict(b=0.5, da=0.4, rtol=1e-7, ftol=1e-7, maxsteps=24, maxits=30)
+    a = orc.newtonarclength(om, F, sign_rule="det", **kw)
+    b = orc.newtonarclength(om, F, sign_rule="stiffness", **kw)
+    assert a["num_steps"] == b["num_steps"] == 24 and np.array_equal(a["num_its"], b["num_its"])
+    assert np.array_equal(a["lam"], b["lam"]) and np.array_equal(a["d"], b["d"])
+    lam = a["lam"]
+    k = int(np.argmax(lam[:14]))
+    assert 2 < k < 13 and lam[k + 4] < lam[k] and np.all(a["num_its"][1:] < 30), (k, lam)
+    free = ~om.constrained_mask().astype(bool)
+    for s_ in (k, k + 4, 23):
+        _, Fi = om.residual(a["d"][s_])
+        assert np.linalg.norm((lam[s_] * F - Fi)[free]) <= 1e-6 * np.linalg.norm(F)
