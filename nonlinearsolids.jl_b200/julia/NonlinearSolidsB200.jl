@@ -17,10 +17,11 @@
 module NonlinearSolidsB200
 
 using NonlinearSolids
+using LinearAlgebra
 import NonlinearSolids: solve!, solution, residual, iterations, model, numdof, is_converged,
     set_residual_fn!, set_jacobian_fn!, set_ctx!, compute_internalforce, compute_dinternalforce, save_state!
 
-export B200NewtonSolver, B200Model, NeoHookean
+export B200NewtonSolver, B200Model, NeoHookean, newmark_step!, tangent!, tangent_solve, bordered_solve
 
 const libnls = get(ENV, "NLS_B200_LIB", "libnls_b200.so")
 

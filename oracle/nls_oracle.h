@@ -17,6 +17,12 @@
  *     1..5 points, the three reference materials, dense K + dense LU Newton.
  * T2 (builder-defined extension): 2-D plane-strain /
  *     3-D Q1 compressible Neo-Hookean, CSR Jacobian, Jacobi-PCG.
+ * Dynamics and continuation: orc_mass_nodes here; the Newmark stepper and the arc-length
+ *     continuation are restated in oracle.py on top of these primitives with dense linear algebra (small cases).
+ *     The reference has no tests for mass.jl, newmark.jl or newtonarclength_fem.jl, and the last two are not
+ *     runnable as shipped, so their parity is unpinned too: the restatements are pinned by known answers (element
+ *     mass rho A L/6 [2 1;1 2], total mass, energy conservation of the average-acceleration rule, equilibrium of the
+ *     converged arc-length states), tests/test_oracle.py.
  */
 #ifndef NLS_ORACLE_H
 #define NLS_ORACLE_H
