@@ -450,8 +450,10 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
   const int chunk = fixed_iters > 0 ? fixed_iters : 16;
   int launched = 0;
   h->h_ctl->done = 0; h->h_ctl->iters = 0;
-  while (launched < total) {
-    const int todo = (total - launched < chunk) ? (total - launched) : chunk;
+  // One PCG iteration = 3 kernels (+ 3 exchanges when distributed). Single GPU: a full chunk of 16 iterations is
+  // captured once into a CUDA graph and replayed (the kernels take fixed pointers and read alpha/beta/done from the
+  // device control block), which removes the per-launch host cost that dominates small models.
+  auto iterate = [&](int todo) -> int {
     for (int i = 0; i < todo; ++i) {
       if ((rc = nls_launch_spmv(h, h->d_p, h->d_Ap, true, true))) return rc;
       if ((rc = nls_allreduce_sum(h, &h->d_ctl->red[0], 1))) return rc;
@@ -461,6 +463,35 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
       k_pcg_pupdate<<<vec_grid(h, n), 256, 0, h->stream>>>(n, h->d_r, h->d_dinv, h->d_p, h->d_ctl);
       NLS_KCHECK(h);
       if ((rc = nls_halo_exchange(h, h->d_p))) return rc;
+    }
+    return NLS_OK;
+  };
+  const bool use_graph = !h->distributed && h->opt_pcg_graph && fixed_iters == 0 && chunk == 16;
+  while (launched < total) {
+    const int todo = (total - launched < chunk) ? (total - launched) : chunk;
+    if (use_graph && todo == chunk) {
+      PcgGraph &G = h->pcg_graph;
+      const bool same = G.exec && G.vals == h->d_vals && G.con == h->d_con && G.n == n && G.nnz == h->nnz &&
+                        G.spmv == h->opt_spmv && G.lanes == h->opt_spmv_lanes;
+      if (!same) {
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = h->launches;
+        NLS_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = iterate(chunk);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = l0;                              // captured, not launched
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { h->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return NLS_ERR_CUDA; }
+        ce = cudaGraphInstantiate(&G.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { G.exec = nullptr; h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return NLS_ERR_CUDA; }
+        G.vals = h->d_vals; G.con = h->d_con; G.n = n; G.nnz = h->nnz; G.spmv = h->opt_spmv; G.lanes = h->opt_spmv_lanes;
+      }
+      NLS_CUDA(h, cudaGraphLaunch(G.exec, h->stream));
+      h->launches += 3 * chunk;
+    } else {
+      if ((rc = iterate(todo))) return rc;
     }
     launched += todo;
     NLS_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, h->stream));

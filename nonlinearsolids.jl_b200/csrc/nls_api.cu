@@ -47,6 +47,7 @@ static void free_pattern(nls_context *h) {
   nls_gather_free(h);
   nls_twophase_free(h);
   dev_free(&h->d_mass); h->have_mass = false;
+  if (h->pcg_graph.exec) { cudaGraphExecDestroy(h->pcg_graph.exec); h->pcg_graph = PcgGraph(); }
   h->h_browptr.clear(); h->h_bcol.clear();
   h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
 }
@@ -861,6 +862,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
   if (!std::strcmp(key, "twophase_3d")) { h->opt_twophase_3d = value; return NLS_OK; }
   if (!std::strcmp(key, "lap3d")) { h->opt_lap3d = value; return NLS_OK; }
+  if (!std::strcmp(key, "pcg_graph")) { h->opt_pcg_graph = value; return NLS_OK; }
   if (!std::strcmp(key, "scratch_mb")) {   // takes effect at the next nls_build_pattern
     h->opt_scratch_mb = value;
     if (h->have_pattern) { NLS_TRY(nls_twophase_build(h)); }

@@ -95,6 +95,14 @@ struct PcgCtl {
   double red[4];                    // scratch for allreduce: [0]=pAp partial, [1]=rz partial, [2]=rr partial
 };
 
+// captured chunk of 16 PCG iterations (single GPU), valid while the kernels' fixed arguments are unchanged
+struct PcgGraph {
+  cudaGraphExec_t exec = nullptr;
+  const void *vals = nullptr, *con = nullptr;
+  int64_t n = 0, nnz = 0;
+  int spmv = 0, lanes = 0;
+};
+
 struct NcclApi;                     // nccl_dyn.h
 
 // peer-memory (CUDA IPC over NVLink) data path of the halo exchange and the Krylov reductions (kernels_p2p.cu)
@@ -181,6 +189,8 @@ struct nls_context {
   double *d_U = nullptr, *d_R = nullptr, *d_dU = nullptr;
   double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr, *d_b = nullptr;
   double *d_tmp = nullptr;
+  PcgGraph pcg_graph;
+  int opt_pcg_graph = 1;
   double *d_mr[7] = {nullptr};          // MINRES work vectors (allocated on first use)
   double *d_partial = nullptr;          // block partial sums
   PcgCtl *d_ctl = nullptr;
