@@ -69,6 +69,40 @@ def main():
                                   rowptr=rp.tolist(), colind=ci.tolist(), vals=om.jacobian_csr(U).tolist())
     with open(os.path.join(HERE, "oracle_cases.json"), "w") as f:
         json.dump(cases, f)
+
+    # dynamics and continuation: mass matrix, Newmark histories, arc-length path
+    dyn = {}
+    c = cases["q1_2d_n4_distorted"]
+    om = orc.OracleModel(2, np.array(c["conn"], dtype=np.int32).reshape(-1, 4), np.array(c["coords"]).reshape(-1, 2),
+                         mat_kind=orc.MAT_NEOHOOKEAN, mat=(c["mu"], c["lam"]))
+    dyn["mass_q1_2d_n4_distorted"] = dict(case="q1_2d_n4_distorted", rho=1.7, vals=om.mass_csr(1.7).tolist())
+    p, q, nel, rho, A = 2, 3, 4, 2.0, 0.5
+    mesh = nls.bar_mesh(nel, p)
+    om = orc.OracleModel(1, mesh.conn, mesh.coords, p=p, nq=q, mat_kind=orc.MAT_EXPONENTIAL, mat=(1.0, 2.0), area=A)
+    om.set_dirichlet([0], [0.0]); om.set_neumann([mesh.nn - 1], [0.0])
+    out = om.newmark(rho, 0.05, 0.3, area=A, bc_update=lambda t: (None, [0.2 * t]), rtol=1e-11, atol=1e-13, maxits=20)
+    dyn["newmark_bar_exp_p2_q3"] = dict(nel=nel, p=p, q=q, rho=rho, area=A, dt=0.05, maxtime=0.3, tip_rate=0.2,
+                                        U=out["U"].tolist(), Ud=out["Ud"].tolist(), Udd=out["Udd"].tolist(),
+                                        num_its=out["num_its"].tolist())
+    nx, ny, R, th0, t = 25, 3, 10.0, 0.25, 0.08
+    m = nls.grid_mesh((nx, ny), 2)
+    s_, yy = m.coords[:, 0], m.coords[:, 1] * (nx - 1) / (ny - 1)
+    th, r = (2 * s_ - 1) * th0, R + (yy - 0.5) * t
+    X = np.stack([r * np.sin(th), r * np.cos(th) - R * np.cos(th0)], axis=1)
+    E, nu = 1000.0, 0.3
+    mu, lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    om = orc.OracleModel(2, m.conn, X, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mu, lam))
+    ends = np.concatenate([np.arange(ny) * nx, np.arange(ny) * nx + nx - 1])
+    dofs = (ends[:, None] * 2 + np.arange(2)[None, :]).ravel()
+    om.set_dirichlet(dofs, np.zeros(len(dofs)))
+    apex = (ny - 1) * nx + nx // 2
+    F = np.zeros(om.ndof); F[2 * apex + 1] = -0.05
+    out = orc.newtonarclength(om, F, b=0.5, da=0.4, rtol=1e-7, ftol=1e-7, maxsteps=20, maxits=30)
+    dyn["arclength_arch_25x3"] = dict(nx=nx, ny=ny, R=R, th0=th0, t=t, E=E, nu=nu, load=-0.05, b=0.5, da=0.4, rtol=1e-7, ftol=1e-7,
+                                      maxsteps=20, maxits=30, lam=out["lam"].tolist(), apex_v=out["d"][:, 2 * apex + 1].tolist(),
+                                      num_its=out["num_its"].tolist())
+    with open(os.path.join(HERE, "oracle_dynamics_cases.json"), "w") as f:
+        json.dump(dyn, f)
     print("wrote", os.listdir(HERE))
 
 

@@ -180,3 +180,50 @@ def test_two_rank_nccl_parity(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_golden_dynamics_fixtures(nls):
+    """Committed dynamics / continuation vectors (tests/golden/oracle_dynamics_cases.json: consistent mass, Newmark
+    histories, an arc-length path through a limit point) reproduced by the CUDA path."""
+    dyn = json.load(open(os.path.join(GOLD, "oracle_dynamics_cases.json")))
+    cases = json.load(open(os.path.join(GOLD, "oracle_cases.json")))
+    # consistent mass
+    g = dyn["mass_q1_2d_n4_distorted"]
+    c = cases[g["case"]]
+    fem = nls.FEMModel(nls.Mesh(2, np.array(c["conn"], dtype=np.int32).reshape(-1, 4), coords=np.array(c["coords"])))
+    mat = nls.NeoHookean(c["mu"], c["lam"]); mat.rho = g["rho"]
+    M = nls.CSRMatrix(fem)
+    nls.assemblemass(mat, fem, M)
+    assert rel_err(M.vals, np.array(g["vals"])) <= RTOL
+    # Newmark
+    g = dyn["newmark_bar_exp_p2_q3"]
+    mat = nls.ExponentialMaterial(1.0, 2.0, rho=g["rho"])
+    mesh = nls.bar_mesh(g["nel"], g["p"])
+    fem = nls.FEMModel(mesh, g["q"], g["p"], data={"A": g["area"]})
+    fem.addboundary(nls.Dirichlet([0], [0.0]))
+    fem.addboundary(nls.TimeDependent(nls.Neumann([mesh.nn - 1], [0.0]), lambda t: [g["tip_rate"] * t]))
+    s = nls.NewtonSolver(fem, rtol=1e-11, atol=1e-13, maxits=20, lin_rtol=1e-13)
+    nls.set_residual_fn(s, nls.Residual(mat)); nls.set_jacobian_fn(s, nls.Jacobian(mat))
+    ts = nls.NewmarkTimeStepper(s, mat, dt=g["dt"], maxtime=g["maxtime"])
+    nls.set_ctx(s, ts)
+    ts.solve()
+    assert ts.num_its[:ts.step + 1, 0].astype(int).tolist() == g["num_its"]
+    for mine, theirs in [(ts.U, g["U"]), (ts.Ud, g["Ud"]), (ts.Udd, g["Udd"])]:
+        assert rel_err(mine[:ts.step + 1], np.array(theirs)) <= 1e-10
+    # arc-length continuation
+    g = dyn["arclength_arch_25x3"]
+    nx, ny = g["nx"], g["ny"]
+    m = nls.grid_mesh((nx, ny), 2)
+    s_, yy = m.coords[:, 0], m.coords[:, 1] * (nx - 1) / (ny - 1)
+    th, r = (2 * s_ - 1) * g["th0"], g["R"] + (yy - 0.5) * g["t"]
+    X = np.stack([r * np.sin(th), r * np.cos(th) - g["R"] * np.cos(g["th0"])], axis=1)
+    fem = nls.FEMModel(nls.Mesh(2, m.conn, coords=X))
+    ends = np.concatenate([np.arange(ny) * nx, np.arange(ny) * nx + nx - 1])
+    dofs = (ends[:, None] * 2 + np.arange(2)[None, :]).ravel()
+    fem.addboundary(nls.Dirichlet(dofs, np.zeros(len(dofs))))
+    apex = (ny - 1) * nx + nx // 2
+    F = np.zeros(fem.ndof); F[2 * apex + 1] = g["load"]
+    res = nls.newtonarclength(fem, nls.NeoHookean(E=g["E"], nu=g["nu"]), F, b=g["b"], da=g["da"], rtol=g["rtol"], ftol=g["ftol"],
+                              maxsteps=g["maxsteps"], maxits=g["maxits"], lin_rtol=1e-13)
+    assert res.num_its.tolist() == g["num_its"]
+    assert rel_err(res.lam, np.array(g["lam"])) <= 1e-8 and rel_err(res.d[:, 2 * apex + 1], np.array(g["apex_v"])) <= 1e-8

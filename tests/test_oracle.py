@@ -463,3 +463,25 @@ def test_arclength_restatement_snap_through(orc):
     for s_ in (k, k + 4, 23):
         _, Fi = om.residual(a["d"][s_])
         assert np.linalg.norm((lam[s_] * F - Fi)[free]) <= 1e-6 * np.linalg.norm(F)
+
+
+def test_dynamics_golden_regression(orc):
+    """The committed dynamics / continuation vectors (tests/golden/oracle_dynamics_cases.json) are what the oracle produces."""
+    import json
+    import os
+    import __graft_entry__ as g
+    nls = g.load_package()
+    here = os.path.dirname(os.path.abspath(__file__))
+    dyn = json.load(open(os.path.join(here, "golden", "oracle_dynamics_cases.json")))
+    cases = json.load(open(os.path.join(here, "golden", "oracle_cases.json")))
+    c = cases[dyn["mass_q1_2d_n4_distorted"]["case"]]
+    om = orc.OracleModel(2, np.array(c["conn"], dtype=np.int32).reshape(-1, 4), np.array(c["coords"]).reshape(-1, 2),
+                         mat_kind=orc.MAT_NEOHOOKEAN, mat=(c["mu"], c["lam"]))
+    assert np.allclose(om.mass_csr(dyn["mass_q1_2d_n4_distorted"]["rho"]), dyn["mass_q1_2d_n4_distorted"]["vals"], rtol=1e-14, atol=0)
+    nm = dyn["newmark_bar_exp_p2_q3"]
+    mesh = nls.bar_mesh(nm["nel"], nm["p"])
+    om = orc.OracleModel(1, mesh.conn, mesh.coords, p=nm["p"], nq=nm["q"], mat_kind=orc.MAT_EXPONENTIAL, mat=(1.0, 2.0), area=nm["area"])
+    om.set_dirichlet([0], [0.0]); om.set_neumann([mesh.nn - 1], [0.0])
+    out = om.newmark(nm["rho"], nm["dt"], nm["maxtime"], area=nm["area"], bc_update=lambda t: (None, [nm["tip_rate"] * t]),
+                     rtol=1e-11, atol=1e-13, maxits=20)
+    assert out["num_its"].tolist() == nm["num_its"] and np.allclose(out["U"], nm["U"], rtol=1e-12, atol=1e-16)
