@@ -30,19 +30,22 @@
 #define G2_KS 50          // doubles per element in shared memory: 10 symmetric 2x2 blocks (40) + f_e (8) + 2 pad;
                           // 25 x 16 B (odd) -> the reduce-scatter's STS.128 are conflict-free
 #define G2_MAXSRC 8       // most elements around one node the packed block lists can hold
+#define G2_KREG 10        // symmetric blocks accumulated in registers (of 10); any rest lives in the element's smem record
+
+#define G2_HDR 8          // int32 words of the cluster header in front of the touched-node list
 
 struct GatherArgs {
   int64_t ncl;
   int maxt, maxe, maxb, nsw;  // padded strides: touched nodes, elements, CSR blocks; source words per block (2 or 4)
-  const int32_t *tn;      // [ncl][4 + maxt]: {nt, ne, nb, 0}, node ids
+  const int32_t *tn;      // [ncl][G2_HDR + maxt]: {nt, ne, nb, 0, base_lo, base_hi, 0, 0}, node ids; base = smallest block-row start
   const uint32_t *lconn;  // [ncl][maxe]: 4 local node indices (bytes) into the touched-node list
   const int32_t *cn;      // [ncl][G2_NCP] owned node ids (-1 = none)
-  const int64_t *b0;      // [ncl][G2_NCP] block-row start of the node
+  const int32_t *b0;      // [ncl][G2_NCP] block-row start of the node, relative to the cluster's base
   const int32_t *deg;     // [ncl][G2_NCP] block-row length
-  const uint32_t *bsrc;   // [ncl][1 + nsw][maxb]: word 0 = nl | jb << 8; then 16-bit source codes, two per word:
-                          //   offset of the 2x2 block in Ks (15 bits) | transposed << 15; unused sources point at the
-                          //   zero record Ks[maxe]
-  const uint16_t *rsrc;   // [ncl][G2_NCP][G2_MAXSRC]: offsets in Ks of the node's f_e pairs, ascending element; unused -> zero record
+  const uint16_t *btask;  // [ncl][maxb]: one task per CSR block: owner nl | column block jb << 7
+  const uint32_t *bsrc;   // [ncl][nsw][maxb]: 16-bit source codes, two per word: offset of the 2x2 block in Ks (15 bits) |
+                          //   transposed << 15; unused sources point at the zero record Ks[maxe]
+  const uint16_t *rsrc;   // [ncl][G2_NCP][2 nsw]: offsets in Ks of the node's f_e pairs, ascending element; unused -> zero record
   unsigned long long *prof; // optional per-phase cycle counters (nls_set_option "profile_phases"), else NULL
 };
 
@@ -62,7 +65,7 @@ template <bool DO_R, bool DO_K>
 // (8 LDS.128) instead of being held across the loop: 32 registers the accumulators need.
 __device__ __forceinline__ void q1_2d_qp_accumulate(const double2 *__restrict__ xu, const unsigned lc, const double *__restrict__ Tq,
                                                     const double w, const double mu, const double lam,
-                                                    double (&Kb)[10][4], double2 *__restrict__ ferec, const bool first) {
+                                                    double (&Kb)[G2_KREG][4], double2 *__restrict__ rec, const bool first) {
   double J[4] = {0, 0, 0, 0}, Ji[4], F[4] = {1, 0, 0, 1}, Fi[4], G[4][2], g[4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -93,11 +96,11 @@ __device__ __forceinline__ void q1_2d_qp_accumulate(const double2 *__restrict__ 
     // 16 registers fewer across the loop than keeping it beside the 40 K accumulators
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      double2 o = ferec[a];
+      double2 o = rec[20 + a];
       if (first) o = make_double2(0.0, 0.0);
       o.x = fma(P00, G[a][0], fma(P01, G[a][1], o.x));
       o.y = fma(P10, G[a][0], fma(P11, G[a][1], o.y));
-      ferec[a] = o;
+      rec[20 + a] = o;
     }
   }
   if (DO_K) {
@@ -111,35 +114,49 @@ __device__ __forceinline__ void q1_2d_qp_accumulate(const double2 *__restrict__ 
 #pragma unroll
       for (int b = a; b < 4; ++b) {
         const int s = ((a == 0) ? 0 : (a == 1 ? 4 : (a == 2 ? 7 : 9))) + (b - a);
-        Kb[s][0] = fma(d0, g[b][0], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Kb[s][0])));
-        Kb[s][1] = fma(c2g0, g[b][1], fma(c3g1, g[b][0], Kb[s][1]));
-        Kb[s][2] = fma(c2g1, g[b][0], fma(c3g0, g[b][1], Kb[s][2]));
-        Kb[s][3] = fma(d1, g[b][1], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Kb[s][3])));
+        if (s < G2_KREG) {
+          Kb[s][0] = fma(d0, g[b][0], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Kb[s][0])));
+          Kb[s][1] = fma(c2g0, g[b][1], fma(c3g1, g[b][0], Kb[s][1]));
+          Kb[s][2] = fma(c2g1, g[b][0], fma(c3g0, g[b][1], Kb[s][2]));
+          Kb[s][3] = fma(d1, g[b][1], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], Kb[s][3])));
+        } else {      // the last blocks are accumulated in the element's own record like f_e: registers for a third CTA per SM
+          double2 o0 = rec[2 * s], o1 = rec[2 * s + 1];
+          if (first) { o0 = make_double2(0.0, 0.0); o1 = make_double2(0.0, 0.0); }
+          o0.x = fma(d0, g[b][0], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], o0.x)));
+          o0.y = fma(c2g0, g[b][1], fma(c3g1, g[b][0], o0.y));
+          o1.x = fma(c2g1, g[b][0], fma(c3g0, g[b][1], o1.x));
+          o1.y = fma(d1, g[b][1], fma(c1Gx, G[b][0], fma(c1Gy, G[b][1], o1.y)));
+          rec[2 * s] = o0; rec[2 * s + 1] = o1;
+        }
       }
     }
   }
 }
 
+// Residency: the fused pass needs 222 registers to stay spill-free (two CTAs per SM); the Jacobian-only and
+// residual-only passes fit 168 and run three CTAs per SM (measured: fused 0.124 ms at 2 vs 0.134 ms at 3 with
+// spills; Jacobian-only 0.114 -> 0.105 ms at 3).
 template <bool DO_R, bool DO_K>
-__global__ void __launch_bounds__(G2_THREADS, 2)
+__global__ void __launch_bounds__(G2_THREADS, (DO_R && DO_K) ? 2 : 3)
 k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ TabQ1 T,
                    const __grid_constant__ MatParams mp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // ---- shared-memory carve-up (all sub-buffers 16-byte aligned) ----
-  const int tn_words = 4 + P.maxt;
+  // ---- shared-memory carve-up (all sub-buffers 16-byte aligned); 74.5 KB at C2 -> three CTAs per SM ----
+  const int tn_words = G2_HDR + P.maxt;
   double *Ks = reinterpret_cast<double *>(smem_raw);                                  // [maxe + 1][G2_KS], last record = zeros
   double *Tsm = Ks + (size_t)(P.maxe + 1) * G2_KS;                                    // 40 doubles: dN[4][4][2], w[4], pad
   int32_t *tnb = reinterpret_cast<int32_t *>(Tsm + 40);                               // [3][tn_words]
-  unsigned char *bbase = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);      // [2] stage buffers
-  const size_t b_xu = 0, b_b0 = b_xu + (size_t)P.maxt * 32, b_lc = b_b0 + G2_NCP * 8, b_cn = b_lc + (size_t)P.maxe * 4,
-               b_dg = b_cn + G2_NCP * 4, b_rs = b_dg + G2_NCP * 4, b_bs = b_rs + G2_NCP * G2_MAXSRC * 2,
-               b_size = b_bs + (size_t)(1 + P.nsw) * P.maxb * 4;
+  unsigned char *b1base = reinterpret_cast<unsigned char *>(tnb + 3 * tn_words);     // [2] stages of the phase-1 inputs
+  const size_t b1_xu = 0, b1_lc = (size_t)P.maxt * 32, b1_size = b1_lc + (size_t)P.maxe * 4;
+  unsigned char *B2 = b1base + 2 * b1_size;                                           // single stage of the phase-2 lists
+  const size_t b2_b0 = 0, b2_cn = b2_b0 + G2_NCP * 4, b2_dg = b2_cn + G2_NCP * 4, b2_rs = b2_dg + G2_NCP * 4,
+               b2_bt = b2_rs + (size_t)G2_NCP * 4 * P.nsw, b2_bs = b2_bt + (((size_t)P.maxb * 2 + 15) & ~(size_t)15);
   const int tid = threadIdx.x;
   if (tid < 32) Tsm[tid] = T.dN[tid >> 3][(tid >> 1) & 3][tid & 1];
   else if (tid < 36) Tsm[tid] = T.w[tid - 32];
   else if (tid >= 64 && tid < 64 + G2_KS) Ks[(size_t)P.maxe * G2_KS + tid - 64] = 0.0;
 
-  auto issue_A = [&](int64_t c, int k) {          // node list of cluster c -> tnb[k % 3]
+  auto issue_A = [&](int64_t c, int k) {          // header + node list of cluster c -> tnb[k % 3]
     if (c < P.ncl) {
       const int32_t *src = P.tn + c * tn_words;
       int32_t *dst = tnb + (k % 3) * tn_words;
@@ -147,27 +164,33 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
     }
     cp_async_commit();
   };
-  auto issue_B = [&](int64_t c, int k) {          // everything else of cluster c -> stage k & 1
+  auto issue_B1 = [&](int64_t c, int k) {         // phase-1 inputs of cluster c -> stage k & 1 (one cluster ahead)
     if (c < P.ncl) {
-      unsigned char *B = bbase + (size_t)(k & 1) * b_size;
+      unsigned char *B = b1base + (size_t)(k & 1) * b1_size;
       const int32_t *tn = tnb + (k % 3) * tn_words;
       const int nt = tn[0];
-      double *xu = reinterpret_cast<double *>(B + b_xu);
+      double *xu = reinterpret_cast<double *>(B + b1_xu);
       for (int t = tid; t < nt; t += G2_THREADS) {
-        const int id = tn[4 + t];
+        const int id = tn[G2_HDR + t];
         cp_async16(xu + 4 * t, A.coords + 2 * (int64_t)id);
         cp_async16(xu + 4 * t + 2, A.U + 2 * (int64_t)id);
       }
-      for (int w = tid * 2; w < G2_NCP; w += G2_THREADS * 2) cp_async16(B + b_b0 + w * 8, P.b0 + c * G2_NCP + w);
-      for (int w = tid * 4; w < P.maxe; w += G2_THREADS * 4) cp_async16(B + b_lc + w * 4, P.lconn + c * P.maxe + w);
-      for (int w = tid * 4; w < G2_NCP; w += G2_THREADS * 4) {
-        cp_async16(B + b_cn + w * 4, P.cn + c * G2_NCP + w);
-        cp_async16(B + b_dg + w * 4, P.deg + c * G2_NCP + w);
-      }
-      for (int w = tid * 8; w < G2_NCP * G2_MAXSRC; w += G2_THREADS * 8) cp_async16(B + b_rs + w * 2, P.rsrc + c * (G2_NCP * G2_MAXSRC) + w);
-      const int nbw = (1 + P.nsw) * P.maxb;   // uint32 entries, multiple of 4
-      for (int w = tid * 4; w < nbw; w += G2_THREADS * 4) cp_async16(B + b_bs + w * 4, P.bsrc + c * nbw + w);
+      for (int w = tid * 4; w < P.maxe; w += G2_THREADS * 4) cp_async16(B + b1_lc + w * 4, P.lconn + c * P.maxe + w);
     }
+    cp_async_commit();
+  };
+  auto issue_B2 = [&](int64_t c) {                // phase-2 lists of cluster c (same iteration: they land during phase 1)
+    for (int w = tid * 4; w < G2_NCP; w += G2_THREADS * 4) {
+      cp_async16(B2 + b2_b0 + w * 4, P.b0 + c * G2_NCP + w);
+      cp_async16(B2 + b2_cn + w * 4, P.cn + c * G2_NCP + w);
+      cp_async16(B2 + b2_dg + w * 4, P.deg + c * G2_NCP + w);
+    }
+    const int nrs = G2_NCP * 2 * P.nsw;           // uint16 entries, multiple of 8
+    for (int w = tid * 8; w < nrs; w += G2_THREADS * 8) cp_async16(B2 + b2_rs + w * 2, P.rsrc + c * nrs + w);
+    const int nbt = (P.maxb + 7) & ~7;            // uint16 entries
+    for (int w = tid * 8; w < nbt; w += G2_THREADS * 8) cp_async16(B2 + b2_bt + w * 2, P.btask + c * nbt + w);
+    const int nbw = P.nsw * P.maxb;               // uint32 entries, multiple of 4
+    for (int w = tid * 4; w < nbw; w += G2_THREADS * 4) cp_async16(B2 + b2_bs + w * 4, P.bsrc + c * nbw + w);
     cp_async_commit();
   };
 
@@ -177,54 +200,56 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   issue_A(c0 + cstep, 1);
   cp_async_wait<1>();            // A(0) landed
   __syncthreads();
-  issue_B(c0, 0);
+  issue_B1(c0, 0);
 
   int k = 0;
   for (int64_t c = c0; c < P.ncl; c += cstep, ++k) {
     const long long tp0 = P.prof ? clock64() : 0;
     issue_A(c + 2 * cstep, k + 2);
-    const long long tq0 = P.prof ? clock64() : 0;
-    cp_async_wait<1>();          // everything but A(k+2): A(k+1) and B(k) have landed
-    const long long tq1 = P.prof ? clock64() : 0;
-    __syncthreads();
-    const long long tq2 = P.prof ? clock64() : 0;
-    issue_B(c + cstep, k + 1);   // flies while cluster k is computed
+    cp_async_wait<1>();          // everything but A(k+2): A(k+1) and B1(k) have landed
+    __syncthreads();             // ... and every warp is done with the previous cluster's Ks and phase-2 lists
+    issue_B2(c);                 // lands while phase 1 runs
+    issue_B1(c + cstep, k + 1);  // the next cluster's phase-1 inputs
     const long long tp1 = P.prof ? clock64() : 0;
 
-    const unsigned char *B = bbase + (size_t)(k & 1) * b_size;
-    const int ne = tnb[(k % 3) * tn_words + 1];
-    const int nb = tnb[(k % 3) * tn_words + 2];
+    const unsigned char *B = b1base + (size_t)(k & 1) * b1_size;
+    const int32_t *hdr = tnb + (k % 3) * tn_words;
+    const int ne = hdr[1], nb = hdr[2];
+    const int64_t base = (int64_t)(uint32_t)hdr[4] | ((int64_t)hdr[5] << 32);
     // ---- phase 1: one thread per element, quadrature loop rolled (the accumulators are the register budget) ----
     {
-      const double *xu = reinterpret_cast<const double *>(B + b_xu);
-      const unsigned *lcv = reinterpret_cast<const unsigned *>(B + b_lc);
+      const double *xu = reinterpret_cast<const double *>(B + b1_xu);
+      const unsigned *lcv = reinterpret_cast<const unsigned *>(B + b1_lc);
       for (int sl = tid; sl < ne; sl += G2_THREADS) {
         const unsigned lc = lcv[sl];
-        double Kb[10][4];
+        double Kb[G2_KREG][4];
 #pragma unroll
-        for (int s = 0; s < 10; ++s)
+        for (int s = 0; s < G2_KREG; ++s)
 #pragma unroll
           for (int j = 0; j < 4; ++j) Kb[s][j] = 0.0;
         double2 *dst = reinterpret_cast<double2 *>(Ks + (size_t)sl * G2_KS);
 #pragma unroll 1
         for (int q = 0; q < 4; ++q)
-          q1_2d_qp_accumulate<DO_R, DO_K>(reinterpret_cast<const double2 *>(xu), lc, Tsm + q * 8, Tsm[32 + q], mu, lam, Kb, dst + 20, q == 0);
+          q1_2d_qp_accumulate<DO_R, DO_K>(reinterpret_cast<const double2 *>(xu), lc, Tsm + q * 8, Tsm[32 + q], mu, lam, Kb, dst, q == 0);
         if (DO_K) {
 #pragma unroll
-          for (int s = 0; s < 10; ++s) { dst[2 * s] = make_double2(Kb[s][0], Kb[s][1]); dst[2 * s + 1] = make_double2(Kb[s][2], Kb[s][3]); }
+          for (int s = 0; s < G2_KREG; ++s) { dst[2 * s] = make_double2(Kb[s][0], Kb[s][1]); dst[2 * s + 1] = make_double2(Kb[s][2], Kb[s][3]); }
         }
       }
     }
+    cp_async_wait<1>();          // everything but B1(k+1): the phase-2 lists B2(k) have landed
     __syncthreads();
     const long long tp2 = P.prof ? clock64() : 0;
     // ---- phase 2: one task per CSR block of the cluster's rows: sum the element blocks that land in it, in
     //      ascending element order (padded list: unused sources read the zero record), and write its two row
     //      segments (adjacent tasks -> adjacent 16 B). R: one task per node over its f_e list. ----
     if (DO_K) {
-      const uint32_t *bs = reinterpret_cast<const uint32_t *>(B + b_bs);
-      const int64_t *b0v = reinterpret_cast<const int64_t *>(B + b_b0);
-      const int32_t *dgv = reinterpret_cast<const int32_t *>(B + b_dg);
+      const uint16_t *bt = reinterpret_cast<const uint16_t *>(B2 + b2_bt);
+      const uint32_t *bs = reinterpret_cast<const uint32_t *>(B2 + b2_bs);
+      const int32_t *b0v = reinterpret_cast<const int32_t *>(B2 + b2_b0);
+      const int32_t *dgv = reinterpret_cast<const int32_t *>(B2 + b2_dg);
       const unsigned ks_s = (unsigned)__cvta_generic_to_shared(Ks);
+      double *vbase = A.vals + 4 * base;
       auto ld2 = [](unsigned addr, double2 &lo_, double2 &hi_) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(lo_.x), "=d"(lo_.y) : "r"(addr));
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(hi_.x), "=d"(hi_.y) : "r"(addr));
@@ -234,7 +259,7 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
         // two tasks are interleaved, so 16 LDS.128 are in flight per thread instead of a dependent chain
 #pragma unroll 2
         for (int blk = tid; blk < nb; blk += G2_THREADS) {
-          const uint32_t w0 = bs[blk], c0w = bs[P.maxb + blk], c1w = bs[2 * P.maxb + blk];
+          const uint32_t w0 = bt[blk], c0w = bs[blk], c1w = bs[P.maxb + blk];
           double2 x[4][2];
           ld2(ks_s + ((c0w & 0x7fffu) << 3), x[0][0], x[0][1]);
           ld2(ks_s + ((c0w >> 13) & 0x3fff8u), x[1][0], x[1][1]);
@@ -247,18 +272,18 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
             lo.x += x[s4][0].x; lo.y += tr[s4] ? x[s4][1].x : x[s4][0].y;
             hi.x += tr[s4] ? x[s4][0].y : x[s4][1].x; hi.y += x[s4][1].y;
           }
-          const int nl = w0 & 0xff, jb = (w0 >> 8) & 0xff;
-          double *row = A.vals + 4 * b0v[nl] + 2 * jb;
+          const int nl = w0 & 0x7f, jb = w0 >> 7;
+          double *row = vbase + 4 * (int64_t)b0v[nl] + 2 * jb;
           *reinterpret_cast<double2 *>(row) = lo;
           *reinterpret_cast<double2 *>(row + 2 * dgv[nl]) = hi;
         }
       } else {
         for (int blk = tid; blk < nb; blk += G2_THREADS) {
-          const uint32_t w0 = bs[blk];
-          const int nl = w0 & 0xff, jb = (w0 >> 8) & 0xff;
+          const uint32_t w0 = bt[blk];
+          const int nl = w0 & 0x7f, jb = w0 >> 7;
           double2 lo = make_double2(0.0, 0.0), hi = make_double2(0.0, 0.0);
           for (int sw = 0; sw < P.nsw; ++sw) {
-            const uint32_t cw = bs[(1 + sw) * P.maxb + blk];
+            const uint32_t cw = bs[sw * P.maxb + blk];
             double2 x0, x1, y0, y1;
             ld2(ks_s + ((cw & 0x7fffu) << 3), x0, x1);
             ld2(ks_s + ((cw >> 13) & 0x3fff8u), y0, y1);
@@ -266,42 +291,35 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
             lo.x += x0.x; lo.y += tr0 ? x1.x : x0.y; hi.x += tr0 ? x0.y : x1.x; hi.y += x1.y;
             lo.x += y0.x; lo.y += tr1 ? y1.x : y0.y; hi.x += tr1 ? y0.y : y1.x; hi.y += y1.y;
           }
-          double *row = A.vals + 4 * b0v[nl] + 2 * jb;
+          double *row = vbase + 4 * (int64_t)b0v[nl] + 2 * jb;
           *reinterpret_cast<double2 *>(row) = lo;
           *reinterpret_cast<double2 *>(row + 2 * dgv[nl]) = hi;
         }
       }
     }
     if (DO_R) {
-      const int32_t *cnv = reinterpret_cast<const int32_t *>(B + b_cn);
+      const int32_t *cnv = reinterpret_cast<const int32_t *>(B2 + b2_cn);
+      const uint32_t *rsv = reinterpret_cast<const uint32_t *>(B2 + b2_rs);
       for (int nl = tid; nl < G2_NC; nl += G2_THREADS) {
         const int node = cnv[nl];
         if (node < 0) continue;
-        const uint4 rc = *reinterpret_cast<const uint4 *>(B + b_rs + nl * (G2_MAXSRC * 2));
-        const unsigned rw[4] = {rc.x, rc.y, rc.z, rc.w};
         double2 rs = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int sw = 0; sw < G2_MAXSRC / 2; ++sw) {
-          if (sw < P.nsw) {
-            const double2 f0 = *reinterpret_cast<const double2 *>(Ks + (rw[sw] & 0xffffu));
-            const double2 f1 = *reinterpret_cast<const double2 *>(Ks + (rw[sw] >> 16));
-            rs.x += f0.x; rs.y += f0.y;
-            rs.x += f1.x; rs.y += f1.y;
-          }
+        for (int sw = 0; sw < P.nsw; ++sw) {
+          const uint32_t rw = rsv[nl * P.nsw + sw];
+          const double2 f0 = *reinterpret_cast<const double2 *>(Ks + (rw & 0xffffu));
+          const double2 f1 = *reinterpret_cast<const double2 *>(Ks + (rw >> 16));
+          rs.x += f0.x; rs.y += f0.y;
+          rs.x += f1.x; rs.y += f1.y;
         }
         *reinterpret_cast<double2 *>(A.R + 2 * (int64_t)node) = rs;
       }
     }
-    __syncthreads();             // Ks and stage k & 1 are free again
     if (P.prof && tid == 0) {
       const long long tp3 = clock64();
-      atomicAdd(P.prof + 0, (unsigned long long)(tp1 - tp0));   // staging wait + issue
+      atomicAdd(P.prof + 0, (unsigned long long)(tp1 - tp0));   // staging: waits + issue
       atomicAdd(P.prof + 1, (unsigned long long)(tp2 - tp1));   // phase 1
-      atomicAdd(P.prof + 3, (unsigned long long)(tp3 - tp2));   // phase 2
+      atomicAdd(P.prof + 3, (unsigned long long)(tp3 - tp2));   // phase 2 (thread 0's own tasks)
       atomicAdd(P.prof + 4, 1ull);                               // clusters
-      atomicAdd(P.prof + 5, (unsigned long long)(tq1 - tq0));   // cp.async wait
-      atomicAdd(P.prof + 6, (unsigned long long)(tq2 - tq1));   // barrier after the wait
-      atomicAdd(P.prof + 7, (unsigned long long)(tp1 - tq2));   // issue of the next cluster's stage
     }
   }
   cp_async_wait<0>();
@@ -324,9 +342,9 @@ int nls_gather_nc(void) { return G2_NC; }
 void nls_gather_tile(int *t) { t[0] = G2_TX; t[1] = G2_TY; t[2] = 1; }
 
 static size_t gather_smem(int maxt, int maxe, int maxb, int nsw) {
-  const size_t bsz = (size_t)maxt * 32 + G2_NCP * 8 + (size_t)maxe * 4 + G2_NCP * 4 + G2_NCP * 4 + G2_NCP * G2_MAXSRC * 2 +
-                     (size_t)(1 + nsw) * maxb * 4;
-  return (size_t)(maxe + 1) * G2_KS * 8 + 40 * 8 + (size_t)3 * (4 + maxt) * 4 + 2 * bsz;
+  const size_t b1 = (size_t)maxt * 32 + (size_t)maxe * 4;
+  const size_t b2 = (size_t)G2_NCP * 12 + (size_t)G2_NCP * 4 * nsw + (((size_t)maxb * 2 + 15) & ~(size_t)15) + (size_t)nsw * maxb * 4;
+  return (size_t)(maxe + 1) * G2_KS * 8 + 40 * 8 + (size_t)3 * (G2_HDR + maxt) * 4 + 2 * b1 + b2;
 }
 
 void nls_gather_free(nls_context *h) {
@@ -336,6 +354,7 @@ void nls_gather_free(nls_context *h) {
   if (g.cn) cudaFree(g.cn);
   if (g.b0) cudaFree(g.b0);
   if (g.deg) cudaFree(g.deg);
+  if (g.btask) cudaFree(g.btask);
   if (g.bsrc) cudaFree(g.bsrc);
   if (g.rsrc) cudaFree(g.rsrc);
   g = GatherPlanDev();
@@ -363,30 +382,34 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
     t.erase(std::unique(t.begin(), t.end()), t.end());
     maxt = std::max<int>(maxt, (int)t.size());
     int nb = 0;
+    int64_t lo = INT64_MAX, hi = 0;
     for (int nl = 0; nl < G2_NC; ++nl) {
       const int32_t a = plan.nodes[c * G2_NC + nl];
-      if (a >= 0) nb += (int)(h->h_browptr[a + 1] - h->h_browptr[a]);
+      if (a < 0) continue;
+      nb += (int)(h->h_browptr[a + 1] - h->h_browptr[a]);
+      lo = std::min(lo, h->h_browptr[a]); hi = std::max(hi, h->h_browptr[a]);
     }
+    if (nb > 0 && hi - lo > 0x1fffffff) return NLS_OK;      // block rows of one cluster too far apart for 32-bit offsets
     maxb = std::max(maxb, nb);
   }
   if (maxt > 255) return NLS_OK;
-  const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, MAXB = (maxb + 3) & ~3;
+  const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, MAXB = (maxb + 7) & ~7;
   const int NSW = plan.max_adj <= 4 ? 2 : 4;       // 16-bit source codes, two per word
-  if (gather_smem(MAXT, MAXE, MAXB, NSW) > (size_t)110 * 1024) return NLS_OK;   // two CTAs per SM
-  const int tnw = 4 + MAXT, bw = (1 + NSW) * MAXB;
-  std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NCP, -1), deg((size_t)ncl * G2_NCP, 0);
+  if (gather_smem(MAXT, MAXE, MAXB, NSW) > (size_t)110 * 1024) return NLS_OK;   // at least two CTAs per SM
+  const int tnw = G2_HDR + MAXT;
+  std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NCP, -1), deg((size_t)ncl * G2_NCP, 0), b0((size_t)ncl * G2_NCP, 0);
   std::vector<uint32_t> lconn((size_t)ncl * MAXE, 0);
-  std::vector<int64_t> b0((size_t)ncl * G2_NCP, 0);
   const uint32_t none = (uint32_t)(MAXE * G2_KS);   // the zero record, not transposed
-  std::vector<uint32_t> bsrc((size_t)ncl * bw, none | (none << 16));
-  std::vector<uint16_t> rsrc((size_t)ncl * G2_NCP * G2_MAXSRC, (uint16_t)(none + 40));
+  std::vector<uint32_t> bsrc((size_t)ncl * NSW * MAXB, none | (none << 16));
+  std::vector<uint16_t> btask((size_t)ncl * MAXB, 0);
+  std::vector<uint16_t> rsrc((size_t)ncl * G2_NCP * 2 * NSW, (uint16_t)(none + 40));
   static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
   std::vector<int> nsrc_of;
   for (int64_t c = 0; c < ncl; ++c) {
     const std::vector<int32_t> &t = touched[c];
     const int32_t e0 = plan.eptr[c], ne = plan.eptr[c + 1] - e0;
     tn[c * tnw] = (int32_t)t.size(); tn[c * tnw + 1] = ne;
-    std::copy(t.begin(), t.end(), tn.begin() + c * tnw + 4);
+    std::copy(t.begin(), t.end(), tn.begin() + c * tnw + G2_HDR);
     for (int32_t s = 0; s < ne; ++s) {
       uint32_t packed = 0;
       for (int a = 0; a < nen; ++a) {
@@ -395,20 +418,27 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
       }
       lconn[c * MAXE + s] = packed;
     }
-    uint32_t *bs = bsrc.data() + (size_t)c * bw;
+    int64_t base = INT64_MAX;
+    for (int nl = 0; nl < G2_NC; ++nl) {
+      const int32_t a = plan.nodes[c * G2_NC + nl];
+      if (a >= 0) base = std::min(base, h->h_browptr[a]);
+    }
+    if (base == INT64_MAX) base = 0;
+    tn[c * tnw + 4] = (int32_t)(uint32_t)(base & 0xffffffffll); tn[c * tnw + 5] = (int32_t)(base >> 32);
+    uint16_t *bt = btask.data() + (size_t)c * MAXB;
+    uint32_t *bs = bsrc.data() + (size_t)c * NSW * MAXB;
     int nb = 0;
     for (int nl = 0; nl < G2_NC; ++nl) {
       const int32_t a = plan.nodes[c * G2_NC + nl];
       if (a < 0) continue;
       cn[c * G2_NCP + nl] = a;
-      b0[c * G2_NCP + nl] = h->h_browptr[a];
+      b0[c * G2_NCP + nl] = (int32_t)(h->h_browptr[a] - base);
       const int dg = (int)(h->h_browptr[a + 1] - h->h_browptr[a]);
       deg[c * G2_NCP + nl] = dg;
       const int32_t *lo = h->h_bcol.data() + h->h_browptr[a], *hi = lo + dg;
       const int blk0 = nb;
       nsrc_of.assign(dg, 0);
-      for (int jb = 0; jb < dg; ++jb)
-        bs[blk0 + jb] = (uint32_t)nl | ((uint32_t)jb << 8);
+      for (int jb = 0; jb < dg; ++jb) bt[blk0 + jb] = (uint16_t)(nl | (jb << 7));
       int nrs = 0;
       nb += dg;
       for (int32_t s = 0; s < ne; ++s) {          // ascending slot = ascending element id
@@ -416,26 +446,26 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
         int al = -1;
         for (int q = 0; q < nen; ++q) if (ce[q] == a) al = q;
         if (al < 0) continue;
-        rsrc[((size_t)c * G2_NCP + nl) * G2_MAXSRC + nrs++] = (uint16_t)(s * G2_KS + 40 + al * 2);
+        if (nrs >= 2 * NSW) return NLS_OK;
+        rsrc[((size_t)c * G2_NCP + nl) * 2 * NSW + nrs++] = (uint16_t)(s * G2_KS + 40 + al * 2);
         for (int b = 0; b < nen; ++b) {
           const int jb = (int)(std::lower_bound(lo, hi, ce[b]) - lo);
           const int k = nsrc_of[jb]++;
           if (k >= 2 * NSW) return NLS_OK;        // more elements on one block than the packed list holds
           const int lo_ = std::min(al, b), hi_ = std::max(al, b);
           const uint32_t code = (uint32_t)(s * G2_KS + (bd[lo_] + (hi_ - lo_)) * 4) | (al > b ? 0x8000u : 0u);
-          uint32_t &wsrc = bs[(size_t)(1 + k / 2) * MAXB + blk0 + jb];
+          uint32_t &wsrc = bs[(size_t)(k / 2) * MAXB + blk0 + jb];
           wsrc = (k & 1) ? ((wsrc & 0x0000ffffu) | (code << 16)) : ((wsrc & 0xffff0000u) | code);
         }
       }
     }
     tn[c * tnw + 2] = nb;
-    for (int j = nb; j < MAXB; ++j) bs[j] = 0;    // unused tail (never read: tasks stop at nb)
   }
   GatherPlanDev &g = h->gplan;
   g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.maxb = MAXB; g.nsw = NSW;
 #define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&g.field, sizeof(vec[0]) * vec.size())); \
   NLS_CUDA(h, cudaMemcpyAsync(g.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
-  UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(bsrc, bsrc); UP(rsrc, rsrc);
+  UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(btask, btask); UP(bsrc, bsrc); UP(rsrc, rsrc);
 #undef UP
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_plan = true;
@@ -447,7 +477,7 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
   a.nel = h->nel; a.n_owned = h->n_owned; a.conn = h->d_conn; a.coords = h->d_coords; a.U = h->d_U;
   a.R = h->d_R; a.vals = h->d_vals; a.browptr = h->d_browptr; a.pos = h->d_pos;
   const GatherPlanDev &g = h->gplan;
-  GatherArgs p{g.ncl, g.maxt, g.maxe, g.maxb, g.nsw, g.tn, g.lconn, g.cn, g.b0, g.deg, g.bsrc, g.rsrc,
+  GatherArgs p{g.ncl, g.maxt, g.maxe, g.maxb, g.nsw, g.tn, g.lconn, g.cn, g.b0, g.deg, g.btask, g.bsrc, g.rsrc,
                h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr};
   const size_t shm = gather_smem(g.maxt, g.maxe, g.maxb, g.nsw);
   if (!h->attr_gather) {       // per device: raised once per handle to the opt-in maximum
@@ -456,7 +486,9 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
     cudaFuncSetAttribute(k_asm_q1_2d_gather<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_optin_smem);
     h->attr_gather = true;
   }
-  const int per_sm = h->opt_gather_ctas > 0 ? h->opt_gather_ctas : 2;
+  // persistent CTAs: as many per SM as the shared memory admits (3 for <= 4 elements around a node, else 2)
+  const int fit = (int)std::min<size_t>((want_r && want_k) ? 2 : 3, ((size_t)h->max_optin_smem + 1024) / (shm + 1024));
+  const int per_sm = h->opt_gather_ctas > 0 ? h->opt_gather_ctas : std::max(1, fit);
   const unsigned grid = (unsigned)std::min<int64_t>(g.ncl, (int64_t)h->sm_count * per_sm);
   if (want_r && want_k) k_asm_q1_2d_gather<true, true><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
   else if (want_r)      k_asm_q1_2d_gather<true, false><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);

@@ -64,8 +64,9 @@ struct GatherPlanDev {
   int32_t *tn = nullptr;
   uint32_t *lconn = nullptr;
   int32_t *cn = nullptr;
-  int64_t *b0 = nullptr;
+  int32_t *b0 = nullptr;
   int32_t *deg = nullptr;
+  uint16_t *btask = nullptr;
   uint32_t *bsrc = nullptr;
   uint16_t *rsrc = nullptr;
 };
