@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SIDE = 708          # C2: 708^2 nodes = 1 002 528 DoF
-NCU_TRAFFIC_BYTES = 194.3e6   # measured DRAM traffic of the assembly kernel at C2 (see roofline.traffic_source)
+NCU_TRAFFIC_BYTES = 176.1e6   # measured DRAM traffic of the assembly kernel at C2 (see roofline.traffic_source)
 DIM = 2
 E_MOD, NU = 1.0, 0.3
 
@@ -282,9 +282,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": NCU_TRAFFIC_BYTES if args.assembly in (None, 1) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r1j_ncu_asm2d_gather_v10.txt): 95.0 MB read + 99.2 MB written; the 18 MB above the algorithmic "
-                                           "bytes are the staged cluster plan (node lists, per-block source lists), part of the freshly "
-                                           "written CSR values is still in the 126 MB L2 when the kernel ends",
+                                           "(profiles/r1k_ncu_asm2d_gather_v11.txt): 79.4 MB read + 96.7 MB written; the reads include ~45 MB of staged "
+                                           "cluster plan (node lists, per-block source lists) on top of U and the coordinates, while part of the "
+                                           "freshly written CSR values is still in the 126 MB L2 when the kernel ends",
                          "kernel": "k_asm_q1_2d_gather<R,K> (one launch = one fused assembly pass; no zero-fill needed)"
                                    if args.assembly in (None, 1) else "k_asm_q1_2d<R,K> + zero-fill of R and CSR values",
                          "algorithmic_bytes": abytes, "peak_source": which},
