@@ -35,7 +35,8 @@
 #define G2_HDR 8          // int32 words of the cluster header in front of the touched-node list
 
 struct GatherArgs {
-  int64_t ncl;
+  int64_t ncl;            // this launch walks clusters [c_begin, ncl)
+  int64_t c_begin;
   int maxt, maxe, maxb, nsw;  // padded strides: touched nodes, elements, CSR blocks; source words per block (2 or 4)
   const int32_t *tn;      // [ncl][G2_HDR + maxt]: {nt, ne, nb, 0, base_lo, base_hi, 0, 0}, node ids; base = smallest block-row start
   const uint32_t *lconn;  // [ncl][maxe]: 4 local node indices (bytes) into the touched-node list
@@ -195,7 +196,7 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
   };
 
   const double mu = mp.p[0], lam = mp.p[1];
-  const int64_t c0 = blockIdx.x, cstep = gridDim.x;
+  const int64_t c0 = P.c_begin + blockIdx.x, cstep = gridDim.x;
   issue_A(c0, 0);
   issue_A(c0 + cstep, 1);
   cp_async_wait<1>();            // A(0) landed
@@ -396,6 +397,16 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   const int MAXT = (maxt + 3) & ~3, MAXE = (plan.max_elems + 3) & ~3, MAXB = (maxb + 7) & ~7;
   const int NSW = plan.max_adj <= 4 ? 2 : 4;       // 16-bit source codes, two per word
   if (gather_smem(MAXT, MAXE, MAXB, NSW) > (size_t)110 * 1024) return NLS_OK;   // at least two CTAs per SM
+  // clusters that touch a ghost node go last: the multi-GPU assembly runs the others while the halo is in flight
+  std::vector<int64_t> order((size_t)ncl);
+  int64_t n_interior = 0;
+  {
+    std::vector<int64_t> bnd;
+    for (int64_t c = 0; c < ncl; ++c) {
+      if (!touched[c].empty() && touched[c].back() >= h->n_owned) bnd.push_back(c); else order[n_interior++] = c;
+    }
+    std::copy(bnd.begin(), bnd.end(), order.begin() + n_interior);
+  }
   const int tnw = G2_HDR + MAXT;
   std::vector<int32_t> tn((size_t)ncl * tnw, 0), cn((size_t)ncl * G2_NCP, -1), deg((size_t)ncl * G2_NCP, 0), b0((size_t)ncl * G2_NCP, 0);
   std::vector<uint32_t> lconn((size_t)ncl * MAXE, 0);
@@ -405,9 +416,10 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   std::vector<uint16_t> rsrc((size_t)ncl * G2_NCP * 2 * NSW, (uint16_t)(none + 40));
   static const int bd[4] = {0, 4, 7, 9};           // first symmetric block of local row a
   std::vector<int> nsrc_of;
-  for (int64_t c = 0; c < ncl; ++c) {
-    const std::vector<int32_t> &t = touched[c];
-    const int32_t e0 = plan.eptr[c], ne = plan.eptr[c + 1] - e0;
+  for (int64_t c = 0; c < ncl; ++c) {         // c = position in the device arrays, pc = cluster of the host plan
+    const int64_t pc = order[c];
+    const std::vector<int32_t> &t = touched[pc];
+    const int32_t e0 = plan.eptr[pc], ne = plan.eptr[pc + 1] - e0;
     tn[c * tnw] = (int32_t)t.size(); tn[c * tnw + 1] = ne;
     std::copy(t.begin(), t.end(), tn.begin() + c * tnw + G2_HDR);
     for (int32_t s = 0; s < ne; ++s) {
@@ -420,7 +432,7 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
     }
     int64_t base = INT64_MAX;
     for (int nl = 0; nl < G2_NC; ++nl) {
-      const int32_t a = plan.nodes[c * G2_NC + nl];
+      const int32_t a = plan.nodes[pc * G2_NC + nl];
       if (a >= 0) base = std::min(base, h->h_browptr[a]);
     }
     if (base == INT64_MAX) base = 0;
@@ -429,7 +441,7 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
     uint32_t *bs = bsrc.data() + (size_t)c * NSW * MAXB;
     int nb = 0;
     for (int nl = 0; nl < G2_NC; ++nl) {
-      const int32_t a = plan.nodes[c * G2_NC + nl];
+      const int32_t a = plan.nodes[pc * G2_NC + nl];
       if (a < 0) continue;
       cn[c * G2_NCP + nl] = a;
       b0[c * G2_NCP + nl] = (int32_t)(h->h_browptr[a] - base);
@@ -462,7 +474,7 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
     tn[c * tnw + 2] = nb;
   }
   GatherPlanDev &g = h->gplan;
-  g.ncl = ncl; g.maxt = MAXT; g.maxe = MAXE; g.maxb = MAXB; g.nsw = NSW;
+  g.ncl = ncl; g.ncl_interior = n_interior; g.maxt = MAXT; g.maxe = MAXE; g.maxb = MAXB; g.nsw = NSW;
 #define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&g.field, sizeof(vec[0]) * vec.size())); \
   NLS_CUDA(h, cudaMemcpyAsync(g.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
   UP(tn, tn); UP(lconn, lconn); UP(cn, cn); UP(b0, b0); UP(deg, deg); UP(btask, btask); UP(bsrc, bsrc); UP(rsrc, rsrc);
@@ -472,12 +484,14 @@ int nls_gather_build(nls_context *h, const AsmPlan &plan) {
   return NLS_OK;
 }
 
-int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
+int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k, int64_t c_begin, int64_t c_end) {
   AsmArgs a{};
   a.nel = h->nel; a.n_owned = h->n_owned; a.conn = h->d_conn; a.coords = h->d_coords; a.U = h->d_U;
   a.R = h->d_R; a.vals = h->d_vals; a.browptr = h->d_browptr; a.pos = h->d_pos;
   const GatherPlanDev &g = h->gplan;
-  GatherArgs p{g.ncl, g.maxt, g.maxe, g.maxb, g.nsw, g.tn, g.lconn, g.cn, g.b0, g.deg, g.btask, g.bsrc, g.rsrc,
+  if (c_end < 0) c_end = g.ncl;
+  if (c_end <= c_begin) return NLS_OK;
+  GatherArgs p{c_end, c_begin, g.maxt, g.maxe, g.maxb, g.nsw, g.tn, g.lconn, g.cn, g.b0, g.deg, g.btask, g.bsrc, g.rsrc,
                h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr};
   const size_t shm = gather_smem(g.maxt, g.maxe, g.maxb, g.nsw);
   if (!h->attr_gather) {       // per device: raised once per handle to the opt-in maximum
@@ -489,7 +503,7 @@ int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k) {
   // persistent CTAs: as many per SM as the shared memory admits (3 for <= 4 elements around a node, else 2)
   const int fit = (int)std::min<size_t>((want_r && want_k) ? 2 : 3, ((size_t)h->max_optin_smem + 1024) / (shm + 1024));
   const int per_sm = h->opt_gather_ctas > 0 ? h->opt_gather_ctas : std::max(1, fit);
-  const unsigned grid = (unsigned)std::min<int64_t>(g.ncl, (int64_t)h->sm_count * per_sm);
+  const unsigned grid = (unsigned)std::min<int64_t>(c_end - c_begin, (int64_t)h->sm_count * per_sm);
   if (want_r && want_k) k_asm_q1_2d_gather<true, true><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
   else if (want_r)      k_asm_q1_2d_gather<true, false><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);
   else                  k_asm_q1_2d_gather<false, true><<<grid, G2_THREADS, shm, h->stream>>>(a, p, h->tabq, h->mat);

@@ -396,9 +396,10 @@ int nls_halo_exchange(nls_context *h, double *v) {
   if (!h->distributed || h->nneigh == 0) return NLS_OK;
   if (h->p2p.on) return nls_p2p_halo_exchange(h, v);
   const int dim = h->dim;
+  cudaStream_t st = h->halo_stream ? h->halo_stream : h->stream;
   const int64_t nsend = h->send_ptr[h->nneigh], nrecv = h->recv_ptr[h->nneigh];
   if (nsend > 0) {
-    k_pack<<<(unsigned)((nsend * dim + 255) / 256), 256, 0, h->stream>>>(nsend, dim, h->d_send_nodes, v, h->d_sendbuf);
+    k_pack<<<(unsigned)((nsend * dim + 255) / 256), 256, 0, st>>>(nsend, dim, h->d_send_nodes, v, h->d_sendbuf);
     NLS_KCHECK(h);
   }
   NcclApi *nc = h->nccl;
@@ -407,14 +408,14 @@ int nls_halo_exchange(nls_context *h, double *v) {
     const int64_t s0 = h->send_ptr[q] * dim, s1 = h->send_ptr[q + 1] * dim;
     const int64_t r0 = h->recv_ptr[q] * dim, r1 = h->recv_ptr[q + 1] * dim;
     int e1 = 0, e2 = 0;
-    if (s1 > s0) e1 = nc->Send(h->d_sendbuf + s0, (size_t)(s1 - s0), NCCL_DYN_FLOAT64, h->neigh[q], h->comm, h->stream);
-    if (r1 > r0) e2 = nc->Recv(h->d_recvbuf + r0, (size_t)(r1 - r0), NCCL_DYN_FLOAT64, h->neigh[q], h->comm, h->stream);
+    if (s1 > s0) e1 = nc->Send(h->d_sendbuf + s0, (size_t)(s1 - s0), NCCL_DYN_FLOAT64, h->neigh[q], h->comm, st);
+    if (r1 > r0) e2 = nc->Recv(h->d_recvbuf + r0, (size_t)(r1 - r0), NCCL_DYN_FLOAT64, h->neigh[q], h->comm, st);
     if (e1 || e2) { nc->GroupEnd(); NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclSend/Recv: ") + nc->GetErrorString(e1 ? e1 : e2)); }
   }
   int ge = nc->GroupEnd();
   if (ge != 0) NLS_FAIL(h, NLS_ERR_NCCL, std::string("ncclGroupEnd: ") + nc->GetErrorString(ge));
   if (nrecv > 0) {
-    k_unpack<<<(unsigned)((nrecv * dim + 255) / 256), 256, 0, h->stream>>>(nrecv, dim, h->d_recv_nodes, h->d_recvbuf, v);
+    k_unpack<<<(unsigned)((nrecv * dim + 255) / 256), 256, 0, st>>>(nrecv, dim, h->d_recv_nodes, h->d_recvbuf, v);
     NLS_KCHECK(h);
   }
   return NLS_OK;

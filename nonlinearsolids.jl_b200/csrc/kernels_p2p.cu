@@ -238,7 +238,7 @@ int nls_p2p_halo_exchange(nls_context *h, double *v) {
   for (int q = 0; q < h->nneigh; ++q) { a.dst[q] = p.dst[par][q]; a.dst_flag[q] = p.dst_flag[q]; a.my_flag[q] = p.my_flag[q]; }
   const int64_t ns = h->send_ptr[h->nneigh] * dim, nr = h->recv_ptr[h->nneigh] * dim;
   const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((std::max(ns, nr) + 255) / 256, 64));
-  k_p2p_halo<<<g, 256, 0, h->stream>>>(a, h->d_send_nodes, h->recv_ptr[h->nneigh], h->d_recv_nodes, p.win + (size_t)par * p.H, v,
+  k_p2p_halo<<<g, 256, 0, h->halo_stream ? h->halo_stream : h->stream>>>(a, h->d_send_nodes, h->recv_ptr[h->nneigh], h->d_recv_nodes, p.win + (size_t)par * p.H, v,
                                        epoch, p.d_done, p.d_err);
   P2P_KCHECK(h);
   return NLS_OK;

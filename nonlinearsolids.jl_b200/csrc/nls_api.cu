@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include "nls_internal.h"
@@ -83,6 +84,8 @@ extern "C" int32_t nls_create(int32_t device, nls_handle *out) {
   cudaGetErrorString(e_); delete h; return NLS_ERR_CUDA; } } while (0)
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_halo0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_halo1, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   CK(cudaEventCreate(&h->ev2)); CK(cudaEventCreate(&h->ev3));
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -96,6 +99,7 @@ extern "C" int32_t nls_create(int32_t device, nls_handle *out) {
   CK(cudaMemset(h->d_partial, 0, (3 * RED_BLOCKS_MAX + 2) * sizeof(double)));
 #undef CK
   h->mat.area = 3e-4;  // get(fem.data, :A, 3e-4), defaults.jl:3
+  if (const char *ov = std::getenv("NLS_B200_OVERLAP")) h->opt_overlap_halo = (ov[0] != '0');
   *out = h;
   return NLS_OK;
 }
@@ -123,6 +127,8 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+  cudaEventDestroy(h->ev_halo0); cudaEventDestroy(h->ev_halo1);
+  cudaStreamDestroy(h->comm_stream);
   cudaStreamDestroy(h->stream);
   delete h;
   return NLS_OK;
@@ -410,6 +416,24 @@ static int check_ready(nls_context *h, const char *who) {
 // (::Residual)(fem,U,R,ctx) and/or (::Jacobian)(fem,U,K,ctx) on the device-resident U
 static int assemble(nls_context *h, bool want_r, bool want_k) {
   NLS_TRY(nls_launch_apply_dirichlet(h, h->d_U));              // residual.jl:13 / jacobian.jl:11
+  // multi-GPU, 2-D row-owner kernel: the ghost exchange runs on a second stream while the clusters that touch no
+  // ghost node are assembled; the few clusters at the slab faces follow once it has landed
+  if (h->distributed && h->nneigh > 0 && h->opt_overlap_halo && nls_assembly_mode(h) == NLS_ASM_GATHER &&
+      h->gplan.ncl_interior > 0 && (want_r || want_k) && h->nel > 0) {
+    NLS_CUDA(h, cudaEventRecord(h->ev_halo0, h->stream));
+    NLS_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_halo0, 0));
+    h->halo_stream = h->comm_stream;
+    const int rc = nls_halo_exchange(h, h->d_U);
+    h->halo_stream = nullptr;
+    if (rc) return rc;
+    NLS_CUDA(h, cudaEventRecord(h->ev_halo1, h->comm_stream));
+    NLS_TRY(nls_launch_gather_2d(h, want_r, want_k, 0, h->gplan.ncl_interior));
+    NLS_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo1, 0));
+    NLS_TRY(nls_launch_gather_2d(h, want_r, want_k, h->gplan.ncl_interior, h->gplan.ncl));
+    if (want_r) NLS_TRY(nls_launch_body_force(h, h->d_R));
+    if (want_r) NLS_TRY(nls_launch_neumann(h, h->d_R));
+    return NLS_OK;
+  }
   NLS_TRY(nls_halo_exchange(h, h->d_U));
   if (!nls_assembly_overwrites(h)) {   // the gather kernel writes every row itself
     if (want_r) NLS_CUDA(h, cudaMemsetAsync(h->d_R, 0, sizeof(double) * h->nrows, h->stream));   // residual.jl:14
@@ -863,6 +887,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "twophase_3d")) { h->opt_twophase_3d = value; return NLS_OK; }
   if (!std::strcmp(key, "lap3d")) { h->opt_lap3d = value; return NLS_OK; }
   if (!std::strcmp(key, "pcg_graph")) { h->opt_pcg_graph = value; return NLS_OK; }
+  if (!std::strcmp(key, "overlap_halo")) { h->opt_overlap_halo = value; return NLS_OK; }
   if (!std::strcmp(key, "scratch_mb")) {   // takes effect at the next nls_build_pattern
     h->opt_scratch_mb = value;
     if (h->have_pattern) { NLS_TRY(nls_twophase_build(h)); }

@@ -59,7 +59,7 @@ void nls_gather_tile(int *tile3);
 
 // packed, fixed-stride device copy of the plan (kernels_gather.cu)
 struct GatherPlanDev {
-  int64_t ncl = 0;
+  int64_t ncl = 0, ncl_interior = 0;      // clusters [0, ncl_interior) touch no ghost node
   int maxt = 0, maxe = 0, maxb = 0, nsw = 0;
   int32_t *tn = nullptr;
   uint32_t *lconn = nullptr;
@@ -127,6 +127,10 @@ struct P2PState {
 struct nls_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;   // second stream: halo exchange overlapped with the interior clusters of the 2-D assembly
+  cudaStream_t halo_stream = nullptr;   // when set, nls_halo_exchange enqueues there instead of `stream`
+  cudaEvent_t ev_halo0 = nullptr, ev_halo1 = nullptr;
+  int opt_overlap_halo = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -263,7 +267,7 @@ int nls_launch_twophase(nls_context *h, bool want_r, bool want_k);
 int nls_gather_nc(void);
 int nls_gather_build(nls_context *h, const AsmPlan &plan);
 void nls_gather_free(nls_context *h);
-int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k);
+int nls_launch_gather_2d(nls_context *h, bool want_r, bool want_k, int64_t c_begin = 0, int64_t c_end = -1);
 int nls_launch_apply_dirichlet(nls_context *h, double *U);
 int nls_launch_neumann(nls_context *h, double *R);
 int nls_launch_body_force(nls_context *h, double *R);
