@@ -4,19 +4,23 @@
 // (compute_dinternalforce, src/materials/defaults.jl:77-81 + assemble!, src/fem/element.jl:70) --
 // so results are bit-reproducible run to run.
 //
-// Persistent CTAs walk node clusters (host plan: 16x8-node Morton tiles, nls_host_cluster_plan).
-// Everything a cluster needs is staged into shared memory with cp.async (LDGSTS) while the
-// previous cluster is being computed, so no global-load latency sits on the critical path:
-//   group A(k+2): the list of nodes touched by cluster k+2           (contiguous copy)
-//   group B(k+1): coordinates + displacements of those nodes (16-byte gathers through the list),
-//                 local connectivity, row owners, CSR row bases, per-block source lists
-//   compute(k)  : phase 1  one thread per element: the symmetric half of K_e and f_e over the 4
-//                          quadrature points (rolled loop, 48 accumulators) -> shared memory
-//                 phase 2  one task per CSR block of the cluster's rows: sums the element blocks
-//                          that land in it (ascending element order, branch-free padded list)
-//                          and writes its two 16-byte row segments; adjacent tasks write adjacent
-//                          segments, so the stores coalesce. The diagonal block's task also sums R.
-// History and counters behind this design: DESIGN.md section 5, profiles/r1a..r1h.
+// Persistent CTAs walk node clusters (host plan: tiles of 15 x 7 nodes, nls_host_cluster_plan: their 16 x 8 = 128
+// touching elements are exactly one per thread, one warp per SM sub-partition). Everything a cluster needs is
+// staged into shared memory with cp.async (LDGSTS), so no global-load latency sits on the critical path:
+//   group A (k+2): header + list of nodes touched by cluster k+2           (contiguous copy, two clusters ahead)
+//   group B1(k+1): coordinates + displacements of those nodes (16-byte gathers through the list) and the local
+//                  connectivity: the phase-1 inputs, double buffered, one cluster ahead
+//   group B2(k)  : row owners, 32-bit row bases relative to the cluster, per-block tasks and source lists: the
+//                  phase-2 lists, single buffered, fetched while phase 1 of the same cluster runs
+//   compute(k)   : phase 1  one thread per element: the symmetric half of K_e over the 4 quadrature points (rolled
+//                           loop, 40 register accumulators; f_e accumulated in the element's record) -> smem
+//                  phase 2  one task per CSR block of the cluster's rows: sums the element blocks that land in it
+//                           (ascending element order, branch-free padded list) and writes its two 16-byte row
+//                           segments; adjacent tasks write adjacent segments, so the stores coalesce.
+//                           One task per node sums R.
+// Clusters that touch a ghost node (multi-GPU) are listed last: they are launched separately, after the ghost
+// exchange that runs on a second stream beside the interior clusters has landed (nls_api.cu: assemble()).
+// History and counters behind this design: DESIGN.md section 5, profiles/r1a..r1k.
 #include <algorithm>
 #include <cstring>
 #include "asm_common.cuh"
