@@ -430,6 +430,111 @@ int nls_allreduce_sum(nls_context *h, double *dptr, int count) {
 }
 
 // ------------------------------------------------------------------------------------
+// Whole Jacobi-PCG solve in ONE thread block, for small systems (the reference's own problem sizes: a few hundred
+// DoFs). The multi-kernel loop below costs three dependent launches per iteration (~14 us even graph-replayed);
+// here an iteration is one pass over the block's rows and three block-wide reductions. Same arithmetic, masks
+// and convergence tests as k_pcg_init / k_spmv<DOT> / k_pcg_update / k_pcg_pupdate; only the summation order of the
+// reductions differs. Rows i = tid, tid + 1024, ... (at most PCG_SMALL_RPT per thread; A p stays in registers).
+// ------------------------------------------------------------------------------------
+#define PCG_SMALL_THREADS 1024
+#define PCG_SMALL_RPT 8
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double (*sh)[32]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = warp_sum(v[i]);
+    if (lane == 0) sh[i][wid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = lane < (int)(blockDim.x >> 5) ? sh[i][lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) sh[i][0] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = sh[i][0];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PCG_SMALL_THREADS)
+k_pcg_small(int nrows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, const int32_t *__restrict__ diag,
+            const double *__restrict__ vals, const double *__restrict__ b, const uint8_t *__restrict__ con,
+            double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r, double *p, PcgCtl *ctl,
+            double tol2, int maxits) {
+  __shared__ double sh[2][32];
+  const int tid = threadIdx.x, nthr = blockDim.x;   // nthr: a multiple of 32, nthr * PCG_SMALL_RPT >= nrows
+  double v[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < PCG_SMALL_RPT; ++k) {
+    const int i = tid + k * nthr;
+    if (i < nrows) {
+      const double di = con[i] ? 0.0 : 1.0 / vals[rowptr[i] + diag[i]];
+      const double ri = con[i] ? 0.0 : b[i];
+      const double zi = di * ri;
+      dinv[i] = di; x[i] = 0.0; r[i] = ri; p[i] = zi;
+      v[0] += ri * zi; v[1] += ri * ri;
+    }
+  }
+  block_sum<2>(v, sh);
+  double rz = v[0], rr = v[1];
+  const double bb = v[1];
+  int it = 0, done = (bb == 0.0) ? 1 : 0;
+  while (!done && it < maxits) {
+    double Ap[PCG_SMALL_RPT];
+    double d1[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < PCG_SMALL_RPT; ++k) {
+      const int i = tid + k * nthr;
+      Ap[k] = 0.0;
+      if (i < nrows) {
+        double s = 0.0;
+        for (int64_t q = rowptr[i], e = rowptr[i + 1]; q < e; ++q) s += vals[q] * p[colind[q]];
+        if (con[i]) s = 0.0;
+        Ap[k] = s;
+        d1[0] += p[i] * s;
+      }
+    }
+    block_sum<1>(d1, sh);
+    const double pAp = d1[0];
+    if (!(pAp > 0.0)) { done = 3; break; }
+    const double alpha = rz / pAp;
+    v[0] = 0.0; v[1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < PCG_SMALL_RPT; ++k) {
+      const int i = tid + k * nthr;
+      if (i < nrows) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap[k];
+        r[i] = ri;
+        v[0] += ri * (dinv[i] * ri); v[1] += ri * ri;
+      }
+    }
+    block_sum<2>(v, sh);              // also the barrier after which every thread is done reading p
+    ++it;
+    rr = v[1];
+    if (!(rr == rr)) { done = 3; break; }
+    if (rr <= tol2 * bb) { done = 1; break; }
+    const double beta = v[0] / rz;
+    rz = v[0];
+#pragma unroll
+    for (int k = 0; k < PCG_SMALL_RPT; ++k) {
+      const int i = tid + k * nthr;
+      if (i < nrows) p[i] = dinv[i] * r[i] + beta * p[i];
+    }
+    __syncthreads();                  // the new p is complete before the next matrix-vector product reads it
+  }
+  if (tid == 0) {
+    ctl->iters = it; ctl->done = done; ctl->rr = rr; ctl->bb = bb; ctl->rz = rz; ctl->tol2 = tol2; ctl->maxits = maxits;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Jacobi-PCG driver on the handle's current CSR values. rhs = h->d_b (masked inside),
 // solution -> h->d_dU (zero on constrained DoFs = expand(), fem.jl:98-102).
 //   fixed_iters > 0: run exactly that many iterations without convergence checks (bench).
@@ -439,6 +544,20 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
   int rc;
   const int64_t n = h->nrows;
   RedScratch rs = red_of(h);
+  if (!h->distributed && h->opt_pcg_small && fixed_iters == 0 && n > 0 && n <= (int64_t)PCG_SMALL_THREADS * PCG_SMALL_RPT &&
+      h->nnz <= (int64_t)1 << 21) {
+    const int nthr = (int)std::min<int64_t>(PCG_SMALL_THREADS, std::max<int64_t>(64, ((n + PCG_SMALL_RPT - 1) / PCG_SMALL_RPT + 31) / 32 * 32 * 2));
+    k_pcg_small<<<1, std::min(nthr, PCG_SMALL_THREADS), 0, h->stream>>>((int)n, h->d_rowptr, h->d_colind, h->d_diag, h->d_vals, h->d_b, h->d_con,
+                                                       h->d_dinv, h->d_dU, h->d_r, h->d_p, h->d_ctl, rtol * rtol, maxits);
+    NLS_KCHECK(h);
+    NLS_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    const PcgCtl &c = *h->h_ctl;
+    if (its) *its = c.iters;
+    if (relres) *relres = c.bb > 0.0 ? sqrt(c.rr / c.bb) : 0.0;
+    if (status) *status = (c.done == 1) ? 0 : (c.done == 3 ? 2 : 1);
+    return NLS_OK;
+  }
   if ((rc = nls_launch_extract_dinv(h))) return rc;
   k_pcg_init<<<vec_grid(h, n), 256, 0, h->stream>>>(n, h->d_b, h->d_con, h->d_dinv, h->d_dU, h->d_r, h->d_p, h->d_ctl, rs);
   NLS_KCHECK(h);

@@ -887,6 +887,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "twophase_3d")) { h->opt_twophase_3d = value; return NLS_OK; }
   if (!std::strcmp(key, "lap3d")) { h->opt_lap3d = value; return NLS_OK; }
   if (!std::strcmp(key, "pcg_graph")) { h->opt_pcg_graph = value; return NLS_OK; }
+  if (!std::strcmp(key, "pcg_small")) { h->opt_pcg_small = value; return NLS_OK; }
   if (!std::strcmp(key, "overlap_halo")) { h->opt_overlap_halo = value; return NLS_OK; }
   if (!std::strcmp(key, "scratch_mb")) {   // takes effect at the next nls_build_pattern
     h->opt_scratch_mb = value;

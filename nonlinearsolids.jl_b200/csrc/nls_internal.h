@@ -196,6 +196,7 @@ struct nls_context {
   double *d_tmp = nullptr;
   PcgGraph pcg_graph;
   int opt_pcg_graph = 1;
+  int opt_pcg_small = 1;   // systems of <= 8192 rows: the whole PCG solve in one thread block
   double *d_mr[7] = {nullptr};          // MINRES work vectors (allocated on first use)
   double *d_partial = nullptr;          // block partial sums
   PcgCtl *d_ctl = nullptr;
