@@ -223,7 +223,10 @@ int32_t nls_partition(int32_t nen, int64_t nelem, const int32_t *conn0, int32_t 
                       int64_t *n_loc_elems, int64_t *loc_elems, int64_t *n_ghost, int64_t *ghost_nodes,
                       int64_t *send_ptr /*nranks+1*/, int64_t *send_nodes);
 /* Local numbering: owned nodes [0, n_owned) then ghosts. Rows/R exist for owned nodes only.
- * Lists are local node ids grouped by neighbour rank (ptr arrays have nneigh+1 entries). */
+ * Lists are local node ids grouped by neighbour rank (ptr arrays have nneigh+1 entries); the k-th node a rank
+ * sends to a neighbour is the k-th node that neighbour receives from it. After nls_comm_init this call is
+ * COLLECTIVE over the communicator (every rank sets its halo): it exchanges CUDA IPC handles of the peer-memory
+ * windows (see nls_comm_path). */
 int32_t nls_set_halo(nls_handle h, int64_t n_owned_nodes, int32_t nneigh, const int32_t *neigh_ranks,
                      const int64_t *send_ptr, const int32_t *send_nodes,
                      const int64_t *recv_ptr, const int32_t *recv_nodes);
