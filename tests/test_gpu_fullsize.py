@@ -122,7 +122,7 @@ rank, world, lr = nls.distributed.env_rank()
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-for dim, shape, comp in [(2, (9, 14), -0.02), (3, (5, 4, 9), -0.05)]:
+for dim, shape, comp in [(2, (9, 14), -0.02), (3, (5, 4, 9), -0.05), (2, (40, 46), -0.004)]:   # last: interior + boundary clusters (overlapped halo)
     uid = nls.distributed.broadcast_unique_id(dist, rank, device="cuda")   # one NCCL id per communicator
     mat = nls.NeoHookean(E=1.0, nu=0.3)
     fem, part = nls.distributed.slab_model(nls.FEMModel, shape, dim, world, rank, lr, uid)
@@ -168,7 +168,8 @@ print("rank", rank, "ok")
 
 
 def test_two_rank_nccl_parity(tmp_path):
-    """2 ranks / 2 GPUs: slab partition, NCCL halo exchange + Krylov allreduces; owned rows of R and
+    """2 ranks / 2 GPUs: slab partition, halo exchange + Krylov reductions (peer-memory windows, or NCCL with
+    NLS_B200_P2P=0), the 2-D assembly with the exchange overlapped with its interior clusters; owned rows of R and
     the CSR Jacobian and the Newton solution equal the single-domain oracle."""
     import torch
     if torch.cuda.device_count() < 2:
