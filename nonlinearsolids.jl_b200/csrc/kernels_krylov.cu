@@ -227,7 +227,21 @@ k_pcg_update(int64_t nrows, const double *__restrict__ p, const double *__restri
   }
   const double alpha = ctl->rz / pAp;
   double v[2] = {0.0, 0.0};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x) {
+  // two rows per thread and load (16-byte accesses); the odd last row, if any, goes to one thread
+  const int64_t n2 = nrows >> 1;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *Ap2 = reinterpret_cast<const double2 *>(Ap), *d2 = reinterpret_cast<const double2 *>(dinv);
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 pp = p2[i], ap = Ap2[i], dd = d2[i];
+    double2 xx = x2[i], rr = r2[i];
+    xx.x += alpha * pp.x; xx.y += alpha * pp.y;
+    rr.x -= alpha * ap.x; rr.y -= alpha * ap.y;
+    x2[i] = xx; r2[i] = rr;
+    v[0] += rr.x * (dd.x * rr.x); v[1] += rr.x * rr.x;
+    v[0] += rr.y * (dd.y * rr.y); v[1] += rr.y * rr.y;
+  }
+  if ((nrows & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = nrows - 1;
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * Ap[i];
     r[i] = ri;
@@ -248,8 +262,16 @@ k_pcg_pupdate(int64_t nrows, const double *__restrict__ r, const double *__restr
     return;
   }
   const double beta = ctl->red[1] / ctl->rz;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = dinv[i] * r[i] + beta * p[i];
+  const int64_t n2 = nrows >> 1;
+  const double2 *r2 = reinterpret_cast<const double2 *>(r), *d2 = reinterpret_cast<const double2 *>(dinv);
+  double2 *p2 = reinterpret_cast<double2 *>(p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 rr = r2[i], dd = d2[i];
+    double2 pp = p2[i];
+    pp.x = dd.x * rr.x + beta * pp.x; pp.y = dd.y * rr.y + beta * pp.y;
+    p2[i] = pp;
+  }
+  if ((nrows & 1) && blockIdx.x == 0 && threadIdx.x == 0) { const int64_t i = nrows - 1; p[i] = dinv[i] * r[i] + beta * p[i]; }
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl->rr = rr;
 }
 
