@@ -157,6 +157,7 @@ int nls_launch_scale_add_mass(nls_context *h, double scale, bool scale_existing)
   k_scale_add_mass<<<(unsigned)((h->n_owned + 7) / 8), 256, 0, h->stream>>>(h->n_owned, h->dim, h->d_browptr, h->d_mass, scale,
                                                                              scale_existing ? 1 : 0, h->d_vals);
   DYN_KCHECK(h);
+  h->vals_version++;
   return NLS_OK;
 }
 

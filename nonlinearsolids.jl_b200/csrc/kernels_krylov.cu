@@ -186,6 +186,126 @@ k_bspmv(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__r
   if (DOT) grid_reduce<1>(dot, rs.partial, rs.counter, &ctl->red[0]);
 }
 
+// ------------------------------------------------------------------------------------
+// Symmetric SpMV for the Krylov solvers (PCG / MINRES assume K = K^T): only the upper blocks of every block row
+// (column node >= row node, local numbering) are kept, packed contiguously per row as dim x dim row-major blocks.
+// Row a multiplies its own upper blocks; for its lower neighbours b < a it reads block (b, a) from row b's packed
+// list through a precomputed slot and applies it transposed. Each stored block is fetched from HBM once by its
+// own row and a second time, shortly afterwards, out of L2 by the mirrored row (the window between the two is one
+// node plane of upper blocks: 23 MB at C3), so the DRAM traffic per product is halved: 8 -> ~4.4 B per nonzero.
+// No atomics: every row is still produced by one thread group, in a fixed order.
+// MEASURED SLOWER than the full block-aware product (C3 PCG iteration 1816 vs 1386 us, C2 71 vs 67.5 us): the
+// mirrored 72-byte blocks come out of L2 as scattered sector requests behind a dependent slot lookup, which costs
+// more than streaming twice the bytes from HBM at 90 % of peak. Kept behind nls_set_option("sym_spmv", 1), off by
+// default.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_sym_pack(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__restrict__ dpos,
+           const int64_t *__restrict__ symptr, const double *__restrict__ vals, double *__restrict__ sv) {
+  // one warp per node: the packed blocks of a row are contiguous, so the stores coalesce
+  const int64_t node = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (node >= n_owned) return;
+  const int64_t b0 = browptr[node];
+  const int deg = (int)(browptr[node + 1] - b0), dp = dpos[node], nup = deg - dp;
+  const double *v0 = vals + (int64_t)DIM * DIM * b0;
+  double *o = sv + (int64_t)DIM * DIM * symptr[node];
+  for (int t = threadIdx.x & 31; t < nup * DIM * DIM; t += 32) {
+    const int j = t / (DIM * DIM), ik = t - j * DIM * DIM, i = ik / DIM, k = ik - i * DIM;
+    o[t] = v0[(int64_t)i * DIM * deg + DIM * (dp + j) + k];
+  }
+}
+
+// slot of block (a, b), a < b, in the packed storage, seen from row b (its lower entry jb): one thread per block
+__global__ void __launch_bounds__(256)
+k_sym_index(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__restrict__ bcol, const int32_t *__restrict__ dpos,
+            const int64_t *__restrict__ symptr, uint32_t *__restrict__ lowslot) {
+  const int64_t node = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (node >= n_owned) return;
+  const int64_t b0 = browptr[node];
+  const int dp = dpos[node];
+  const int64_t lp = b0 - symptr[node];
+  for (int jb = threadIdx.x & 31; jb < dp; jb += 32) {
+    const int a = bcol[b0 + jb];
+    int64_t lo = browptr[a], hi = browptr[a + 1] - 1;
+    const int64_t a0 = lo;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (bcol[mid] < (int32_t)node) lo = mid + 1; else hi = mid; }
+    lowslot[lp + jb] = (uint32_t)(symptr[a] + (lo - a0) - dpos[a]);
+  }
+}
+
+// T lanes per node; a lane takes whole blocks: first the lower neighbours (block read at its slot, applied
+// transposed), then the node's own packed upper blocks (contiguous).
+template <int DIM, int T, bool DOT>
+__global__ void __launch_bounds__(256)
+k_symspmv(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__restrict__ bcol, const int32_t *__restrict__ dpos,
+          const int64_t *__restrict__ symptr, const uint32_t *__restrict__ lowslot, const double *__restrict__ sv,
+          const double *__restrict__ x, double *__restrict__ y, const uint8_t *__restrict__ con, PcgCtl *ctl, RedScratch rs) {
+  if (DOT) {
+    if (ctl->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->rz = ctl->red[1];
+  }
+  constexpr int D2 = DIM * DIM;
+  const int lane = threadIdx.x % T;
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x / T;
+  double dot[1] = {0.0};
+  for (int64_t base = 0; base < n_owned; base += stride) {
+    const int64_t node = base + gid;
+    const bool valid = node < n_owned;
+    double acc[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) acc[i] = 0.0;
+    if (valid) {
+      const int64_t b0 = browptr[node], sp = symptr[node];
+      const int deg = (int)(browptr[node + 1] - b0), dp = dpos[node];
+      const uint32_t *ls = lowslot + (b0 - sp);
+      for (int j = lane; j < dp; j += T) {                 // lower neighbours: K_(c,node)^T x_c
+        const int c = bcol[b0 + j];
+        const double *kp = sv + (int64_t)D2 * (int64_t)ls[j];
+        double xv[DIM], K[D2];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) xv[k] = x[(int64_t)DIM * c + k];
+#pragma unroll
+        for (int t = 0; t < D2; ++t) K[t] = kp[t];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) acc[i] = fma(K[k * DIM + i], xv[k], acc[i]);
+      }
+      const double *up = sv + (int64_t)D2 * sp;
+      for (int j = lane; j < deg - dp; j += T) {           // own upper blocks
+        const int c = bcol[b0 + dp + j];
+        const double *kp = up + D2 * j;
+        double xv[DIM], K[D2];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) xv[k] = x[(int64_t)DIM * c + k];
+#pragma unroll
+        for (int t = 0; t < D2; ++t) K[t] = kp[t];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) acc[i] = fma(K[i * DIM + k], xv[k], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (valid && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) {
+        const int64_t row = DIM * node + i;
+        double s = acc[i];
+        if (con && con[row]) s = 0.0;
+        y[row] = s;
+        if (DOT) dot[0] += x[row] * s;
+      }
+    }
+  }
+  if (DOT) grid_reduce<1>(dot, rs.partial, rs.counter, &ctl->red[0]);
+}
+
 // diagonal -> Jacobi preconditioner; constrained rows get 0 (their residual is 0 anyway)
 __global__ void k_extract_dinv(int64_t nrows, const int64_t *rowptr, const int32_t *diag, const double *vals,
                                const uint8_t *con, double *dinv) {
@@ -355,9 +475,79 @@ static int bspmv_t(nls_context *h, const double *x, double *y, const uint8_t *co
   return NLS_OK;
 }
 
+template <int DIM>
+static int symspmv_t(nls_context *h, const double *x, double *y, const uint8_t *con, bool dot) {
+  constexpr int T = 4;
+  int64_t g = (h->n_owned * T + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g > RED_BLOCKS_MAX) g = RED_BLOCKS_MAX;
+  if (g < 1) g = 1;
+  if (dot) k_symspmv<DIM, T, true><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, h->d_dpos, h->d_symptr, h->d_lowslot, h->d_symvals, x, y, con, h->d_ctl, red_of(h));
+  else     k_symspmv<DIM, T, false><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, h->d_dpos, h->d_symptr, h->d_lowslot, h->d_symvals, x, y, con, h->d_ctl, red_of(h));
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
+// Packs the upper blocks of the current CSR values for the symmetric product (once per set of values). Returns with
+// h->sym_active = false when the option is off or the storage does not fit; the solvers then use the full product.
+int nls_sym_prepare(nls_context *h) {
+  h->sym_active = false;
+  if (!h->opt_sym_spmv || h->dim < 2 || !h->have_sym_index || h->n_owned == 0) return NLS_OK;
+  if (!h->d_symvals) {
+    if (cudaMalloc((void **)&h->d_symvals, sizeof(double) * (size_t)std::max<int64_t>(1, h->nsym) * h->dim * h->dim) != cudaSuccess) {
+      cudaGetLastError(); h->d_symvals = nullptr; h->opt_sym_spmv = 0; return NLS_OK;
+    }
+    h->sym_version = -1;
+  }
+  if (h->sym_version != h->vals_version) {
+    const unsigned g = (unsigned)((h->n_owned + 7) / 8);
+    if (h->dim == 2) k_sym_pack<2><<<g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_dpos, h->d_symptr, h->d_vals, h->d_symvals);
+    else             k_sym_pack<3><<<g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_dpos, h->d_symptr, h->d_vals, h->d_symvals);
+    NLS_KCHECK(h);
+    h->sym_version = h->vals_version;
+  }
+  h->sym_active = true;
+  return NLS_OK;
+}
+
+int nls_sym_build_index(nls_context *h) {
+  // host: position of the diagonal block in every block row, prefix sums of the upper counts
+  h->have_sym_index = false;
+  if (h->dim < 2 || h->n_owned == 0) return NLS_OK;
+  const int64_t no = h->n_owned;
+  std::vector<int32_t> dpos((size_t)no);
+  std::vector<int64_t> symptr((size_t)no + 1, 0);
+  for (int64_t a = 0; a < no; ++a) {
+    const int32_t *lo = h->h_bcol.data() + h->h_browptr[a], *hi = h->h_bcol.data() + h->h_browptr[a + 1];
+    const int32_t *d = std::lower_bound(lo, hi, (int32_t)a);
+    dpos[a] = (int32_t)(d - lo);
+    symptr[a + 1] = symptr[a] + (hi - d);
+  }
+  h->nsym = symptr[no];
+  const int64_t nlow = h->nnzb - h->nsym;
+  if (h->nsym >= ((int64_t)1 << 32)) return NLS_OK;
+  if (h->d_dpos) cudaFree(h->d_dpos);
+  if (h->d_symptr) cudaFree(h->d_symptr);
+  if (h->d_lowslot) cudaFree(h->d_lowslot);
+  if (h->d_symvals) { cudaFree(h->d_symvals); h->d_symvals = nullptr; }
+  h->d_dpos = nullptr; h->d_symptr = nullptr; h->d_lowslot = nullptr;
+  NLS_CUDA(h, cudaMalloc((void **)&h->d_dpos, sizeof(int32_t) * no));
+  NLS_CUDA(h, cudaMalloc((void **)&h->d_symptr, sizeof(int64_t) * (no + 1)));
+  NLS_CUDA(h, cudaMalloc((void **)&h->d_lowslot, sizeof(uint32_t) * (size_t)std::max<int64_t>(1, nlow)));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_dpos, dpos.data(), sizeof(int32_t) * no, cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_symptr, symptr.data(), sizeof(int64_t) * (no + 1), cudaMemcpyHostToDevice, h->stream));
+  k_sym_index<<<(unsigned)((no + 7) / 8), 256, 0, h->stream>>>(no, h->d_browptr, h->d_bcol, h->d_dpos, h->d_symptr, h->d_lowslot);
+  NLS_KCHECK(h);
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_sym_index = true;
+  return NLS_OK;
+}
+
 int nls_launch_spmv(nls_context *h, const double *x, double *y, bool masked, bool with_dot) {
   if (h->nrows == 0) return NLS_OK;
   const uint8_t *con = masked ? h->d_con : nullptr;
+  if (h->sym_active && h->dim >= 2) return h->dim == 2 ? symspmv_t<2>(h, x, y, con, with_dot) : symspmv_t<3>(h, x, y, con, with_dot);
   if (h->opt_spmv == 1 && h->dim >= 2) {   // block-aware traversal of the same CSR values
     const int t = h->opt_spmv_lanes;
     if (h->dim == 2) {
@@ -581,6 +771,8 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
     return NLS_OK;
   }
   if ((rc = nls_launch_extract_dinv(h))) return rc;
+  if ((rc = nls_sym_prepare(h))) return rc;       // the solver's products read the packed upper blocks (K = K^T)
+  struct SymScope { nls_context *h; ~SymScope() { h->sym_active = false; } } sym_scope{h};
   k_pcg_init<<<vec_grid(h, n), 256, 0, h->stream>>>(n, h->d_b, h->d_con, h->d_dinv, h->d_dU, h->d_r, h->d_p, h->d_ctl, rs);
   NLS_KCHECK(h);
   if ((rc = nls_allreduce_sum(h, &h->d_ctl->red[1], 2))) return rc;
@@ -614,7 +806,7 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
     if (use_graph && todo == chunk) {
       PcgGraph &G = h->pcg_graph;
       const bool same = G.exec && G.vals == h->d_vals && G.con == h->d_con && G.n == n && G.nnz == h->nnz &&
-                        G.spmv == h->opt_spmv && G.lanes == h->opt_spmv_lanes;
+                        G.spmv == h->opt_spmv + (h->sym_active ? 16 : 0) && G.lanes == h->opt_spmv_lanes;
       if (!same) {
         if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -628,7 +820,7 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
         ce = cudaGraphInstantiate(&G.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { G.exec = nullptr; h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return NLS_ERR_CUDA; }
-        G.vals = h->d_vals; G.con = h->d_con; G.n = n; G.nnz = h->nnz; G.spmv = h->opt_spmv; G.lanes = h->opt_spmv_lanes;
+        G.vals = h->d_vals; G.con = h->d_con; G.n = n; G.nnz = h->nnz; G.spmv = h->opt_spmv + (h->sym_active ? 16 : 0); G.lanes = h->opt_spmv_lanes;
       }
       NLS_CUDA(h, cudaGraphLaunch(G.exec, h->stream));
       h->launches += 3 * chunk;
@@ -682,6 +874,8 @@ int nls_minres_solve(nls_context *h, double rtol, int maxits, int *its, double *
   double *x = h->d_dU;
   const unsigned g = vec_grid(h, n);
   if ((rc = nls_launch_extract_dinv(h))) return rc;
+  if ((rc = nls_sym_prepare(h))) return rc;
+  struct SymScope { nls_context *h; ~SymScope() { h->sym_active = false; } } sym_scope{h};
   NLS_CUDA(h, cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
   NLS_CUDA(h, cudaMemsetAsync(w, 0, sizeof(double) * n, h->stream));
   NLS_CUDA(h, cudaMemsetAsync(w2, 0, sizeof(double) * n, h->stream));

@@ -48,6 +48,8 @@ static void free_pattern(nls_context *h) {
   nls_gather_free(h);
   nls_twophase_free(h);
   dev_free(&h->d_mass); h->have_mass = false;
+  dev_free(&h->d_dpos); dev_free(&h->d_symptr); dev_free(&h->d_lowslot); dev_free(&h->d_symvals);
+  h->have_sym_index = false; h->sym_active = false; h->nsym = 0;
   if (h->pcg_graph.exec) { cudaGraphExecDestroy(h->pcg_graph.exec); h->pcg_graph = PcgGraph(); }
   h->h_browptr.clear(); h->h_bcol.clear();
   h->have_pattern = false; h->nrows = h->nnz = h->nnzb = 0;
@@ -368,6 +370,8 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
   NLS_CUDA(h, cudaMemsetAsync(h->d_diag, 0, sizeof(int32_t) * h->nrows, h->stream));
   NLS_TRY(nls_launch_expand_pattern(h));
   NLS_TRY(nls_launch_build_pos(h));
+  NLS_TRY(nls_sym_build_index(h));
+  h->vals_version++;
   // plan of the gather (row-owner) assembly: 2-D only for now; falls back to the atomic scatter
   // when a cluster would not fit in shared memory
   if (h->dim == 2 && h->n_owned > 0 && h->nel > 0) {
@@ -430,6 +434,7 @@ static int assemble(nls_context *h, bool want_r, bool want_k) {
     NLS_TRY(nls_launch_gather_2d(h, want_r, want_k, 0, h->gplan.ncl_interior));
     NLS_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo1, 0));
     NLS_TRY(nls_launch_gather_2d(h, want_r, want_k, h->gplan.ncl_interior, h->gplan.ncl));
+    if (want_k) h->vals_version++;
     if (want_r) NLS_TRY(nls_launch_body_force(h, h->d_R));
     if (want_r) NLS_TRY(nls_launch_neumann(h, h->d_R));
     return NLS_OK;
@@ -440,6 +445,7 @@ static int assemble(nls_context *h, bool want_r, bool want_k) {
     if (want_k) NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));  // jacobian.jl:13
   }
   NLS_TRY(nls_launch_assembly(h, want_r, want_k));
+  if (want_k) h->vals_version++;
   if (want_r) NLS_TRY(nls_launch_body_force(h, h->d_R));       // residual.jl:19-23 (DistributedForce)
   if (want_r) NLS_TRY(nls_launch_neumann(h, h->d_R));          // residual.jl:24-25
   return NLS_OK;
@@ -492,6 +498,7 @@ extern "C" int32_t nls_set_values(nls_handle h, const double *vals) {
   if (!vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_values: null vals");
   NLS_CUDA(h, cudaMemcpyAsync(h->d_vals, vals, sizeof(double) * h->nnz, cudaMemcpyHostToDevice, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->vals_version++;
   return NLS_OK;
 }
 
@@ -888,6 +895,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "lap3d")) { h->opt_lap3d = value; return NLS_OK; }
   if (!std::strcmp(key, "pcg_graph")) { h->opt_pcg_graph = value; return NLS_OK; }
   if (!std::strcmp(key, "pcg_small")) { h->opt_pcg_small = value; return NLS_OK; }
+  if (!std::strcmp(key, "sym_spmv")) { h->opt_sym_spmv = value; return NLS_OK; }
   if (!std::strcmp(key, "overlap_halo")) { h->opt_overlap_halo = value; return NLS_OK; }
   if (!std::strcmp(key, "scratch_mb")) {   // takes effect at the next nls_build_pattern
     h->opt_scratch_mb = value;

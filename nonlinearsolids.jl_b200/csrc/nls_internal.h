@@ -184,6 +184,16 @@ struct nls_context {
   bool lap_valid = false;
   int opt_lap3d = 1;      // 1: use it when the 320 B/element fit in HBM
 
+  // symmetric product of the Krylov solvers: packed upper blocks + index (kernels_krylov.cu)
+  int32_t *d_dpos = nullptr;
+  int64_t *d_symptr = nullptr;
+  uint32_t *d_lowslot = nullptr;
+  double *d_symvals = nullptr;
+  int64_t nsym = 0;
+  bool have_sym_index = false, sym_active = false;
+  int64_t vals_version = 0, sym_version = -1;   // bumped whenever the CSR values change
+  int opt_sym_spmv = 0;   // experimental (nls_set_option "sym_spmv"): measured slower than the full product, see DESIGN.md 4
+
   // gather-assembly plan (device copy)
   bool have_plan = false;
   GatherPlanDev gplan;
@@ -278,6 +288,8 @@ int nls_launch_commit_state(nls_context *h, const double *dU);
 
 int nls_launch_spmv(nls_context *h, const double *x, double *y, bool masked, bool with_dot);
 int nls_launch_extract_dinv(nls_context *h);
+int nls_sym_build_index(nls_context *h);
+int nls_sym_prepare(nls_context *h);
 double nls_dev_masked_norm2(nls_context *h, const double *v, bool masked, int *rc);  // sqrt(sum v_i^2) over owned (free) DoFs
 int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, double *out);
 int nls_launch_axpy(nls_context *h, int64_t n, double a, const double *x, double *y);

@@ -228,6 +228,32 @@ def test_krylov_hooks(nls, orc):
     assert st.value == 1 and its.value == 3
 
 
+def test_symmetric_product_option(nls, orc):
+    """The experimental upper-blocks-only SpMV of the Krylov solvers (option sym_spmv, off by default) gives the same
+    PCG and MINRES solutions as the full product."""
+    for dim, n in ((2, 12), (3, 7)):
+        mat = nls.NeoHookean(E=1.0, nu=0.3)
+        fem, om = grid_problem(nls, orc, n, dim, mat, compress=-0.01)
+        vals = om.jacobian_csr(nls.smooth_field(fem.mesh.coords, amp=0.002))
+        H = fem.handle(mat)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        H.call("nls_set_option", b"pcg_small", 0)
+        b = np.random.default_rng(11).standard_normal(fem.ndof)
+        sols = {}
+        for sym in (0, 1):
+            H.call("nls_set_option", b"sym_spmv", sym)
+            H.call("nls_set_values", dp(vals))
+            for name in ("nls_linear_solve", "nls_linear_solve_indefinite"):
+                x = np.zeros(fem.ndof)
+                its, st, rr = C.c_int32(0), C.c_int32(0), C.c_double(0)
+                H.call(name, 1e-12, 20000, dp(b), dp(x), C.byref(its), C.byref(rr), C.byref(st))
+                assert st.value == 0
+                sols[(sym, name)] = (x, its.value)
+        for name in ("nls_linear_solve", "nls_linear_solve_indefinite"):
+            assert rel_err(sols[(1, name)][0], sols[(0, name)][0]) <= 1e-9
+            assert abs(sols[(1, name)][1] - sols[(0, name)][1]) <= 3
+
+
 def test_errors_are_loud(nls):
     H = nls.Handle(0)
     with pytest.raises(nls.NLSError):
