@@ -1,27 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native Newton hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong] [--config C3|C2]
 
-Metric (BASELINE.json): assembled DoF/s of one fused residual+Jacobian evaluation, plus the
-Newton-step time, on the C2 workload (2-D plane-strain Neo-Hookean, structured Q1 mesh,
-708 nodes per side = 1 002 528 DoF per GPU; weak scaling stacks one such slab per rank along y).
+Metric (BASELINE.json): assembled DoF/s of one fused residual+Jacobian evaluation, plus the Newton-step time, on the
+north-star workload C3: 3-D Q1 hexahedral compressible Neo-Hookean cube, structured, 150 nodes per side = 10 125 000 DoF
+per GPU (weak scaling stacks one such block per rank along z; --scaling strong splits the one cube in z-slabs).
 
 A "step" is one residual+Jacobian assembly pass over the whole (local) mesh:
-  value : device-resident (U, R, CSR values stay in HBM), CUDA-event timed on the library's stream,
-          L2 flushed between iterations, max over ranks.
-  e2e   : the same pass through the reference-facing call nls_residual_jacobian with HOST buffers
-          (pinned), H2D of U and D2H of U, R and the CSR values inside the timed region.
-  newton_step : one Newton step (assembly + Jacobi-PCG solve + update + residual norm), device-resident.
-  cpu_baseline: the oracle's C restatement of the reference algorithm on the box's host cores.
---impl reference times that CPU restatement alone (Julia is not installed, so the reference
-itself cannot run).
+  value        device-resident (U, R, CSR values stay in HBM), CUDA-event timed on the library's stream, L2 flushed between
+               iterations, max over ranks.
+  e2e          the same pass through the reference-facing call nls_residual_jacobian with HOST buffers (pinned): H2D of U
+               and D2H of U, R and the CSR values inside the timed region.
+  parity       outside the timed region, on every rank: the owned rows of two node planes in the middle of the rank's
+               slab (R and CSR rows) against the CPU oracle run on the five-plane sub-mesh around them.
+  newton_step  full Newton solve of the load step of SURVEY 8d (face z=0 clamped, opposite face pushed by -0.1*t at
+               t = 0.1, affine initial guess), rtol 1e-10, device-resident; per-iteration time and PCG counts.
+  c2           the round-1 headline (2-D plane strain, 708^2 nodes) for continuity.
+  cpu_baseline the oracle's C restatement of the reference algorithm on the box's host cores (bounded sample).
+--impl reference times that CPU restatement alone (Julia is not installed, so the reference itself cannot run).
 """
 import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -31,10 +33,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_SIDE = 708          # C2: 708^2 nodes = 1 002 528 DoF
-NCU_TRAFFIC_BYTES = 176.1e6   # measured DRAM traffic of the assembly kernel at C2 (see roofline.traffic_source)
-DIM = 2
+CONFIGS = {"C3": dict(dim=3, n=150, name="C3: 3-D Q1 hexahedral compressible Neo-Hookean cube, structured"),
+           "C2": dict(dim=2, n=708, name="C2: 2-D plane-strain Q1 compressible Neo-Hookean, structured")}
 E_MOD, NU = 1.0, 0.3
+LOAD_T = 0.1                      # prescribed compression -0.1 * t, single step t = 0.1
 
 
 def measured_peaks():
@@ -45,48 +47,66 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(cfg_key, kernel_hint):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu summary (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ent = json.load(f).get(cfg_key)
+        if ent and (kernel_hint is None or kernel_hint in ent.get("kernel", "")):
+            return float(ent["dram_bytes"]), ent.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML while the GPU is loaded."""
 
     def __init__(self, gpu):
-        self.gpu, self.proc, self.lines = gpu, None, []
+        self.gpu, self.stop_flag, self.thread = gpu, False, None
+        self.sm, self.smax, self.reasons, self.err = [], None, set(), None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:      # noqa: BLE001
+            self.err = "nvml unavailable: %s" % e
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:   # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+            time.sleep(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "samples": 0, "reasons": [self.err or "no samples"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "samples": len(self.sm),
+                "reasons": sorted(self.reasons)}
 
 
 def algorithmic_bytes(dim, nen, nel, nn, ndof_rows, nnz):
@@ -94,32 +114,47 @@ def algorithmic_bytes(dim, nen, nel, nn, ndof_rows, nnz):
     return 4 * nen * nel + 8 * dim * nn + 8 * ndof_rows + 8 * ndof_rows + 8 * nnz
 
 
-def build_local_model(nls, nranks, rank, device, uid=None):
-    shape = (N_SIDE, N_SIDE * nranks)
+def global_shape(cfg, nranks, scaling):
+    n, dim = cfg["n"], cfg["dim"]
+    return (n,) * (dim - 1) + ((n * nranks) if scaling == "weak" else n,)
+
+
+def workload_string(cfg, nranks, scaling):
+    sh = global_shape(cfg, nranks, scaling)
+    return "%s, %s nodes (%d DoF), fused residual+Jacobian assembly" % (
+        cfg["name"], " x ".join(str(s) for s in sh), int(np.prod(sh)) * cfg["dim"])
+
+
+def build_local_model(nls, cfg, nranks, rank, device, uid, scaling):
+    """The rank's slab of the structured mesh with the load step of SURVEY 8d: slowest-axis face 0 clamped, opposite face
+    pushed by -0.1 t (scaled with the height of the stacked domain, so the strain is the same at every N)."""
+    dim, n = cfg["dim"], cfg["n"]
+    shape = global_shape(cfg, nranks, scaling)
     mat = nls.NeoHookean(E=E_MOD, nu=NU)
+    plane = int(np.prod(shape[:-1]))
     if nranks == 1:
-        mesh = nls.grid_mesh(shape, DIM)
+        mesh = nls.grid_mesh(shape, dim)
         fem = nls.FEMModel(mesh, device=device)
-        n_owned, p0 = mesh.nn, 0
+        n_owned, p0, p1 = mesh.nn, 0, shape[-1]
     else:
-        sl = nls.slab_local_mesh(shape, DIM, nranks, rank)
+        sl = nls.slab_local_mesh(shape, dim, nranks, rank)
         mesh = sl["mesh"]
         fem = nls.FEMModel(mesh, device=device)
         fem.set_partition(sl["n_owned"], sl["neigh"], sl["send_ptr"], sl["send_nodes"], sl["recv_ptr"], sl["recv_nodes"])
         fem.set_comm(rank, nranks, uid)
-        n_owned, p0 = sl["n_owned"], sl["node_off"][rank]
-    plane = N_SIDE
-    # face y=0 clamped, opposite face pushed by -0.1*t (t = 0.1 -> -0.01 ... here one step, t = 0.1)
-    if rank == 0:
-        b = np.arange(plane)
-        d = (b[:, None] * DIM + np.arange(DIM)[None, :]).ravel()
+        n_owned = sl["n_owned"]
+        cuts = nls.slab_planes(shape[-1], nranks)
+        p0, p1 = cuts[rank], cuts[rank + 1]
+    height = (shape[-1] - 1) / (n - 1)
+    if p0 == 0:
+        d = (np.arange(plane)[:, None] * dim + np.arange(dim)[None, :]).ravel()
         fem.addboundary(nls.Dirichlet(d, np.zeros(len(d))))
-    if rank == nranks - 1:
-        ytop = N_SIDE * nranks - 1
-        t_nodes = ytop * plane + np.arange(plane) - p0
-        d = t_nodes * DIM + (DIM - 1)
-        fem.addboundary(nls.Dirichlet(d, np.full(len(d), -0.1 * 0.1 * (N_SIDE * nranks - 1) / (N_SIDE - 1))))
-    return fem, mat, mesh, n_owned
+    if p1 == shape[-1] and p1 > p0:
+        t_nodes = (shape[-1] - 1 - p0) * plane + np.arange(plane)
+        d = t_nodes * dim + (dim - 1)
+        fem.addboundary(nls.Dirichlet(d, np.full(len(d), -0.1 * LOAD_T * height)))
+    info = dict(shape=shape, plane=plane, p0=p0, p1=p1, n_owned=n_owned, height=height)
+    return fem, mat, mesh, info
 
 
 def _quiet_stdout():
@@ -135,6 +170,64 @@ def _quiet_stdout():
     return emit
 
 
+dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))      # noqa: E731
+
+
+def parity_check(nls, cfg, info, mesh, H, U_local, threads):
+    """Owned rows of two node planes in the middle of this rank's slab -- R and the CSR rows, pattern included -- against
+    the CPU oracle on the five-plane sub-mesh around them (every element that touches the two planes is inside it)."""
+    from oracle import oracle as orc
+    dim, plane, p0, p1 = cfg["dim"], info["plane"], info["p0"], info["p1"]
+    if p1 - p0 < 5:
+        return None
+    zc = (p0 + p1) // 2
+    za, zb = zc - 2, zc + 3                      # sub-mesh node planes [za, zb)
+    sub_shape = info["shape"][:-1] + (zb - za,)
+    sub = nls.grid_mesh(sub_shape, dim)
+    lo_node = (za - p0) * plane                  # local id of the sub-mesh's first node (owned planes are numbered in order)
+    sub.coords[:] = mesh.coords[lo_node:lo_node + sub.nn]
+    mat = nls.NeoHookean(E=E_MOD, nu=NU)
+    om = orc.OracleModel(dim, sub.conn, sub.coords, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mat.mu, mat.lam), nthreads=threads)
+    Usub = U_local[lo_node * dim:(lo_node + sub.nn) * dim].copy()
+    _, Ro = om.residual(Usub)
+    Ko = om.jacobian_csr(Usub)
+    Rabs, Kabs = om.contribution_scale(Usub)
+    rpo, cio = om.pattern()
+    r0s, r1s = 1 * plane * dim, 3 * plane * dim                  # sub-mesh rows of planes zc-1, zc
+    row0, row1 = (zc - 1 - p0) * plane * dim, (zc + 1 - p0) * plane * dim
+    e0, e1 = rpo[r0s], rpo[r1s]
+    R = np.zeros(row1 - row0); rp = np.zeros(row1 - row0 + 1, dtype=np.int64)
+    ci = np.zeros(e1 - e0, dtype=np.int32); vals = np.zeros(e1 - e0)
+    H.call("nls_dev_download_rows", row0, row1, dp(R), rp.ctypes.data_as(C.POINTER(C.c_int64)),
+           ci.ctypes.data_as(C.POINTER(C.c_int32)), dp(vals))
+    pattern_ok = bool(np.array_equal(rp - rp[0], rpo[r0s:r1s + 1] - e0) and
+                      np.array_equal(ci.astype(np.int64) - lo_node * dim, cio[e0:e1]))
+    Ros, Kos = Ro[r0s:r1s], Ko[e0:e1]
+    out = {"rows": int(row1 - row0), "entries": int(e1 - e0), "planes": [int(zc - 1), int(zc)], "pattern_bit_exact": pattern_ok,
+           "R_rel": float(np.abs(R - Ros).max() / np.abs(Ros).max()),
+           "K_rel": float(np.abs(vals - Kos).max() / np.abs(Kos).max()),
+           "R_entrywise_rel": float((np.abs(R - Ros) / np.where(Rabs[r0s:r1s] > 0, Rabs[r0s:r1s], 1.0)).max()),
+           "K_entrywise_rel": float((np.abs(vals - Kos) / np.where(Kabs[e0:e1] > 0, Kabs[e0:e1], 1.0)).max()),
+           "oracle": "oracle/nls_oracle.c on the %s-node sub-mesh, %d threads" % (" x ".join(str(s) for s in sub_shape), threads)}
+    return out
+
+
+def time_assembly(H, steps, warmup, barrier):
+    ms = C.c_float(0)
+
+    def step_dev():
+        H.call("nls_flush_l2")
+        H.call("nls_dev_barrier")        # N > 1: line the ranks' streams up, so the halo wait inside the step is not host jitter
+        H.call("nls_timer_start")
+        H.call("nls_dev_assemble", 1, 1)
+        H.call("nls_timer_stop", C.byref(ms))
+        return ms.value
+    for _ in range(warmup):
+        step_dev()
+    H.call("nls_sync"); barrier()
+    return [step_dev() for _ in range(steps)]
+
+
 def run_ours(args):
     emit = _quiet_stdout()
     import __graft_entry__ as g
@@ -142,13 +235,19 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = CONFIGS[args.config]
+    dim = cfg["dim"]
     dist = None
-    uid = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def new_uid():
+        if dist is None:
+            return None
+        import torch
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             buf = (C.c_uint8 * 128)()
@@ -156,7 +255,7 @@ def run_ours(args):
             assert rc == 0, nls.lib().nls_last_error(None)
             idt.copy_(torch.tensor(list(bytes(buf)), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        uid = bytes(idt.cpu().numpy().tolist())
+        return bytes(idt.cpu().numpy().tolist())
 
     def barrier():
         if dist is not None:
@@ -170,13 +269,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    fem, mat, mesh, n_owned = build_local_model(nls, world, rank, local_rank, uid)
+    def gather_obj(o):
+        if dist is None:
+            return [o]
+        lst = [None] * world
+        dist.all_gather_object(lst, o)
+        return lst
+
+    t_setup = time.perf_counter()
+    fem, mat, mesh, info = build_local_model(nls, cfg, world, rank, local_rank, new_uid(), args.scaling)
     H = fem.handle(mat)
     L = nls.lib()
+    setup_s = time.perf_counter() - t_setup
     if args.assembly is not None:
         H.call("nls_set_option", b"assembly", args.assembly)
-    if args.gather_ctas:
-        H.call("nls_set_option", b"gather_ctas", args.gather_ctas)
     scheme = L.nls_assembly_scheme(H.h)
     comm_path = L.nls_comm_path(H.h)
     comm_us = None
@@ -184,120 +290,152 @@ def run_ours(args):
         uh, ua = C.c_float(0), C.c_float(0)
         H.call("nls_dev_comm_probe", 200, C.byref(uh), C.byref(ua))
         comm_us = {"halo_exchange_us": uh.value, "allreduce_us": ua.value}
-    sys.stderr.write("rank %d: assembly scheme %d (0 atomic, 1 gather, 2 element records), comm path %d (1 NCCL, 2 peer memory) %s\n"
-                     % (rank, scheme, comm_path, comm_us))
+    sys.stderr.write("rank %d: setup %.1f s, assembly scheme %d (0 atomic, 1 gather, 2 element records, 3 line pairs), comm path %d %s\n"
+                     % (rank, setup_s, scheme, comm_path, comm_us))
     nrows, nnz = C.c_int64(0), C.c_int64(0)
     H.call("nls_pattern_size", C.byref(nrows), C.byref(nnz))
     nrows, nnz = nrows.value, nnz.value
     U0 = nls.smooth_field(mesh.coords)
-    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     H.call("nls_dev_upload_u", dp(U0))
-    ms = C.c_float(0)
 
     # ---- value: device-resident fused R+K assembly ----
-    def step_dev():
-        H.call("nls_flush_l2")
-        H.call("nls_dev_barrier")        # N > 1: line the ranks' streams up, so the halo wait inside the step is not host jitter
-        H.call("nls_timer_start")
-        H.call("nls_dev_assemble", 1, 1)
-        H.call("nls_timer_stop", C.byref(ms))
-        return ms.value
-
-    for _ in range(args.warmup):
-        step_dev()
+    times = time_assembly(H, 0, args.warmup, barrier)
     clocks = ClockSampler(local_rank)
-    H.call("nls_sync"); barrier()
     clocks.start()
     l0 = L.nls_kernel_launches(H.h)
     t_wall0 = time.perf_counter()
-    times = [step_dev() for _ in range(args.steps)]
+    times = time_assembly(H, args.steps, 0, barrier)
     H.call("nls_sync"); barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = L.nls_kernel_launches(H.h) - l0
-    ms_step = allmax(float(np.sum(times)) / args.steps)
-    # extend the clock sample over a longer loaded window (the K steps alone are a few ms)
-    for _ in range(2500):          # fixed count on every rank: each assembly holds a halo exchange
+    ms_local = float(np.sum(times)) / args.steps
+    ms_step = allmax(ms_local)
+    # keep the GPU loaded for ~1.5 s more so the clock sample covers a loaded window (same count on every rank)
+    for _ in range(int(min(4000, max(20, 1500.0 / max(ms_step, 1e-3))))):
         H.call("nls_dev_assemble", 1, 1)
     H.call("nls_sync")
     clk = clocks.stop()
-    total_dof = N_SIDE * N_SIDE * world * DIM
+    total_dof = int(np.prod(info["shape"])) * dim
+    kernel = {0: "atomic scatter: k_asm_q1_%dd<R,K> + zero-fill of R and the CSR values" % dim,
+              1: "k_asm_q1_2d_gather<R,K> (one launch = one fused pass, no zero-fill)",
+              2: "k_elem_q1_store + k_rows_from_records", 3: "k_asm_q1_3d_lines<R,K> (one launch = one fused pass, no zero-fill, no atomics)"}[scheme]
+
+    # ---- parity against the CPU oracle (outside the timed region), every rank ----
+    parity = None
+    if not args.skip_parity:
+        Udev = np.zeros(fem.ndof)
+        H.call("nls_dev_download_u", dp(Udev))       # as assembled: Dirichlet values written, ghosts exchanged
+        try:
+            par = parity_check(nls, cfg, info, mesh, H, Udev, max(1, (os.cpu_count() or 1) // world))
+        except Exception as e:      # noqa: BLE001
+            par = {"error": repr(e)}
+        allp = gather_obj(par)
+        if rank == 0:
+            good = [p for p in allp if p and "error" not in p]
+            parity = {k: max(p[k] for p in good) for k in ("R_rel", "K_rel", "R_entrywise_rel", "K_entrywise_rel")} if good else {}
+            parity.update({"pattern_bit_exact": all(p["pattern_bit_exact"] for p in good) if good else None,
+                           "ranks_checked": len(good), "rows_per_rank": good[0]["rows"] if good else 0,
+                           "entries_per_rank": good[0]["entries"] if good else 0, "oracle": good[0]["oracle"] if good else None,
+                           "tolerance": 1e-12, "errors": [p["error"] for p in allp if p and "error" in p]})
 
     # ---- e2e: host buffers through the reference-facing call ----
-    try:
-        import torch
-        pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()
-    except Exception:
-        pin = lambda n: np.empty(n)
-    Uh, Rh, Vh = pin(fem.ndof), pin(nrows), pin(nnz)
-    Uh[:] = U0
-    e2e_steps = 0 if args.skip_e2e else args.steps
-    for _ in range(0 if args.skip_e2e else max(1, args.warmup // 2)):
-        H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))
-    e2e_s = allmax((time.perf_counter() - t0) / max(1, e2e_steps)) or 1e-30
-    barrier()
+    e2e = None
+    if not args.skip_e2e:
+        try:
+            import torch
+            pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()     # noqa: E731
+        except Exception:       # noqa: BLE001
+            pin = lambda n: np.empty(n)     # noqa: E731
+        Uh, Rh, Vh = pin(fem.ndof), pin(nrows), pin(nnz)
+        Uh[:] = U0
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))          # warm-up (page-in of the pinned buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))
+        e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
+        barrier()
+        e2e = {"value": total_dof / e2e_s, "unit": "DoF/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "h2d_bytes_per_step": 8 * fem.ndof, "d2h_bytes_per_step": 8 * (fem.ndof + nrows + nnz)}
+        del Uh, Rh, Vh
 
-    # ---- Newton step (assembly + PCG + update + norm), device-resident ----
-    # initial guess: the affine field that interpolates the two Dirichlet faces (a zero guess would
-    # invert the top element layer: the prescribed 1% compression exceeds the element height 1/707)
-    height = (N_SIDE * world - 1) / (N_SIDE - 1)
-    Uaff = np.zeros((mesh.nn, DIM)); Uaff[:, DIM - 1] = -0.1 * 0.1 * mesh.coords[:, DIM - 1]
-    Uaff = Uaff.ravel()
-    H.call("nls_dev_upload_u", dp(Uaff))
-    li, nr = C.c_int32(0), C.c_double(0)
+    # ---- Newton: the load step of SURVEY 8d, full solve, device-resident ----
     newton = None
     if not args.skip_newton:
-        H.call("nls_dev_newton_step", args.lin_rtol, 200, C.byref(li), C.byref(nr))      # warm-up (short)
+        # initial guess: the affine field that interpolates the two Dirichlet faces (a zero guess would invert the top
+        # element layer: the prescribed compression exceeds the element height)
+        Uaff = np.zeros((mesh.nn, dim)); Uaff[:, dim - 1] = -0.1 * LOAD_T * mesh.coords[:, dim - 1]
+        Uaff = Uaff.ravel()
         H.call("nls_dev_upload_u", dp(Uaff))
+        opts = nls._lib.NewtonOpts(rtol=1e-10, atol=1e-14, dtol=1e6, maxits=25, type_modified=0,
+                                   lin_rtol=args.lin_rtol, lin_maxits=100000)
+        res = nls._lib.NewtonResult()
+        hist = np.zeros(64)
         H.call("nls_sync"); barrier()
-        H.call("nls_timer_start")
-        H.call("nls_dev_newton_step", args.lin_rtol, 50000, C.byref(li), C.byref(nr))
-        H.call("nls_timer_stop", C.byref(ms))
-        nstep_ms = allmax(ms.value)
+        H.call("nls_dev_newton_solve", C.byref(opts), dp(hist), C.byref(res))
+        tot_ms = allmax(res.ms_total)
+        its = max(1, res.iterations)
         spmv_bytes = 12 * nnz + 24 * nrows
         pcg_iter_bytes = spmv_bytes + 128 * nrows
-        abytes = algorithmic_bytes(DIM, mesh.nen, mesh.nel, mesh.nn, nrows, nnz)
-        alg = 2 * abytes - 8 * nnz + li.value * pcg_iter_bytes + 32 * nrows
+        abytes = algorithmic_bytes(dim, mesh.nen, mesh.nel, mesh.nn, nrows, nnz)
+        alg = (res.iterations + 1) * abytes + res.lin_its_total * pcg_iter_bytes + res.iterations * 32 * nrows
         hbm, _ = measured_peaks()
-        newton = {"ms": nstep_ms, "pcg_iterations": li.value, "lin_rtol": args.lin_rtol,
-                  "residual_norm_after": nr.value, "algorithmic_GB": alg / 1e9,
-                  "achieved_GBs": alg / nstep_ms / 1e6, "frac_of_hbm": alg / nstep_ms / 1e6 / hbm}
+        newton = {"ms": tot_ms / its, "total_ms": tot_ms, "iterations": int(res.iterations), "reason": int(res.reason),
+                  "converged": int(res.reason) in (1, 2), "pcg_iterations": int(res.lin_its_total),
+                  "ms_assembly": allmax(res.ms_assembly), "ms_linear": allmax(res.ms_linear),
+                  "rtol": 1e-10, "atol": 1e-14, "lin_rtol": args.lin_rtol,
+                  "load": "face 0 of the slowest axis clamped, opposite face -0.1*t at t=0.1 (1 %% compression), affine initial guess",
+                  "residual_norms": [float(v) for v in hist[:res.nhist]],
+                  "algorithmic_GB": alg / 1e9, "achieved_GBs": alg / tot_ms / 1e6, "frac_of_hbm": alg / tot_ms / 1e6 / hbm}
 
-    abytes = algorithmic_bytes(DIM, mesh.nen, mesh.nel, mesh.nn, nrows, nnz)
+    # ---- C2 (round-1 headline) for continuity: assembly only ----
+    c2 = None
+    if args.config == "C3" and not args.skip_c2:
+        try:
+            cfg2 = CONFIGS["C2"]
+            fem2, mat2, mesh2, info2 = build_local_model(nls, cfg2, world, rank, local_rank, new_uid(), "weak")
+            H2 = fem2.handle(mat2)
+            H2.call("nls_dev_upload_u", dp(nls.smooth_field(mesh2.coords)))
+            t2 = time_assembly(H2, max(10, args.steps), 5, barrier)
+            ms2 = allmax(float(np.mean(t2)))
+            nr2, nz2 = C.c_int64(0), C.c_int64(0)
+            H2.call("nls_pattern_size", C.byref(nr2), C.byref(nz2))
+            ab2 = algorithmic_bytes(2, mesh2.nen, mesh2.nel, mesh2.nn, nr2.value, nz2.value)
+            hbm, _ = measured_peaks()
+            dof2 = int(np.prod(info2["shape"])) * 2
+            tr2, _src = ncu_traffic("C2", None)
+            c2 = {"workload": workload_string(cfg2, world, "weak"), "value": dof2 / (ms2 * 1e-3), "unit": "DoF/s", "ms_per_step": ms2,
+                  "roofline_frac": ab2 / (float(np.mean(t2)) * 1e-3) / 1e9 / hbm, "algorithmic_bytes": ab2, "traffic": tr2}
+            del H2, fem2
+        except Exception as e:      # noqa: BLE001
+            c2 = {"error": repr(e)}
+
+    abytes = algorithmic_bytes(dim, mesh.nen, mesh.nel, mesh.nn, nrows, nnz)
     hbm, which = measured_peaks()
-    achieved = abytes / (float(np.mean(times)) * 1e-3) / 1e9
+    achieved = abytes / (ms_local * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.config, "lines" if scheme == 3 else ("gather" if scheme == 1 else None))
     out = None
     if rank == 0:
         out = {
             "metric": "assembled DoF/s (residual+Jacobian)", "value": total_dof / (ms_step * 1e-3), "unit": "DoF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 2-D plane-strain Neo-Hookean, structured Q1, %d x %d nodes (%d DoF), fused residual+Jacobian assembly"
-                       % (N_SIDE, N_SIDE * world, total_dof), "per_gpu_dof": N_SIDE * N_SIDE * DIM,
-                       "nnz_per_gpu": nnz, "partition": "y-slabs, one per GPU" if world > 1 else "single GPU",
-                       "cache": "L2 flushed (256 MiB memset) between timed iterations"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_string(cfg, world, args.scaling), "per_gpu_dof": int(nrows),
+                       "nnz_per_gpu": int(nnz), "partition": "z-slabs, one per GPU" if world > 1 else "single GPU",
+                       "cache": "L2 flushed (256 MiB memset) between timed iterations", "setup_s": setup_s},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": NCU_TRAFFIC_BYTES if args.assembly in (None, 1) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r1k_ncu_asm2d_gather_v11.txt): 79.4 MB read + 96.7 MB written; the reads include ~45 MB of staged "
-                                           "cluster plan (node lists, per-block source lists) on top of U and the coordinates, while part of the "
-                                           "freshly written CSR values is still in the 126 MB L2 when the kernel ends",
-                         "kernel": "k_asm_q1_2d_gather<R,K> (one launch = one fused assembly pass; no zero-fill needed)"
-                                   if args.assembly in (None, 1) else "k_asm_q1_2d<R,K> + zero-fill of R and CSR values",
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
                          "algorithmic_bytes": abytes, "peak_source": which},
-            "e2e": {"value": total_dof / e2e_s, "unit": "DoF/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": 8 * fem.ndof, "d2h_bytes_per_step": 8 * (fem.ndof + nrows + nnz)},
-            "gpu_launches": int(launches), "clocks": clk, "newton_step": newton,
+            "e2e": e2e, "parity": parity,
+            "gpu_launches": int(launches), "clocks": clk, "newton_step": newton, "c2": c2,
             "comm": {"path": {0: "single GPU", 1: "NCCL send/recv + allreduce", 2: "peer-memory windows over NVLink (CUDA IPC)"}[comm_path],
                      "latency": comm_us},
             "wall_s_timed_region": t_wall,
         }
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.skip_cpu:
-        out["cpu_baseline"] = cpu_baseline(nls, sample_rows=args.cpu_rows)
+        out["cpu_baseline"] = cpu_baseline(nls, cfg, planes=args.cpu_planes)
     if rank == 0:
         emit(out)
     if dist is not None:
@@ -305,15 +443,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(nls, sample_rows=N_SIDE, steps=1, threads=None):
-    """Oracle (C restatement of the reference algorithm: separate residual and Jacobian passes,
-    CSR storage) on the host cores; a bounded sample = the first `sample_rows` node rows of C2."""
+def cpu_baseline(nls, cfg, planes, steps=1, threads=None):
+    """Oracle (C restatement of the reference algorithm: separate residual and Jacobian passes, CSR storage) on the host
+    cores; a bounded sample = the first `planes` node planes of the workload's mesh."""
     from oracle import oracle as orc
     threads = threads or os.cpu_count() or 1
-    shape = (N_SIDE, sample_rows)
-    mesh = nls.grid_mesh(shape, DIM)
+    dim, n = cfg["dim"], cfg["n"]
+    shape = (n,) * (dim - 1) + (planes,)
+    mesh = nls.grid_mesh(shape, dim)
     mat = nls.NeoHookean(E=E_MOD, nu=NU)
-    om = orc.OracleModel(DIM, mesh.conn, mesh.coords, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mat.mu, mat.lam), nthreads=threads)
+    om = orc.OracleModel(dim, mesh.conn, mesh.coords, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mat.mu, mat.lam), nthreads=threads)
     U = nls.smooth_field(mesh.coords)
     om.pattern()
     om.residual(U); om.jacobian_csr(U)          # warm-up (page-in)
@@ -323,9 +462,10 @@ def cpu_baseline(nls, sample_rows=N_SIDE, steps=1, threads=None):
         om.residual(U)
         om.jacobian_csr(U)
         best = min(best, time.perf_counter() - t0)
-    ndof = mesh.nn * DIM
+    ndof = mesh.nn * dim
     return {"value": ndof / best, "unit": "DoF/s", "cores": threads, "kind": "port", "seconds": best,
-            "sample": "%d x %d-node slab of the C2 mesh (%d DoF), residual pass + Jacobian pass, CSR" % (N_SIDE, sample_rows, ndof)}
+            "sample": "the first %d node planes of the mesh (%s nodes, %d DoF), residual pass + Jacobian pass, CSR"
+                      % (planes, " x ".join(str(s) for s in shape), ndof)}
 
 
 def run_reference(args):
@@ -335,25 +475,25 @@ def run_reference(args):
         return
     import __graft_entry__ as g
     nls = g.load_package()   # host-side mesh generators only; no GPU, no libnls_b200 compute
+    cfg = CONFIGS[args.config]
     threads = os.cpu_count() or 1
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     for _ in range(max(0, args.warmup - 1)):
-        cpu_baseline(nls, sample_rows=args.cpu_rows, threads=threads)
+        cpu_baseline(nls, cfg, planes=args.cpu_planes, threads=threads)
     t0 = time.perf_counter()
-    vals = [cpu_baseline(nls, sample_rows=args.cpu_rows, threads=threads) for _ in range(args.steps)]
+    vals = [cpu_baseline(nls, cfg, planes=args.cpu_planes, threads=threads) for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     v = float(np.median([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
-    total_dof = N_SIDE * N_SIDE * world * DIM
     print(json.dumps({
         "impl": "reference", "metric": "assembled DoF/s (residual+Jacobian)", "value": v, "unit": "DoF/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.median([x["seconds"] for x in vals])),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 2-D plane-strain Neo-Hookean, structured Q1, %d x %d nodes (%d DoF), residual+Jacobian assembly"
-                   % (N_SIDE, N_SIDE * world, total_dof),
-                   "note": "CPU restatement (oracle/) of the reference algorithm on %d host threads; Julia is not installed. "
-                           "Each step is a bounded sample: %s" % (threads, cb["sample"])},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_string(cfg, world, args.scaling),
+                   "note": "CPU restatement (oracle/) of the reference algorithm on %d host threads; Julia is not installed. The rate "
+                           "is measured on a bounded sample of the workload at every N (the CPU path does not scale with the GPU "
+                           "count): %s" % (threads, cb["sample"])},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall}))
@@ -365,16 +505,22 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--lin-rtol", dest="lin_rtol", type=float, default=1e-8)
     ap.add_argument("--skip-newton", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--gather-ctas", dest="gather_ctas", type=int, default=0)
-    ap.add_argument("--assembly", type=int, default=None, help="0 atomic scatter, 1 gather/row-owner (default)")
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--skip-c2", action="store_true")
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
+    ap.add_argument("--assembly", type=int, default=None, help="0 atomic scatter, 1 best atomic-free scheme (default)")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--cpu-rows", dest="cpu_rows", type=int, default=N_SIDE)
+    ap.add_argument("--cpu-planes", dest="cpu_planes", type=int, default=0, help="node planes of the CPU sample (0: 9 in 3-D, 708 in 2-D)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
+    if a.cpu_planes <= 0:
+        a.cpu_planes = 9 if CONFIGS[a.config]["dim"] == 3 else CONFIGS[a.config]["n"]
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -192,6 +192,10 @@ int32_t nls_dev_upload_u(nls_handle h, const double *U);
 int32_t nls_dev_download_u(nls_handle h, double *U);
 int32_t nls_dev_download_r(nls_handle h, double *R);
 int32_t nls_dev_download_vals(nls_handle h, double *vals);
+/* Rows [row0, row1) of the device-resident operators: R[row0:row1], and of the CSR Jacobian the row pointers
+   (row1 - row0 + 1 entries, as stored: offsets into the whole matrix), column indices and values of those rows.
+   Any output may be NULL. For spot checks of large models whose whole Jacobian should not cross PCIe. */
+int32_t nls_dev_download_rows(nls_handle h, int64_t row0, int64_t row1, double *R, int64_t *rowptr, int32_t *colind, double *vals);
 int32_t nls_dev_assemble(nls_handle h, int32_t want_residual, int32_t want_jacobian);
 int32_t nls_dev_spmv(nls_handle h);          /* work vector Ap = K * work vector p (p := U for the hook) */
 int32_t nls_dev_pcg_iterations(nls_handle h, int32_t niter); /* exactly niter PCG iterations on b = -R */

@@ -84,6 +84,7 @@ PROTOTYPES = {
     "nls_dev_download_u": (C.c_int32, [_H, _dp]),
     "nls_dev_download_r": (C.c_int32, [_H, _dp]),
     "nls_dev_download_vals": (C.c_int32, [_H, _dp]),
+    "nls_dev_download_rows": (C.c_int32, [_H, C.c_int64, C.c_int64, _dp, _lp, _ip, _dp]),
     "nls_dev_assemble": (C.c_int32, [_H, C.c_int32, C.c_int32]),
     "nls_dev_spmv": (C.c_int32, [_H]),
     "nls_dev_pcg_iterations": (C.c_int32, [_H, C.c_int32]),

@@ -491,6 +491,7 @@ int nls_launch_assembly(nls_context *h, bool want_r, bool want_k) {
   const int mode = nls_assembly_mode(h);
   if (mode == NLS_ASM_GATHER) return nls_launch_gather_2d(h, want_r, want_k);
   if (mode == NLS_ASM_TWOPHASE) return nls_launch_twophase(h, want_r, want_k);
+  if (mode == NLS_ASM_LINES) return nls_launch_lines3(h, want_r, want_k);
   if (h->dim == 2) {
     const unsigned g = nblk(h->nel, 128);
     if (want_r && want_k) k_asm_q1_2d<true, true><<<g, 128, 0, h->stream>>>(a, h->tabq, h->mat);

@@ -335,6 +335,7 @@ int nls_assembly_mode(nls_context *h) {
   if (h->opt_assembly == 0 || h->dim < 2) return NLS_ASM_ATOMIC;
   if (h->dim == 2 && h->opt_assembly == 1 && h->have_plan) return NLS_ASM_GATHER;
   TwoPhasePlan &t = h->tplan;
+  if (h->dim == 3 && h->opt_assembly == 1 && h->lplan.ok) return NLS_ASM_LINES;
   if (h->dim == 3 && h->opt_assembly == 1 && !h->opt_twophase_3d) return NLS_ASM_ATOMIC;
   if (t.ok && !t.scratch) {       // first use: the record scratch; without room for it keep the atomic scatter
     if (cudaMalloc((void **)&t.scratch, t.scratch_bytes) != cudaSuccess) { cudaGetLastError(); t.scratch = nullptr; t.ok = false; }

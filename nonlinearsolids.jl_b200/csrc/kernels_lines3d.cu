@@ -1,0 +1,664 @@
+// kernels_lines3d.cu -- atomic-free ("pair-owner") assembly of the 3-D Q1 Neo-Hookean residual and CSR Jacobian on
+// meshes with grid topology (lexicographic hexahedral grids and their slab partitions, coordinates arbitrary).
+//
+// Replaces, like kernels_assembly.cu:  compute_internalforce / compute_dinternalforce (src/materials/defaults.jl:29-46,
+// 68-82) with restrict! / unrestrict! / assemble! (src/fem/element.jl:64-70) folded in. The 24 x 24 element matrix is
+// never formed: every 3 x 3 CSR block K_AB = sum over the elements e that hold both nodes, over their 8 quadrature
+// points, of
+//     c2 g_A (x) g_B + c3 g_B (x) g_A   (+ mu * L_AB on the diagonal, L = reference-configuration Laplacian, built once per mesh)
+// is summed by ONE thread in a fixed order and stored once, together with its transpose K_BA (K is symmetric): no
+// atomics, no zero-fill of the CSR values, no element-matrix exchange, bit-reproducible run to run.
+//
+// Work decomposition. Node lines run along x (the fastest node index). A CTA owns a tile of L3_TY x L3_TZ lines and
+// marches along x; per x-interval i (the elements between node planes i and i+1 of the (TY+1) x (TZ+1) element columns
+// that touch the tile):
+//   phase A  one thread per (element column, quadrature point): J, H = sum u (x) dN, M = J + H, M^-1, ln det F,
+//            g_a = M^-T dN_a (spatial gradients) and the scalars -> shared-memory records (SoA, 16-byte columns:
+//            every LDS.128 / STS.128 of a warp is conflict-free)
+//   phase B  one thread per (line, half-stencil offset): the line pair (L, L + d), d in {(0,0), (1,0), (-1,1), (0,1), (1,1)}
+//            in (y, z). It accumulates the four blocks between nodes {i, i+1} of L and {i, i+1} of L + d over the one or
+//            two (self: four) element columns that hold both lines -- symmetric and skew parts separately, 15 DFMA per
+//            block and point instead of 18 -- writes the blocks that interval i completes (rows of L and, transposed, rows
+//            of L + d) and carries the (i+1, i+1) block into the next interval. The self pair also sums f_int.
+// Every CSR block is written by exactly one thread of the grid; a tile only recomputes the quadrature-point records of the
+// element columns on its border (81 columns per 64 lines). Row addresses are closed-form per line (host tables,
+// verified against the CSR pattern when the plan is built); meshes without grid topology keep the atomic scatter.
+#include <algorithm>
+#include <cstring>
+#include "asm_common.cuh"
+
+#define L3_TY 8
+#define L3_TZ 8
+#define L3_NL (L3_TY * L3_TZ)            // lines per tile
+#define L3_CY (L3_TY + 1)                // element columns per tile row
+#define L3_NCOL (L3_CY * (L3_TZ + 1))    // 81 element columns touch a tile
+#define L3_ZCOL L3_NCOL                  // an all-zero column: what pairs read where the mesh has no element
+#define L3_NCOLP (L3_NCOL + 1)
+#define L3_NY2 (L3_TY + 2)               // node lines cached per row
+#define L3_NLC (L3_NY2 * (L3_TZ + 2))    // 100 node lines touch those columns
+#define L3_NLCP 104
+#define L3_THREADS 384                   // 12 warps; 10 of them own line pairs in phase B
+#define L3_NPT (5 * L3_NL)               // pair threads per tile
+
+struct L3Line {                          // per node line (y, z): closed-form CSR addressing of its rows
+  int64_t lb;                            // block-row start of the line's first node
+  int32_t nl;                            // neighbour lines present (block-row length = nl * (2 or 3))
+  int8_t rank[9];                        // rank of neighbour line (dz+1)*3 + (dy+1) among them in column order, -1 = absent
+  int8_t pad[3];
+};
+
+struct L3Args {
+  int nx, ny, nzp, nunits;
+  const int32_t *pbase;                  // [nzp] first node id of each node plane
+  const uint8_t *pown;                   // [nzp] plane holds owned nodes
+  const L3Line *info;                    // [nzp * ny]
+  const int4 *units;                     // {y0, z0, i0, i1}: tile origin and x-interval range
+  const int64_t *lapoff;                 // [nunits] offset of the unit's Laplacian values
+  double *lap;                           // [unit][interval (+1)][3][L3_NPT]
+  const double *coords, *U;
+  double *R, *vals;
+  unsigned *counter;                     // [2] next unit, CTAs done
+};
+
+__device__ __forceinline__ void l3_cp8(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void l3_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void l3_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// stores of 3 / 6 consecutive doubles at an 8-byte aligned address: 16-byte stores wherever the alignment allows.
+// Inline PTX on purpose: written as C++ the optimiser merges the stores of the two alignment branches into one
+// unconditional 16-byte store that is misaligned for half of the addresses (seen in the SASS of the first version).
+__device__ __forceinline__ void l3_stg1(double *p, double a) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(a)); }
+__device__ __forceinline__ void l3_stg2(double *p, double a, double b) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b)); }
+__device__ __forceinline__ void l3_st3(double *p, double a, double b, double c) {
+  if ((reinterpret_cast<uintptr_t>(p) & 8) == 0) { l3_stg2(p, a, b); l3_stg1(p + 2, c); }
+  else { l3_stg1(p, a); l3_stg2(p + 1, b, c); }
+}
+__device__ __forceinline__ void l3_st6(double *p, double a, double b, double c, double d, double e, double f) {
+  if ((reinterpret_cast<uintptr_t>(p) & 8) == 0) { l3_stg2(p, a, b); l3_stg2(p + 2, c, d); l3_stg2(p + 4, e, f); }
+  else { l3_stg1(p, a); l3_stg2(p + 1, b, c); l3_stg2(p + 3, d, e); l3_stg1(p + 5, f); }
+}
+
+// one block accumulator: {D0, D1, D2, S01, S02, S12, W01, W02, W12}; K_ik = S_ik + W_ik, K_ki = S_ik - W_ik, K_ii = 2 D_i
+__device__ __forceinline__ void l3_acc(double (&K)[9], const double (&p)[3], const double (&m)[3], const double (&b)[3]) {
+  K[0] = fma(p[0], b[0], K[0]); K[1] = fma(p[1], b[1], K[1]); K[2] = fma(p[2], b[2], K[2]);
+  K[3] = fma(p[0], b[1], fma(p[1], b[0], K[3]));
+  K[4] = fma(p[0], b[2], fma(p[2], b[0], K[4]));
+  K[5] = fma(p[1], b[2], fma(p[2], b[1], K[5]));
+  K[6] = fma(m[0], b[1], fma(-m[1], b[0], K[6]));
+  K[7] = fma(m[0], b[2], fma(-m[2], b[0], K[7]));
+  K[8] = fma(m[1], b[2], fma(-m[2], b[1], K[8]));
+}
+__device__ __forceinline__ void l3_full(const double (&K)[9], const double dl, double (&F)[3][3]) {
+  F[0][0] = fma(2.0, K[0], dl); F[1][1] = fma(2.0, K[1], dl); F[2][2] = fma(2.0, K[2], dl);
+  F[0][1] = K[3] + K[6]; F[1][0] = K[3] - K[6];
+  F[0][2] = K[4] + K[7]; F[2][0] = K[4] - K[7];
+  F[1][2] = K[5] + K[8]; F[2][1] = K[5] - K[8];
+}
+
+struct L3Row { double *p; int64_t stride; };   // first entry of a block in scalar row 0, distance between the scalar rows
+// block at x-offset dx (-1, 0, +1) of the neighbour-line triple `rank` in the row of node i of a line
+__device__ __forceinline__ L3Row l3_row(double *vals, const int64_t lb, const int nl, const int rank, const int i, const int nxm1, const int dx) {
+  const int w = (i == 0 || i == nxm1) ? 2 : 3;
+  const int64_t b0 = lb + (int64_t)nl * (i == 0 ? 0 : 3 * i - 1);
+  const int pos = rank * w + dx + (i == 0 ? 0 : 1);
+  L3Row r;
+  r.stride = 3 * (int64_t)nl * w;
+  r.p = vals + 9 * b0 + 3 * pos;
+  return r;
+}
+
+template <bool DO_R, bool DO_K, bool LAP_BUILD>
+__global__ void __launch_bounds__(L3_THREADS, 1)
+k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
+  constexpr int NARR = DO_R ? 16 : 13;          // double2 arrays per quadrature point: 4 corner pairs x 3, scalars, stress x 3
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *REC = reinterpret_cast<double2 *>(smem_raw);                 // [8][NARR][L3_NCOLP]
+  double *XU = reinterpret_cast<double *>(REC + 8 * NARR * L3_NCOLP);   // [3 planes][6][L3_NLCP]: X, u of the cached node lines
+  double *TAB = XU + 3 * 6 * L3_NLCP;                                   // dN[8][8][3], w[8]
+  __shared__ int s_unit;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < 192; k += L3_THREADS) TAB[k] = T.dN[k / 24][(k / 3) & 7][k % 3];
+  if (tid < 8) TAB[192 + tid] = T.w[tid];
+  for (int k = tid; k < 8 * NARR; k += L3_THREADS) REC[k * L3_NCOLP + L3_ZCOL] = make_double2(0.0, 0.0);
+  const double mu = LAP_BUILD ? 0.0 : mp.p[0], lam = mp.p[1];
+  const int nx = P.nx, ny = P.ny, nzp = P.nzp, nxm1 = nx - 1;
+
+  // phase-B role of this warp: {self, self, (0,1), (0,1), (1,0), (1,0), (-1,1), (-1,1), none, none, (1,1), (1,1)} -- per SM
+  // sub-partition (warp & 3) the roles add up to about the same DFMA count
+  int ptype, dy, dz;
+  switch (warp >> 1) {
+    case 0: ptype = 0; dy = 0; dz = 0; break;
+    case 1: ptype = 3; dy = 0; dz = 1; break;
+    case 2: ptype = 1; dy = 1; dz = 0; break;
+    case 3: ptype = 2; dy = -1; dz = 1; break;
+    case 5: ptype = 4; dy = 1; dz = 1; break;
+    default: ptype = -1; dy = 0; dz = 0; break;
+  }
+  const int ll = (warp & 1) * 32 + lane, ly = ll & (L3_TY - 1), lz = ll / L3_TY;
+  const int pidx = ptype * L3_NL + ll;
+
+  for (;;) {
+    if (tid == 0) s_unit = (int)atomicAdd(P.counter, 1u);
+    __syncthreads();
+    const int u = s_unit;
+    if (u >= P.nunits) break;
+    const int4 un = P.units[u];
+    const int y0 = un.x, z0 = un.y, i0 = un.z, i1 = un.w;
+
+    // ---- per-unit role of this thread in phase B ----
+    bool wd = false, wm = false;
+    int colv[4] = {L3_ZCOL, L3_ZCOL, L3_ZCOL, L3_ZCOL}, offA[4] = {0, 0, 0, 0}, offB[2] = {0, 0};
+    int64_t lbA = 0, lbB = 0;
+    int nlA = 0, nlB = 0, rA = 0, rB = 0;
+    int64_t nodeA0 = 0;
+    if (ptype >= 0 && (DO_K || ptype == 0)) {
+      const int y = y0 + ly, z = z0 + lz, y2 = y + dy, z2 = z + dz;
+      const bool e1 = y < ny && z < nzp, e2 = e1 && y2 >= 0 && y2 < ny && z2 < nzp;
+      if (e1 && e2) {
+        wd = P.pown[z] != 0;
+        wm = ptype != 0 && P.pown[z2] != 0;
+      }
+      if (wd || wm) {
+        auto col_of = [&](int ey, int ez) -> int {
+          return (ey >= 0 && ey < ny - 1 && ez >= 0 && ez < nzp - 1) ? (ez - z0 + 1) * L3_CY + (ey - y0 + 1) : L3_ZCOL;
+        };
+        // element columns that hold both lines, with the corner pair (dy' + 2 dz') of each line inside the column
+        if (ptype == 0) {
+          colv[0] = col_of(y - 1, z - 1); offA[0] = 3; colv[1] = col_of(y, z - 1); offA[1] = 2;
+          colv[2] = col_of(y - 1, z); offA[2] = 1;     colv[3] = col_of(y, z); offA[3] = 0;
+        } else if (ptype == 1) {
+          colv[0] = col_of(y, z - 1); offA[0] = 2; offB[0] = 3; colv[1] = col_of(y, z); offA[1] = 0; offB[1] = 1;
+        } else if (ptype == 2) {
+          colv[0] = col_of(y - 1, z); offA[0] = 1; offB[0] = 2;
+        } else if (ptype == 3) {
+          colv[0] = col_of(y - 1, z); offA[0] = 1; offB[0] = 3; colv[1] = col_of(y, z); offA[1] = 0; offB[1] = 2;
+        } else {
+          colv[0] = col_of(y, z); offA[0] = 0; offB[0] = 3;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) offA[k] *= 3 * L3_NCOLP;
+        offB[0] *= 3 * L3_NCOLP; offB[1] *= 3 * L3_NCOLP;
+        if (wd) {
+          const L3Line a = P.info[z * ny + y];
+          lbA = a.lb; nlA = a.nl; rA = a.rank[(dz + 1) * 3 + (dy + 1)];
+          nodeA0 = (int64_t)P.pbase[z] + (int64_t)y * nx;
+        }
+        if (wm) {
+          const L3Line b = P.info[z2 * ny + y2];
+          lbB = b.lb; nlB = b.nl; rB = b.rank[(1 - dz) * 3 + (1 - dy)];
+        }
+      }
+    }
+    const bool on = wd || wm;
+    const bool two = (ptype == 1 || ptype == 3);
+    double *lapu = P.lap + P.lapoff[u] + pidx;
+
+    // accumulators: Kd = (A_i, B_i), Ku = (A_i, B_i+1), Kl = (A_i+1, B_i), Kn = (A_i+1, B_i+1); self: Kd, Kn hold 6 symmetric sums
+    double Kd[9], Ku[9], Kl[9], Kn[9], fd[3] = {0, 0, 0}, fn[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Kd[k] = 0.0; Ku[k] = 0.0; Kl[k] = 0.0; Kn[k] = 0.0; }
+
+    auto load_plane = [&](int ip) {            // X, u of node plane ip of the cached lines -> ring slot ip % 3
+      if (ip > nxm1) return;
+      const int slot = ip % 3;
+      for (int k = tid; k < 2 * L3_NLC; k += L3_THREADS) {
+        const int c = k >> 1, half = k & 1;
+        const int y = y0 - 1 + c % L3_NY2, z = z0 - 1 + c / L3_NY2;
+        if (y < 0 || y >= ny || z < 0 || z >= nzp) continue;
+        const int64_t node = (int64_t)P.pbase[z] + (int64_t)y * nx + ip;
+        const double *src = (half ? P.U : P.coords) + 3 * node;
+        double *dst = XU + (slot * 6 + 3 * half) * L3_NLCP + c;
+        l3_cp8(dst, src); l3_cp8(dst + L3_NLCP, src + 1); l3_cp8(dst + 2 * L3_NLCP, src + 2);
+      }
+    };
+
+    const int ifirst = i0 > 0 ? i0 - 1 : 0;    // a chunk that starts inside the line first runs one interval without stores
+    load_plane(ifirst); load_plane(ifirst + 1);
+    l3_commit(); l3_wait_all();
+    __syncthreads();
+
+    for (int i = ifirst; i < i1; ++i) {
+      load_plane(i + 2);
+      l3_commit();
+      double lp0 = 0.0, lp1 = 0.0, lp2 = 0.0;
+      const bool store = i >= i0;
+      if (!LAP_BUILD && DO_K && on && store) {
+        const double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
+        lp0 = lq[0]; lp1 = lq[L3_NPT]; lp2 = lq[2 * L3_NPT];
+      }
+      // ---------------- phase A: quadrature-point records of interval i ----------------
+      {
+        const int slo = i % 3, shi = (i + 1) % 3;
+#pragma unroll 1
+        for (int item = tid; item < 8 * L3_NCOL; item += L3_THREADS) {
+          const int q = item / L3_NCOL, col = item - q * L3_NCOL;
+          const int cyi = col % L3_CY, czi = col / L3_CY;
+          const int ey = y0 - 1 + cyi, ez = z0 - 1 + czi;
+          if (ey < 0 || ey >= ny - 1 || ez < 0 || ez >= nzp - 1) continue;
+          const double *tq = TAB + q * 24;
+          double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const int cl = (czi + (a >> 2)) * L3_NY2 + cyi + ((a >> 1) & 1);
+            const double *xs = XU + ((a & 1) ? shi : slo) * 6 * L3_NLCP + cl;
+            const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const double x = xs[d * L3_NLCP];
+              J[d * 3 + 0] = fma(x, dn0, J[d * 3 + 0]); J[d * 3 + 1] = fma(x, dn1, J[d * 3 + 1]); J[d * 3 + 2] = fma(x, dn2, J[d * 3 + 2]);
+            }
+            if (!LAP_BUILD) {
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                const double v = xs[(3 + d) * L3_NLCP];
+                H[d * 3 + 0] = fma(v, dn0, H[d * 3 + 0]); H[d * 3 + 1] = fma(v, dn1, H[d * 3 + 1]); H[d * 3 + 2] = fma(v, dn2, H[d * 3 + 2]);
+              }
+            }
+          }
+          double Ji[9], Mi[9];
+          const double detJ = inv3(J, Ji);
+          const double wdet = TAB[192 + q] * detJ;
+          double cs, cw, lnJ = 0.0, c1 = 0.0, c2 = 0.0;
+          if (LAP_BUILD) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Mi[k] = Ji[k];
+            cs = 0.5 * wdet; cw = 0.5 * wdet;
+          } else {
+            double M[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) M[k] = J[k] + H[k];
+            const double detM = inv3(M, Mi);
+            lnJ = log(detM / detJ);
+            c1 = wdet * mu; c2 = wdet * lam;
+            const double c3 = c1 - c2 * lnJ;
+            cs = 0.5 * (c2 + c3); cw = 0.5 * (c2 - c3);
+          }
+          double2 *rq = REC + q * NARR * L3_NCOLP + col;
+          rq[12 * L3_NCOLP] = make_double2(cs, cw);
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            double g[2][3];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              const int a = 2 * pr + s;
+              const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) g[s][k] = fma(dn0, Mi[k], fma(dn1, Mi[3 + k], dn2 * Mi[6 + k]));
+            }
+            rq[(pr * 3 + 0) * L3_NCOLP] = make_double2(g[0][0], g[0][1]);
+            rq[(pr * 3 + 1) * L3_NCOLP] = make_double2(g[0][2], g[1][0]);
+            rq[(pr * 3 + 2) * L3_NCOLP] = make_double2(g[1][1], g[1][2]);
+          }
+          if (DO_R && !LAP_BUILD) {
+            // Kirchhoff stress times w detJ: tau = mu (b - I) + lam lnJ I, b - I = Hp + Hp^T + Hp Hp^T, Hp = H J^-1 = F - I
+            double Hp[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Hp[r * 3 + c] = fma(H[r * 3], Ji[c], fma(H[r * 3 + 1], Ji[3 + c], H[r * 3 + 2] * Ji[6 + c]));
+            const double cl = c2 * lnJ;
+            auto ee = [&](int r, int c) {
+              return (Hp[r * 3 + c] + Hp[c * 3 + r]) + fma(Hp[r * 3], Hp[c * 3], fma(Hp[r * 3 + 1], Hp[c * 3 + 1], Hp[r * 3 + 2] * Hp[c * 3 + 2]));
+            };
+            rq[13 * L3_NCOLP] = make_double2(fma(c1, ee(0, 0), cl), fma(c1, ee(1, 1), cl));
+            rq[14 * L3_NCOLP] = make_double2(fma(c1, ee(2, 2), cl), c1 * ee(0, 1));
+            rq[15 * L3_NCOLP] = make_double2(c1 * ee(0, 2), c1 * ee(1, 2));
+          }
+        }
+      }
+      // The fence is required, not decoration: without it the phase-B loads of some warps returned the previous
+      // interval's records although every STS above precedes this barrier in program order (found by comparing
+      // against the oracle on 3 x 2 x 3 nodes; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
+      __threadfence_block();
+      __syncthreads();
+      // ---------------- phase B: line pairs ----------------
+      if (on) {
+        if (ptype == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (colv[k] == L3_ZCOL) continue;
+            const double2 *base = REC + colv[k] + offA[k];
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+              const double2 *rq = base + q * NARR * L3_NCOLP;
+              const double2 a0 = rq[0], a1 = rq[L3_NCOLP], a2 = rq[2 * L3_NCOLP];
+              const double2 cc = rq[12 * L3_NCOLP - offA[k]];
+              const double glo[3] = {a0.x, a0.y, a1.x}, ghi[3] = {a1.y, a2.x, a2.y};
+              if (DO_K) {
+                const double plo[3] = {cc.x * glo[0], cc.x * glo[1], cc.x * glo[2]};
+                const double mlo[3] = {cc.y * glo[0], cc.y * glo[1], cc.y * glo[2]};
+                const double phi[3] = {cc.x * ghi[0], cc.x * ghi[1], cc.x * ghi[2]};
+                // (lo, lo) and (hi, hi): symmetric, K_ik = 2 cs g_i g_k
+                Kd[0] = fma(plo[0], glo[0], Kd[0]); Kd[1] = fma(plo[1], glo[1], Kd[1]); Kd[2] = fma(plo[2], glo[2], Kd[2]);
+                Kd[3] = fma(plo[0], glo[1], Kd[3]); Kd[4] = fma(plo[0], glo[2], Kd[4]); Kd[5] = fma(plo[1], glo[2], Kd[5]);
+                Kn[0] = fma(phi[0], ghi[0], Kn[0]); Kn[1] = fma(phi[1], ghi[1], Kn[1]); Kn[2] = fma(phi[2], ghi[2], Kn[2]);
+                Kn[3] = fma(phi[0], ghi[1], Kn[3]); Kn[4] = fma(phi[0], ghi[2], Kn[4]); Kn[5] = fma(phi[1], ghi[2], Kn[5]);
+                l3_acc(Ku, plo, mlo, ghi);
+              }
+              if (DO_R && !LAP_BUILD) {
+                const double2 t0 = rq[13 * L3_NCOLP - offA[k]], t1 = rq[14 * L3_NCOLP - offA[k]], t2 = rq[15 * L3_NCOLP - offA[k]];
+                // tau = {xx, yy | zz, xy | xz, yz}
+                fd[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], fd[0])));
+                fd[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], fd[1])));
+                fd[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], fd[2])));
+                fn[0] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], fn[0])));
+                fn[1] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], fn[1])));
+                fn[2] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], fn[2])));
+              }
+            }
+          }
+        } else {
+          auto pair_col = [&](const int col, const int oa, const int ob) {
+            const double2 *base = REC + col;
+#pragma unroll 1
+            for (int q = 0; q < 8; ++q) {
+              const double2 *rq = base + q * NARR * L3_NCOLP;
+              const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
+              const double2 b0 = rq[ob], b1 = rq[ob + L3_NCOLP], b2 = rq[ob + 2 * L3_NCOLP];
+              const double2 cc = rq[12 * L3_NCOLP];
+              const double blo[3] = {b0.x, b0.y, b1.x}, bhi[3] = {b1.y, b2.x, b2.y};
+              const double plo[3] = {cc.x * a0.x, cc.x * a0.y, cc.x * a1.x}, mlo[3] = {cc.y * a0.x, cc.y * a0.y, cc.y * a1.x};
+              const double phi[3] = {cc.x * a1.y, cc.x * a2.x, cc.x * a2.y}, mhi[3] = {cc.y * a1.y, cc.y * a2.x, cc.y * a2.y};
+              l3_acc(Kd, plo, mlo, blo); l3_acc(Ku, plo, mlo, bhi);
+              l3_acc(Kl, phi, mhi, blo); l3_acc(Kn, phi, mhi, bhi);
+            }
+          };
+          if (DO_K) {
+            pair_col(colv[0], offA[0], offB[0]);
+            if (two) pair_col(colv[1], offA[1], offB[1]);
+          }
+        }
+        // ---- interval i completes (A_i, B_i), (A_i, B_i+1), (A_i+1, B_i): store them, direct and transposed ----
+        if (store) {
+          if (ptype == 0) {
+            if (DO_K) {
+              double Fu[3][3];
+              l3_full(Ku, 0.0, Fu);
+              if (LAP_BUILD) {
+                double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
+                lq[0] = 2.0 * (Kd[0] + Kd[1] + Kd[2]); lq[L3_NPT] = Fu[0][0] + Fu[1][1] + Fu[2][2]; lq[2 * L3_NPT] = 0.0;
+              } else {
+                const double l0 = mu * lp0, l1 = mu * lp1;
+                Fu[0][0] += l1; Fu[1][1] += l1; Fu[2][2] += l1;
+                const double d00 = fma(2.0, Kd[0], l0), d11 = fma(2.0, Kd[1], l0), d22 = fma(2.0, Kd[2], l0);
+                const double d01 = 2.0 * Kd[3], d02 = 2.0 * Kd[4], d12 = 2.0 * Kd[5];
+                const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
+                l3_st6(ra.p, d00, d01, d02, Fu[0][0], Fu[0][1], Fu[0][2]);
+                l3_st6(ra.p + ra.stride, d01, d11, d12, Fu[1][0], Fu[1][1], Fu[1][2]);
+                l3_st6(ra.p + 2 * ra.stride, d02, d12, d22, Fu[2][0], Fu[2][1], Fu[2][2]);
+                const L3Row rn = l3_row(P.vals, lbA, nlA, rA, i + 1, nxm1, -1);
+                l3_st3(rn.p, Fu[0][0], Fu[1][0], Fu[2][0]);
+                l3_st3(rn.p + rn.stride, Fu[0][1], Fu[1][1], Fu[2][1]);
+                l3_st3(rn.p + 2 * rn.stride, Fu[0][2], Fu[1][2], Fu[2][2]);
+              }
+            }
+            if (DO_R && !LAP_BUILD) l3_st3(P.R + 3 * (nodeA0 + i), fd[0], fd[1], fd[2]);
+          } else if (DO_K) {
+            double Fd[3][3], Fu[3][3], Fl[3][3];
+            l3_full(Kd, mu * lp0, Fd); l3_full(Ku, mu * lp1, Fu); l3_full(Kl, mu * lp2, Fl);
+            if (LAP_BUILD) {
+              double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
+              lq[0] = Fd[0][0] + Fd[1][1] + Fd[2][2]; lq[L3_NPT] = Fu[0][0] + Fu[1][1] + Fu[2][2]; lq[2 * L3_NPT] = Fl[0][0] + Fl[1][1] + Fl[2][2];
+            } else {
+              if (wd) {
+                const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) l3_st6(ra.p + r * ra.stride, Fd[r][0], Fd[r][1], Fd[r][2], Fu[r][0], Fu[r][1], Fu[r][2]);
+                const L3Row rn = l3_row(P.vals, lbA, nlA, rA, i + 1, nxm1, -1);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) l3_st3(rn.p + r * rn.stride, Fl[r][0], Fl[r][1], Fl[r][2]);
+              }
+              if (wm) {
+                const L3Row rb = l3_row(P.vals, lbB, nlB, rB, i, nxm1, 0);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) l3_st6(rb.p + r * rb.stride, Fd[0][r], Fd[1][r], Fd[2][r], Fl[0][r], Fl[1][r], Fl[2][r]);
+                const L3Row rn = l3_row(P.vals, lbB, nlB, rB, i + 1, nxm1, -1);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) l3_st3(rn.p + r * rn.stride, Fu[0][r], Fu[1][r], Fu[2][r]);
+              }
+            }
+          }
+        }
+        // shift: node i+1 becomes node i
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { Kd[k] = Kn[k]; Kn[k] = 0.0; Ku[k] = 0.0; Kl[k] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { fd[k] = fn[k]; fn[k] = 0.0; }
+      }
+      l3_wait_all();
+      __threadfence_block();
+      __syncthreads();
+    }
+    // ---- the last node of the line: its diagonal-offset block has no further interval ----
+    if (on && i1 == nxm1) {
+      const int i = nxm1;
+      double lp0 = 0.0;
+      if (!LAP_BUILD && DO_K) lp0 = lapu[(int64_t)(i1 - i0) * 3 * L3_NPT];
+      if (ptype == 0) {
+        if (DO_K) {
+          if (LAP_BUILD) {
+            lapu[(int64_t)(i1 - i0) * 3 * L3_NPT] = 2.0 * (Kd[0] + Kd[1] + Kd[2]);
+          } else {
+            const double l0 = mu * lp0;
+            const double d00 = fma(2.0, Kd[0], l0), d11 = fma(2.0, Kd[1], l0), d22 = fma(2.0, Kd[2], l0);
+            const double d01 = 2.0 * Kd[3], d02 = 2.0 * Kd[4], d12 = 2.0 * Kd[5];
+            const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
+            l3_st3(ra.p, d00, d01, d02); l3_st3(ra.p + ra.stride, d01, d11, d12); l3_st3(ra.p + 2 * ra.stride, d02, d12, d22);
+          }
+        }
+        if (DO_R && !LAP_BUILD) l3_st3(P.R + 3 * (nodeA0 + i), fd[0], fd[1], fd[2]);
+      } else if (DO_K) {
+        double Fd[3][3];
+        l3_full(Kd, mu * lp0, Fd);
+        if (LAP_BUILD) {
+          lapu[(int64_t)(i1 - i0) * 3 * L3_NPT] = Fd[0][0] + Fd[1][1] + Fd[2][2];
+        } else {
+          if (wd) {
+            const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) l3_st3(ra.p + r * ra.stride, Fd[r][0], Fd[r][1], Fd[r][2]);
+          }
+          if (wm) {
+            const L3Row rb = l3_row(P.vals, lbB, nlB, rB, i, nxm1, 0);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) l3_st3(rb.p + r * rb.stride, Fd[0][r], Fd[1][r], Fd[2][r]);
+          }
+        }
+      }
+    }
+  }
+  // the last CTA to run out of units rearms the counters for the next launch
+  if (tid == 0) {
+    __threadfence();
+    const unsigned d = atomicAdd(P.counter + 1, 1u);
+    if (d == gridDim.x - 1) { P.counter[0] = 0u; P.counter[1] = 0u; __threadfence(); }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+void nls_lines3_free(nls_context *h) {
+  Lines3Plan &p = h->lplan;
+  if (p.d_pbase) cudaFree(p.d_pbase);
+  if (p.d_pown) cudaFree(p.d_pown);
+  if (p.d_info) cudaFree(p.d_info);
+  if (p.d_units) cudaFree(p.d_units);
+  if (p.d_lapoff) cudaFree(p.d_lapoff);
+  if (p.d_lap) cudaFree(p.d_lap);
+  if (p.d_counter) cudaFree(p.d_counter);
+  p = Lines3Plan();
+}
+
+static size_t lines3_smem(bool do_r) {
+  return (size_t)8 * (do_r ? 16 : 13) * L3_NCOLP * 16 + (size_t)3 * 6 * L3_NLCP * 8 + 200 * 8;
+}
+
+// Detects grid topology (x-fastest lines, planes with arbitrary base ids: full grids and slab-local meshes), builds the
+// per-line addressing tables, checks them against the CSR pattern entry by entry, and lists the work units. Leaves
+// p.ok false (and the atomic scatter in use) for any other mesh.
+int nls_lines3_build(nls_context *h) {
+  nls_lines3_free(h);
+  Lines3Plan &p = h->lplan;
+  if (h->dim != 3 || h->nen != 8 || h->nel == 0 || h->n_owned == 0) return NLS_OK;
+  if (lines3_smem(true) + 1024 > (size_t)h->max_optin_smem) return NLS_OK;
+  const int32_t *c = h->h_conn.data();
+  const int64_t nel = h->nel, nn = h->nn;
+  if (c[1] != c[0] + 1) return NLS_OK;
+  const int64_t nx = (int64_t)c[2] - c[0];
+  if (nx < 2 || nx > 1000000 || nel % (nx - 1)) return NLS_OK;
+  const int64_t epr = nx - 1, rows = nel / epr;
+  int64_t nyr = 1;
+  while (nyr < rows && c[nyr * epr * 8] == c[0] + nyr * nx && c[nyr * epr * 8 + 4] == c[4] + nyr * nx) ++nyr;
+  const int64_t ny = nyr + 1, epl = epr * nyr;
+  if (nel % epl) return NLS_OK;
+  const int64_t nlay = nel / epl, nzp = nlay + 1, plane = nx * ny;
+  if (nn != plane * nzp || nzp > 1000000 || ny > 1000000) return NLS_OK;
+  std::vector<int32_t> pbase((size_t)nzp);
+  for (int64_t k = 0; k < nlay; ++k) pbase[k] = c[k * epl * 8];
+  pbase[nlay] = c[(nlay - 1) * epl * 8 + 4];
+  for (int64_t k = 0; k < nzp; ++k) if (pbase[k] < 0 || (int64_t)pbase[k] + plane > nn) return NLS_OK;
+  {
+    std::vector<int32_t> s(pbase);
+    std::sort(s.begin(), s.end());
+    for (int64_t k = 1; k < nzp; ++k) if ((int64_t)s[k] - s[k - 1] < plane) return NLS_OK;
+  }
+  for (int64_t k = 0; k < nlay; ++k)
+    for (int64_t j = 0; j < nyr; ++j)
+      for (int64_t i = 0; i < epr; ++i) {
+        const int32_t *ce = c + ((k * nyr + j) * epr + i) * 8;
+        const int64_t n0 = pbase[k] + j * nx + i, n1 = pbase[k + 1] + j * nx + i;
+        if (ce[0] != n0 || ce[1] != n0 + 1 || ce[2] != n0 + nx || ce[3] != n0 + nx + 1 ||
+            ce[4] != n1 || ce[5] != n1 + 1 || ce[6] != n1 + nx || ce[7] != n1 + nx + 1) return NLS_OK;
+      }
+  std::vector<uint8_t> pown((size_t)nzp);
+  for (int64_t k = 0; k < nzp; ++k) {
+    pown[k] = pbase[k] < h->n_owned;
+    if (pown[k] && (int64_t)pbase[k] + plane > h->n_owned) return NLS_OK;
+  }
+  // per-line tables, verified against the pattern
+  std::vector<L3Line> info((size_t)(nzp * ny));
+  const int64_t *bp = h->h_browptr.data();
+  const int32_t *bc = h->h_bcol.data();
+  for (int64_t z = 0; z < nzp; ++z)
+    for (int64_t y = 0; y < ny; ++y) {
+      L3Line &li = info[z * ny + y];
+      std::memset(&li, 0, sizeof(li));
+      for (int k = 0; k < 9; ++k) li.rank[k] = -1;
+      if (!pown[z]) continue;
+      std::pair<int64_t, int> nb[9];
+      int nl = 0;
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int64_t z2 = z + dz, y2 = y + dy;
+          if (z2 < 0 || z2 >= nzp || y2 < 0 || y2 >= ny) continue;
+          nb[nl++] = {(int64_t)pbase[z2] + y2 * nx, (dz + 1) * 3 + (dy + 1)};
+        }
+      std::sort(nb, nb + nl);
+      for (int k = 0; k < nl; ++k) li.rank[nb[k].second] = (int8_t)k;
+      li.nl = nl;
+      const int64_t first = (int64_t)pbase[z] + y * nx;
+      li.lb = bp[first];
+      for (int64_t i = 0; i < nx; ++i) {
+        const int64_t a = first + i;
+        const int w = (i == 0 || i == nx - 1) ? 2 : 3;
+        const int64_t b0 = li.lb + (int64_t)nl * (i == 0 ? 0 : 3 * i - 1);
+        if (bp[a] != b0 || bp[a + 1] - bp[a] != (int64_t)nl * w) return NLS_OK;
+        for (int k = 0; k < nl; ++k)
+          for (int dx = (i == 0 ? 0 : -1); dx <= (i == nx - 1 ? 0 : 1); ++dx)
+            if (bc[b0 + k * w + dx + (i == 0 ? 0 : 1)] != nb[k].first + i + dx) return NLS_OK;
+      }
+    }
+  // work units: tiles of lines x chunks of x-intervals, largest first
+  const int64_t nxi = nx - 1;
+  std::vector<std::pair<int64_t, int4>> units;
+  int64_t ntiles = 0;
+  for (int64_t z0 = 0; z0 < nzp; z0 += L3_TZ)
+    for (int64_t y0 = 0; y0 < ny; y0 += L3_TY) {
+      bool work = false;
+      for (int64_t z = z0; z < std::min<int64_t>(z0 + L3_TZ, nzp); ++z) work = work || pown[z] || (z + 1 < nzp && pown[z + 1]);
+      if (work) ++ntiles;
+    }
+  if (ntiles == 0) return NLS_OK;
+  int64_t nch = std::max<int64_t>(1, (8 * (int64_t)h->sm_count + ntiles - 1) / ntiles);
+  int64_t clen = std::max<int64_t>(std::min<int64_t>(24, nxi), (nxi + nch - 1) / nch);
+  nch = (nxi + clen - 1) / clen;
+  for (int64_t z0 = 0; z0 < nzp; z0 += L3_TZ)
+    for (int64_t y0 = 0; y0 < ny; y0 += L3_TY) {
+      int64_t nlines = 0;
+      for (int64_t z = z0; z < std::min<int64_t>(z0 + L3_TZ, nzp); ++z)
+        if (pown[z] || (z + 1 < nzp && pown[z + 1])) nlines += std::min<int64_t>(L3_TY, ny - y0);
+      if (nlines == 0) continue;
+      for (int64_t ch = 0; ch < nch; ++ch) {
+        const int64_t i0 = ch * clen, i1 = std::min(nxi, i0 + clen);
+        units.push_back({nlines * (i1 - i0 + (i0 > 0 ? 1 : 0)), make_int4((int)y0, (int)z0, (int)i0, (int)i1)});
+      }
+    }
+  std::stable_sort(units.begin(), units.end(), [](const std::pair<int64_t, int4> &a, const std::pair<int64_t, int4> &b) { return a.first > b.first; });
+  std::vector<int4> uv(units.size());
+  std::vector<int64_t> lapoff(units.size());
+  int64_t lapn = 0;
+  for (size_t k = 0; k < units.size(); ++k) {
+    uv[k] = units[k].second;
+    lapoff[k] = lapn;
+    lapn += (int64_t)(uv[k].w - uv[k].z + 1) * 3 * L3_NPT;
+  }
+  p.nx = (int)nx; p.ny = (int)ny; p.nzp = (int)nzp; p.nunits = (int)uv.size(); p.lap_doubles = lapn;
+#define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&p.field, sizeof(vec[0]) * vec.size())); \
+  NLS_CUDA(h, cudaMemcpyAsync(p.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
+  UP(d_pbase, pbase); UP(d_pown, pown); UP(d_info, info); UP(d_units, uv); UP(d_lapoff, lapoff);
+#undef UP
+  NLS_CUDA(h, cudaMalloc((void **)&p.d_counter, 2 * sizeof(unsigned)));
+  NLS_CUDA(h, cudaMemsetAsync(p.d_counter, 0, 2 * sizeof(unsigned), h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  p.ok = true;
+  return NLS_OK;
+}
+
+template <bool R, bool K, bool LB>
+static void lines3_launch(nls_context *h, const L3Args &a, unsigned grid, size_t shm) {
+  k_asm_q1_3d_lines<R, K, LB><<<grid, L3_THREADS, shm, h->stream>>>(a, h->tabq, h->mat);
+}
+
+int nls_launch_lines3(nls_context *h, bool want_r, bool want_k) {
+  Lines3Plan &p = h->lplan;
+  if (!p.ok) NLS_FAIL(h, NLS_ERR_STATE, "lines assembly: no plan");
+  if (!h->attr_lines3) {       // the kernel also holds a few bytes of static shared memory: ask for what it needs, not the opt-in maximum
+    const int need = (int)lines3_smem(true);
+    cudaError_t e1 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e2 = cudaFuncSetAttribute(k_asm_q1_3d_lines<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e3 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e4 = cudaFuncSetAttribute(k_asm_q1_3d_lines<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+      cudaGetLastError();
+      NLS_FAIL(h, NLS_ERR_CUDA, "lines assembly: cannot raise the dynamic shared-memory limit");
+    }
+    h->attr_lines3 = true;
+  }
+  L3Args a{};
+  a.nx = p.nx; a.ny = p.ny; a.nzp = p.nzp; a.nunits = p.nunits;
+  a.pbase = p.d_pbase; a.pown = p.d_pown; a.info = reinterpret_cast<const L3Line *>(p.d_info);
+  a.units = reinterpret_cast<const int4 *>(p.d_units); a.lapoff = p.d_lapoff; a.lap = p.d_lap;
+  a.coords = h->d_coords; a.U = h->d_U; a.R = h->d_R; a.vals = h->d_vals; a.counter = p.d_counter;
+  const unsigned grid = (unsigned)std::min<int64_t>(p.nunits, h->sm_count);
+  if (want_k && !p.lap_valid) {     // once per mesh: the reference-configuration Laplacian of every block this scheme stores
+    if (!p.d_lap) {
+      if (cudaMalloc((void **)&p.d_lap, sizeof(double) * (size_t)p.lap_doubles) != cudaSuccess) {
+        cudaGetLastError(); p.d_lap = nullptr; p.ok = false;
+        NLS_FAIL(h, NLS_ERR_CUDA, "lines assembly: no memory for the Laplacian table");
+      }
+      a.lap = p.d_lap;
+    }
+    lines3_launch<false, true, true>(h, a, grid, lines3_smem(false));
+    h->launches++;
+    p.lap_valid = true;
+  }
+  if (want_r && want_k) lines3_launch<true, true, false>(h, a, grid, lines3_smem(true));
+  else if (want_k)      lines3_launch<false, true, false>(h, a, grid, lines3_smem(false));
+  else                  lines3_launch<true, false, false>(h, a, grid, lines3_smem(true));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = std::string("lines kernel launch: ") + cudaGetErrorString(e); return NLS_ERR_CUDA; }
+  h->launches++;
+  return NLS_OK;
+}

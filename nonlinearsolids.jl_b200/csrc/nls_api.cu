@@ -47,6 +47,7 @@ static void free_pattern(nls_context *h) {
   dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
   nls_gather_free(h);
   nls_twophase_free(h);
+  nls_lines3_free(h);
   dev_free(&h->d_mass); h->have_mass = false;
   dev_free(&h->d_dpos); dev_free(&h->d_symptr); dev_free(&h->d_lowslot); dev_free(&h->d_symvals);
   h->have_sym_index = false; h->sym_active = false; h->nsym = 0;
@@ -382,6 +383,7 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
     NLS_TRY(nls_gather_build(h, plan));
   }
   NLS_TRY(nls_twophase_build(h));
+  NLS_TRY(nls_lines3_build(h));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_pattern = true;
   return NLS_OK;
@@ -800,6 +802,21 @@ extern "C" int32_t nls_dev_download_vals(nls_handle h, double *vals) {
   NLS_ENTER(h);
   if (!h->have_pattern || !vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_download_vals: no pattern or null vals");
   NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_dev_download_rows(nls_handle h, int64_t row0, int64_t row1, double *R, int64_t *rowptr, int32_t *colind, double *vals) {
+  NLS_ENTER(h);
+  if (!h->have_pattern) NLS_FAIL(h, NLS_ERR_STATE, "nls_dev_download_rows: call nls_build_pattern first");
+  if (row0 < 0 || row1 < row0 || row1 > h->nrows) NLS_FAIL(h, NLS_ERR_ARG, "nls_dev_download_rows: row range outside the owned rows");
+  std::vector<int64_t> rp((size_t)(row1 - row0 + 1));
+  NLS_CUDA(h, cudaMemcpyAsync(rp.data(), h->d_rowptr + row0, sizeof(int64_t) * rp.size(), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int64_t e0 = rp.front(), e1 = rp.back();
+  if (rowptr) std::copy(rp.begin(), rp.end(), rowptr);
+  if (R && row1 > row0) NLS_CUDA(h, cudaMemcpyAsync(R, h->d_R + row0, sizeof(double) * (row1 - row0), cudaMemcpyDeviceToHost, h->stream));
+  if (colind && e1 > e0) NLS_CUDA(h, cudaMemcpyAsync(colind, h->d_colind + e0, sizeof(int32_t) * (e1 - e0), cudaMemcpyDeviceToHost, h->stream));
+  if (vals && e1 > e0) NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals + e0, sizeof(double) * (e1 - e0), cudaMemcpyDeviceToHost, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   return NLS_OK;
 }

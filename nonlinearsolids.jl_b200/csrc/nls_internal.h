@@ -84,6 +84,21 @@ struct TwoPhasePlan {
   std::vector<TwoPhaseChunk> chunks;
 };
 
+// plan of the pair-owner assembly of 3-D meshes with grid topology (kernels_lines3d.cu)
+struct Lines3Plan {
+  bool ok = false;                 // the mesh has grid topology and the closed-form row addresses match the pattern
+  bool lap_valid = false;          // the Laplacian table holds the current mesh
+  int nx = 0, ny = 0, nzp = 0, nunits = 0;
+  int64_t lap_doubles = 0;
+  int32_t *d_pbase = nullptr;
+  uint8_t *d_pown = nullptr;
+  void *d_info = nullptr;          // L3Line [nzp * ny]
+  void *d_units = nullptr;         // int4 [nunits]
+  int64_t *d_lapoff = nullptr;
+  double *d_lap = nullptr;
+  unsigned *d_counter = nullptr;
+};
+
 // ---- device control block of the PCG loop (lives in device memory) ----
 struct PcgCtl {
   double rz, rz_new, pAp, rr, bb;   // reductions (global, after allreduce if distributed)
@@ -198,6 +213,7 @@ struct nls_context {
   bool have_plan = false;
   GatherPlanDev gplan;
   TwoPhasePlan tplan;
+  Lines3Plan lplan;
   std::vector<double> h_coords;
 
   // vectors (ndof_local unless noted)
@@ -229,7 +245,7 @@ struct nls_context {
 
   // per-handle (= per-device) record of the dynamic shared-memory limits already raised with cudaFuncSetAttribute
   // (always raised to the device's opt-in maximum, so handles sharing a device cannot lower each other's limit)
-  bool attr_asm3d = false, attr_tp3d = false, attr_gather = false, attr_rows[2][2][2] = {};   // rows: [dim-2][DO_R][DO_K]
+  bool attr_asm3d = false, attr_tp3d = false, attr_gather = false, attr_lines3 = false, attr_rows[2][2][2] = {};   // rows: [dim-2][DO_R][DO_K]
   int max_optin_smem = 227 * 1024;
 
   // L2 flush scratch
@@ -242,8 +258,8 @@ struct nls_context {
   int opt_profile_phases = 0; // debug: per-phase cycle counters of the gather kernel
   uint64_t *d_prof = nullptr;
   int opt_gather_ctas = 0; // persistent CTAs per SM of the gather kernel (0 = default)
-  int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: best row-owner scheme available (2-D: shared-memory
-                          // gather, 3-D: element records + row owners); 2: element records + row owners everywhere
+  int opt_assembly = 1;   // 0: atomic scatter everywhere; 1: best atomic-free scheme available (2-D: shared-memory
+                          // gather, 3-D: line pairs on grid-topology meshes, else the atomic scatter); 2: element records + row owners
   int opt_twophase_3d = 0; // 1: the 3-D default becomes element records + row owners instead of the atomic scatter
   int opt_scratch_mb = 0; // byte budget of the element-record scratch in MiB (0 = default 8192)
 
@@ -269,12 +285,15 @@ struct nls_context {
 
 // ---- kernel launchers (kernels_assembly.cu / kernels_krylov.cu) ----
 int nls_launch_assembly(nls_context *h, bool want_r, bool want_k);
-enum { NLS_ASM_ATOMIC = 0, NLS_ASM_GATHER = 1, NLS_ASM_TWOPHASE = 2 };
+enum { NLS_ASM_ATOMIC = 0, NLS_ASM_GATHER = 1, NLS_ASM_TWOPHASE = 2, NLS_ASM_LINES = 3 };
 int nls_assembly_mode(nls_context *h);          // which scheme the next assembly uses (allocates the record scratch if needed)
 bool nls_assembly_overwrites(nls_context *h);   // true when the scheme writes every row itself (no zero-fill)
 int nls_twophase_build(nls_context *h);
 void nls_twophase_free(nls_context *h);
 int nls_launch_twophase(nls_context *h, bool want_r, bool want_k);
+int nls_lines3_build(nls_context *h);
+void nls_lines3_free(nls_context *h);
+int nls_launch_lines3(nls_context *h, bool want_r, bool want_k);
 int nls_gather_nc(void);
 int nls_gather_build(nls_context *h, const AsmPlan &plan);
 void nls_gather_free(nls_context *h);

@@ -348,6 +348,8 @@ static double orc_inv(int dim, const double *M, double *Mi) { /* row-major dim x
 }
 
 /* ue: [nen][dim]; fe: [nen*dim]; Ke: [nen*dim][nen*dim] row-major */
+static int orc_absmode = 0;   /* set only by orc_assemble_abs (test metric; one caller at a time): sums |contributions| */
+
 static void orc_element_q1(const orc_model *mo, const orc_tabq1 *t, int64_t e, const double *ue,
                            double *fe, double *Ke) {
   int dim = t->dim, nen = t->nen, nd = nen * dim;
@@ -386,7 +388,7 @@ static void orc_element_q1(const orc_model *mo, const orc_tabq1 *t, int64_t e, c
         for (int i = 0; i < dim; ++i) {
           double s = 0.0;
           for (int Jc = 0; Jc < dim; ++Jc) s += P[i * dim + Jc] * G[a][Jc];
-          fe[a * dim + i] += s * wd;
+          fe[a * dim + i] += orc_absmode ? fabs(s * wd) : s * wd;
         }
     }
     if (Ke) {
@@ -411,7 +413,7 @@ static void orc_element_q1(const orc_model *mo, const orc_tabq1 *t, int64_t e, c
             for (int k = 0; k < dim; ++k) {
               double s = 0.0;
               for (int L = 0; L < dim; ++L) s += T[k][L] * G[b][L];
-              row[b * dim + k] += s * wd;
+              row[b * dim + k] += orc_absmode ? fabs(s * wd) : s * wd;
             }
         }
     }
@@ -543,12 +545,13 @@ void orc_mass_nodes(const orc_model *mo, double rho, double area, double *Mn) {
   }
 }
 
-typedef struct { orc_model *mo; double *U, *R; const orc_sink *K; const orc_tab1d *t1; const orc_tabq1 *tq; int nth; } orc_asm_ctx;
+typedef struct { orc_model *mo; double *U, *R; const orc_sink *K; const orc_tab1d *t1; const orc_tabq1 *tq; int nth; int absmode; } orc_asm_ctx;
 
 static void orc_assemble_range(void *vc, int64_t lo, int64_t hi, int tid) {
   orc_asm_ctx *c_ = (orc_asm_ctx *)vc; (void)tid;
   orc_model *mo = c_->mo; double *U = c_->U, *R = c_->R; const orc_sink *K = c_->K;
   int dim = mo->dim, nen = mo->nen, nd = nen * dim, nth = c_->nth;
+  const int ab = c_->absmode;                      /* test metric: sum of |element contributions| per entry */
   for (int64_t e = lo; e < hi; ++e) {              /* defaults.jl:38 / :77 */
     double ue[24], fe[24], Ke[24 * 24];
     const int32_t *c = mo->conn + e * nen;
@@ -564,12 +567,13 @@ static void orc_assemble_range(void *vc, int64_t lo, int64_t hi, int tid) {
       for (int a = 0; a < nen; ++a)                /* unrestrict!, element.jl:67 */
         for (int d = 0; d < dim; ++d) {
           double *p = R + (int64_t)c[a] * dim + d;
-          if (nth > 1) orc_atomic_add(p, fe[a * dim + d]); else *p += fe[a * dim + d];
+          const double v = ab ? fabs(fe[a * dim + d]) : fe[a * dim + d];
+          if (nth > 1) orc_atomic_add(p, v); else *p += v;
         }
     if (K)
       for (int i = 0; i < nd; ++i)                 /* assemble!, element.jl:70 */
         for (int j = 0; j < nd; ++j)
-          orc_sink_add(K, (int64_t)c[i / dim] * dim + i % dim, (int64_t)c[j / dim] * dim + j % dim, Ke[i * nd + j]);
+          orc_sink_add(K, (int64_t)c[i / dim] * dim + i % dim, (int64_t)c[j / dim] * dim + j % dim, ab ? fabs(Ke[i * nd + j]) : Ke[i * nd + j]);
   }
 }
 
@@ -581,9 +585,9 @@ static void orc_assemble(orc_model *mo, double *U, double *R, const orc_sink *K)
   if (R) memset(R, 0, sizeof(double) * ndof);     /* residual.jl:14 */
   orc_tab1d t1; orc_tabq1 tq;
   if (dim == 1) orc_tab1d_init(mo, &t1); else orc_tabq1_init(mo, &tq);
-  orc_asm_ctx ctx = { mo, U, R, K, &t1, &tq, nth };
+  orc_asm_ctx ctx = { mo, U, R, K, &t1, &tq, nth, orc_absmode };
   orc_parallel_for(nth, mo->nel, orc_assemble_range, &ctx);
-  if (R) {                                         /* residual.jl:15,24-25 */
+  if (R && !orc_absmode) {                         /* residual.jl:15,24-25 */
     double *Fext = (double *)calloc((size_t)ndof, sizeof(double));
     if (mo->has_body) orc_body_force(mo, Fext);     /* residual.jl:19-23 */
     for (int64_t k = 0; k < mo->nneu; ++k) Fext[mo->neu_dofs[k]] += mo->neu_vals[k];
@@ -606,6 +610,21 @@ void orc_jacobian_csr(orc_model *mo, double *U, const int64_t *rowptr, const int
   memset(vals, 0, sizeof(double) * rowptr[n]);
   orc_sink s = { NULL, n, rowptr, colind, vals, mo->nthreads > 1 };
   orc_assemble(mo, U, NULL, &s);
+}
+
+/* Test metric, not a reference function: per entry of R and of the CSR Jacobian the sum of the ABSOLUTE contributions
+   (Q1: per quadrature point and element; 1-D: per element) -- the scale an entry-wise relative error is judged against (entries that cancel to ~0 are made of
+   contributions of this size). Not for stateful materials (the element pass runs twice). */
+void orc_assemble_abs(orc_model *mo, double *U, double *Rabs, const int64_t *rowptr, const int32_t *colind, double *vabs) {
+  int64_t n = orc_ndof(mo);
+  orc_absmode = 1;
+  if (Rabs) orc_assemble(mo, U, Rabs, NULL);
+  if (vabs) {
+    memset(vabs, 0, sizeof(double) * rowptr[n]);
+    orc_sink s = { NULL, n, rowptr, colind, vabs, mo->nthreads > 1 };
+    orc_assemble(mo, U, NULL, &s);
+  }
+  orc_absmode = 0;
 }
 
 /* ------------------------------------------------------------------ */

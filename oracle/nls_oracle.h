@@ -114,6 +114,7 @@ void orc_commit_state(orc_model *m, const double *U);    /* save_state! */
 void orc_residual(orc_model *m, double *U, double *R);   /* U is mutated (Dirichlet overwrite) */
 void orc_jacobian_dense(orc_model *m, double *U, double *K /*[ndof][ndof] row-major*/);
 void orc_jacobian_csr(orc_model *m, double *U, const int64_t *rowptr, const int32_t *colind, double *vals);
+void orc_assemble_abs(orc_model *m, double *U, double *Rabs, const int64_t *rowptr, const int32_t *colind, double *vabs); /* test metric: sum |element contributions| */
 void orc_element(const orc_model *m, int64_t e, const double *ue, double *fe, double *Ke); /* one element, no state update */
 
 /* ---- linear algebra ---- */

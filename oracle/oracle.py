@@ -210,6 +210,17 @@ class OracleModel:
                                colind.ctypes.data_as(_ip), _d(vals))
         return vals
 
+    def contribution_scale(self, U):
+        """(Rabs, Kabs): per entry of R and of the CSR Jacobian the sum of the absolute element contributions --
+        the denominator of the entry-wise relative error (tests/helpers.entry_err). A test metric, not a
+        reference function."""
+        U = np.array(U, dtype=np.float64)
+        rowptr, colind = self.pattern()
+        Rabs, vabs = np.zeros(self.ndof), np.zeros(len(colind))
+        lib().orc_assemble_abs(C.byref(self.m), _d(U), _d(Rabs), rowptr.ctypes.data_as(_lp),
+                               colind.ctypes.data_as(_ip), _d(vabs))
+        return Rabs, vabs
+
     def element(self, e, ue):
         ue = np.ascontiguousarray(ue, dtype=np.float64).ravel()
         nd = self.nen * self.dim

@@ -12,6 +12,13 @@ def rel_err(a, b):
     return np.abs(a - b).max() / (s if s > 0 else 1.0)
 
 
+def entry_err(a, b, scale):
+    """Entry-wise relative error: every entry judged against the sum of the absolute element contributions it is made
+    of (oracle.contribution_scale) -- the north star's 'entries within 1e-12 relative', robust to entries that cancel."""
+    s = np.where(scale > 0, scale, 1.0)
+    return float((np.abs(a - b) / s).max()) if len(a) else 0.0
+
+
 def node_dofs(nodes, dim, comps=None):
     comps = range(dim) if comps is None else comps
     return (np.asarray(nodes)[:, None] * dim + np.asarray(list(comps))[None, :]).ravel()
