@@ -145,6 +145,11 @@ int32_t nls_residual(nls_handle h, double *U, double *R);
 int32_t nls_jacobian(nls_handle h, double *U, double *vals);
 /* both in one element pass (same results as residual-then-jacobian, newton_fem.jl:137-138) */
 int32_t nls_residual_jacobian(nls_handle h, double *U, double *R, double *vals);
+/* The material-level dispatch point alone -- compute_internalforce / compute_dinternalforce(material, fem, U, ...;
+   mode = :set), src/materials/defaults.jl:29-46, 68-82: F_int(U) and dF_int/dU with U left untouched (no Dirichlet
+   overwrite) and no external force subtracted. What a Residual / Jacobian functor of the reference calls underneath. */
+int32_t nls_internal_force(nls_handle h, const double *U, double *Fint);
+int32_t nls_internal_force_jacobian(nls_handle h, const double *U, double *vals);
 
 /* ---- Krylov pieces, host buffers (test hooks; replace dofs(K) \ dofs(-R), newton_fem.jl:158) */
 int32_t nls_set_values(nls_handle h, const double *vals);           /* load CSR values */
@@ -212,6 +217,7 @@ int32_t nls_assembly_scheme(nls_handle h);
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
  * {staging, element phase, 0, block-task phase, clusters, cp.async wait, barrier, issue of the next stage}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);
+int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24); /* + per-warp phase cycles of the 3-D line kernel */
 /* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 the default row-owner scheme
  * (2-D: shared-memory gather; 3-D: atomic scatter unless "twophase_3d" = 1), 2 element records + row owners;
  * "scratch_mb" -> byte budget of the element-record scratch; "gather_ctas" -> persistent CTAs per SM;

@@ -10,7 +10,8 @@ from .arclength import ArcLength, ArcLengthResult, newtonarclength
 from ._lib import Handle, NLSError, lib
 from .fem import (Dirichlet, Element, ElementBoundary, FEMModel, Lagrange, Mesh, N, Neumann, Quadrature,
                   TimeDependent, dN, gauss_quadrature, getstate, integrate, interpolate, lagrange)
-from .gallery import CSRMatrix, DistributedForce, Jacobian, Residual, applymass, assemblemass, residual_jacobian
+from .gallery import (CSRMatrix, DistributedForce, Jacobian, Residual, applymass, assemblemass, compute_dinternalforce,
+                      compute_internalforce, residual_jacobian)
 from .materials import (ExponentialMaterial, LinearElasticity1D, LinearElastoPlasticity1D, NeoHookean,
                         initialize_state, save_state)
 from .meshes import bar_mesh, face_nodes, grid_mesh, slab_local_mesh, slab_planes, smooth_field

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "nls_residual": (C.c_int32, [_H, _dp, _dp]),
     "nls_jacobian": (C.c_int32, [_H, _dp, _dp]),
     "nls_residual_jacobian": (C.c_int32, [_H, _dp, _dp, _dp]),
+    "nls_internal_force": (C.c_int32, [_H, _dp, _dp]),
+    "nls_internal_force_jacobian": (C.c_int32, [_H, _dp, _dp]),
     "nls_set_values": (C.c_int32, [_H, _dp]),
     "nls_spmv": (C.c_int32, [_H, _dp, _dp]),
     "nls_dot": (C.c_int32, [_H, C.c_int64, _dp, _dp, _dp]),
@@ -97,6 +99,7 @@ PROTOTYPES = {
     "nls_kernel_launches": (C.c_int64, [_H]),
     "nls_set_option": (C.c_int32, [_H, C.c_char_p, C.c_int32]),
     "nls_debug_counters": (C.c_int32, [_H, _lp]),
+    "nls_debug_counters_ext": (C.c_int32, [_H, _lp]),
     "nls_assembly_scheme": (C.c_int32, [_H]),
     "nls_partition": (C.c_int32, [C.c_int32, C.c_int64, _ip, C.c_int32, _lp, C.c_int32,
                                   _lp, _lp, _lp, _lp, _lp, _lp]),

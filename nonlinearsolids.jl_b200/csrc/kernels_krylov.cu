@@ -581,7 +581,7 @@ int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, dou
   NLS_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   *out = h->h_scal[0];
-  return NLS_OK;
+  return nls_p2p_failed(h);       // a timed-out peer exchange leaves stale ghosts / partial sums: never report NLS_OK over it
 }
 
 // sqrt(sum v_i^2) over owned rows, optionally skipping constrained DoFs -- norm(dofs(fem, R))
@@ -593,6 +593,7 @@ double nls_dev_masked_norm2(nls_context *h, const double *v, bool masked, int *r
   cudaError_t e = cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { h->err = std::string("norm: ") + cudaGetErrorString(e); *rc = NLS_ERR_CUDA; return 0.0; }
+  if ((*rc = nls_p2p_failed(h)) != NLS_OK) return 0.0;
   return sqrt(h->h_scal[0]);
 }
 
@@ -830,6 +831,7 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
     launched += todo;
     NLS_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, h->stream));
     NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const int rcp = nls_p2p_failed(h); if (rcp) return rcp; }
     if (h->h_ctl->done) break;
   }
   const PcgCtl &c = *h->h_ctl;
@@ -922,6 +924,7 @@ int nls_minres_solve(nls_context *h, double rtol, int maxits, int *its, double *
     if (beta == 0.0) { st = 0; break; }                  // exact Krylov subspace
   }
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  { const int rcp = nls_p2p_failed(h); if (rcp) return rcp; }
   if (its) *its = itn;
   if (relres) *relres = fabs(phibar) / beta1;
   if (status) *status = st;

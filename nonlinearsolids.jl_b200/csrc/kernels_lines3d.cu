@@ -58,6 +58,8 @@ struct L3Args {
   const double *coords, *U;
   double *R, *vals;
   unsigned *counter;                     // [2] next unit, CTAs done
+  int dbg_nostore;                       // experiments only: 1 = skip the global stores
+  unsigned long long *prof;              // optional cycle counters (nls_set_option "profile_phases"): phase A, phase B, intervals, unit setup
 };
 
 __device__ __forceinline__ void l3_cp8(void *smem_dst, const void *gmem_src) {
@@ -221,10 +223,11 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     __syncthreads();
 
     for (int i = ifirst; i < i1; ++i) {
+      const long long tp0 = P.prof ? clock64() : 0;
       load_plane(i + 2);
       l3_commit();
       double lp0 = 0.0, lp1 = 0.0, lp2 = 0.0;
-      const bool store = i >= i0;
+      const bool store = i >= i0 && !P.dbg_nostore;
       if (!LAP_BUILD && DO_K && on && store) {
         const double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
         lp0 = lq[0]; lp1 = lq[L3_NPT]; lp2 = lq[2 * L3_NPT];
@@ -310,10 +313,11 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         }
       }
       // The fence is required, not decoration: without it the phase-B loads of some warps returned the previous
-      // interval's records although every STS above precedes this barrier in program order (found by comparing
-      // against the oracle on 3 x 2 x 3 nodes; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
+      // interval's records although every STS above precedes this barrier in program order (found on a 3 x 2 x 3-node
+      // mesh by the parity tests; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
       __threadfence_block();
       __syncthreads();
+      const long long tp1 = P.prof ? clock64() : 0;
       // ---------------- phase B: line pairs ----------------
       if (on) {
         if (ptype == 0) {
@@ -428,9 +432,15 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
 #pragma unroll
         for (int k = 0; k < 3; ++k) { fd[k] = fn[k]; fn[k] = 0.0; }
       }
+      const long long tp2 = P.prof ? clock64() : 0;
       l3_wait_all();
       __threadfence_block();
       __syncthreads();
+      if (P.prof && lane == 0) {      // per warp: phase A (to the barrier), own phase-B work, wait for the slowest warp
+        const long long tp3 = clock64();
+        if (tid == 0) { atomicAdd(P.prof + 0, (unsigned long long)(tp1 - tp0)); atomicAdd(P.prof + 1, (unsigned long long)(tp3 - tp1)); atomicAdd(P.prof + 2, 1ull); }
+        atomicAdd(P.prof + 8 + warp, (unsigned long long)(tp2 - tp1));
+      }
     }
     // ---- the last node of the line: its diagonal-offset block has no further interval ----
     if (on && i1 == nxm1) {
@@ -641,6 +651,8 @@ int nls_launch_lines3(nls_context *h, bool want_r, bool want_k) {
   a.pbase = p.d_pbase; a.pown = p.d_pown; a.info = reinterpret_cast<const L3Line *>(p.d_info);
   a.units = reinterpret_cast<const int4 *>(p.d_units); a.lapoff = p.d_lapoff; a.lap = p.d_lap;
   a.coords = h->d_coords; a.U = h->d_U; a.R = h->d_R; a.vals = h->d_vals; a.counter = p.d_counter;
+  a.dbg_nostore = h->opt_profile_phases == 2;
+  a.prof = h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr;
   const unsigned grid = (unsigned)std::min<int64_t>(p.nunits, h->sm_count);
   if (want_k && !p.lap_valid) {     // once per mesh: the reference-configuration Laplacian of every block this scheme stores
     if (!p.d_lap) {

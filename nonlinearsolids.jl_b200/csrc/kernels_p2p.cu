@@ -30,10 +30,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long epoch, int *err) {
+// `err` lives in device memory and is sticky: once set, every later exchange returns at once instead of spinning its
+// full minute. `herr` is its host-visible twin in mapped pinned memory, which the solvers read wherever they already
+// synchronise with the stream -- no extra copy.
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long epoch, int *err, volatile int *herr) {
+  if (*reinterpret_cast<volatile int *>(err)) return false;
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < epoch) {
-    if (clock64() - t0 > P2P_SPIN_CYCLES) { atomicExch(err, 1); return false; }
+    if (clock64() - t0 > P2P_SPIN_CYCLES || *reinterpret_cast<volatile int *>(err)) {
+      atomicExch(err, 1); *herr = 1; __threadfence_system();
+      return false;
+    }
     __nanosleep(40);
   }
   return true;
@@ -51,7 +58,7 @@ struct P2PHaloArgs {
 // co-resident (grid <= 64), so waiting inside the kernel cannot starve the sending part of another block.
 __global__ void __launch_bounds__(256)
 k_p2p_halo(const P2PHaloArgs a, const int32_t *__restrict__ send_nodes, int64_t nrecv, const int32_t *__restrict__ recv_nodes,
-           const double *win, double *v, unsigned long long epoch, unsigned int *done, int *err) {
+           const double *win, double *v, unsigned long long epoch, unsigned int *done, int *err, volatile int *herr) {
   const int64_t n = a.send_ptr[a.nneigh] * a.dim;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t node_idx = t / a.dim;
@@ -70,7 +77,7 @@ k_p2p_halo(const P2PHaloArgs a, const int32_t *__restrict__ send_nodes, int64_t 
       for (int q = 0; q < a.nneigh; ++q) st_release_sys(a.dst_flag[q], epoch);
     }
     ok = 1;
-    for (int q = 0; q < a.nneigh; ++q) if (!spin_until(a.my_flag[q], epoch, err)) ok = 0;
+    for (int q = 0; q < a.nneigh; ++q) if (!spin_until(a.my_flag[q], epoch, err, herr)) ok = 0;
   }
   __syncthreads();
   if (!ok) return;
@@ -84,7 +91,7 @@ k_p2p_halo(const P2PHaloArgs a, const int32_t *__restrict__ send_nodes, int64_t 
 // one CTA; thread r talks to rank r
 __global__ void __launch_bounds__(64)
 k_p2p_allreduce(double *dptr, int count, int me, int nranks, double *const *peer_red, unsigned long long *const *peer_flag,
-                const double *my_red, const unsigned long long *my_flag, unsigned long long epoch, int *err) {
+                const double *my_red, const unsigned long long *my_flag, unsigned long long epoch, int *err, volatile int *herr) {
   __shared__ int ok;
   const int r = threadIdx.x;
   if (r == 0) ok = 1;
@@ -94,7 +101,7 @@ k_p2p_allreduce(double *dptr, int count, int me, int nranks, double *const *peer
     for (int c = 0; c < count; ++c) dst[c] = dptr[c];
     __threadfence_system();
     st_release_sys(peer_flag[r] + me, epoch);
-    if (!spin_until(my_flag + r, epoch, err)) ok = 0;
+    if (!spin_until(my_flag + r, epoch, err, herr)) ok = 0;
   }
   __syncthreads();
   if (r == 0 && ok) {
@@ -117,6 +124,7 @@ void nls_p2p_free(nls_context *h) {
   if (p.d_peer_rflag) cudaFree(p.d_peer_rflag);
   if (p.d_done) cudaFree(p.d_done);
   if (p.d_err) cudaFree(p.d_err);
+  if (p.h_err) cudaFreeHost((void *)p.h_err);
   p = P2PState();
 }
 
@@ -124,9 +132,18 @@ void nls_p2p_free(nls_context *h) {
 // path stays in use -- when IPC is unavailable on ANY rank or NLS_B200_P2P=0.
 int nls_p2p_setup(nls_context *h) {
   nls_p2p_free(h);
-  if (!h->distributed || !h->comm || h->nranks < 2 || h->nranks > 64 || h->nneigh > 8) return NLS_OK;
+  // nranks is the same on every rank, so this early return is taken by all of them or by none. Per-rank conditions
+  // (too many neighbours, a bad neighbour list) must NOT return here: the exchange below is collective, so such a rank
+  // publishes ok = 0 and all ranks fall back to NCCL together.
+  if (!h->distributed || !h->comm || h->nranks < 2 || h->nranks > 64) return NLS_OK;
   const char *env = std::getenv("NLS_B200_P2P");
-  const bool want = !(env && env[0] == '0');
+  bool neigh_ok = h->nneigh <= 8;
+  for (int q = 0; q < h->nneigh && neigh_ok; ++q) {
+    if (h->neigh[q] < 0 || h->neigh[q] >= h->nranks || h->neigh[q] == h->rank) neigh_ok = false;
+    for (int q2 = 0; q2 < q && neigh_ok; ++q2) if (h->neigh[q2] == h->neigh[q]) neigh_ok = false;
+  }
+  const bool bad_ranks = h->nneigh <= 8 && !neigh_ok;     // an argument error, reported after the collective part
+  const bool want = !(env && env[0] == '0') && neigh_ok;
   P2PState &p = h->p2p;
   NcclApi *nc = h->nccl;
   const int nr = h->nranks, me = h->rank, dim = h->dim;
@@ -141,6 +158,9 @@ int nls_p2p_setup(nls_context *h) {
   NLS_CUDA(h, cudaMemset(p.d_done, 0, sizeof(unsigned int)));
   NLS_CUDA(h, cudaMalloc((void **)&p.d_err, sizeof(int)));
   NLS_CUDA(h, cudaMemset(p.d_err, 0, sizeof(int)));
+  NLS_CUDA(h, cudaHostAlloc((void **)&p.h_err, sizeof(int), cudaHostAllocMapped));
+  *p.h_err = 0;
+  NLS_CUDA(h, cudaHostGetDevicePointer((void **)&p.d_herr, (void *)p.h_err, 0));
   // record: {ok, H, recv offset (doubles) for data from rank s or -1}[nr], win handle, flag handle
   const size_t rec_i64 = (size_t)2 + nr, rec_bytes = rec_i64 * 8 + 2 * sizeof(cudaIpcMemHandle_t);
   std::vector<unsigned char> mine(rec_bytes, 0), all(rec_bytes * nr, 0);
@@ -150,7 +170,7 @@ int nls_p2p_setup(nls_context *h) {
   cudaGetLastError();
   mi[0] = ok ? 1 : 0; mi[1] = H;
   for (int s = 0; s < nr; ++s) mi[2 + s] = -1;
-  for (int q = 0; q < h->nneigh; ++q) mi[2 + h->neigh[q]] = h->recv_ptr[q] * dim;
+  for (int q = 0; q < h->nneigh && neigh_ok; ++q) mi[2 + h->neigh[q]] = h->recv_ptr[q] * dim;
   std::memcpy(mine.data() + rec_i64 * 8, &hw, sizeof(hw));
   std::memcpy(mine.data() + rec_i64 * 8 + sizeof(hw), &hf, sizeof(hf));
   unsigned char *d_send = nullptr, *d_recv = nullptr;
@@ -191,6 +211,7 @@ int nls_p2p_setup(nls_context *h) {
     NLS_FAIL(h, NLS_ERR_NCCL, "ncclAllReduce (p2p agreement) failed");
   NLS_CUDA(h, cudaMemcpyAsync(&notok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (bad_ranks) { nls_p2p_free(h); NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: neighbour rank out of range, equal to this rank, or listed twice"); }
   if (notok != 0.0) { nls_p2p_free(h); return NLS_OK; }
   // per-neighbour destinations (both parities) and flags
   p.H = H;
@@ -239,7 +260,7 @@ int nls_p2p_halo_exchange(nls_context *h, double *v) {
   const int64_t ns = h->send_ptr[h->nneigh] * dim, nr = h->recv_ptr[h->nneigh] * dim;
   const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((std::max(ns, nr) + 255) / 256, 64));
   k_p2p_halo<<<g, 256, 0, h->halo_stream ? h->halo_stream : h->stream>>>(a, h->d_send_nodes, h->recv_ptr[h->nneigh], h->d_recv_nodes, p.win + (size_t)par * p.H, v,
-                                       epoch, p.d_done, p.d_err);
+                                       epoch, p.d_done, p.d_err, p.d_herr);
   P2P_KCHECK(h);
   return NLS_OK;
 }
@@ -250,16 +271,20 @@ int nls_p2p_allreduce(nls_context *h, double *dptr, int count) {
   const unsigned long long epoch = ++p.red_epoch;
   const int par = (int)(epoch & 1);
   k_p2p_allreduce<<<1, 64, 0, h->stream>>>(dptr, count, h->rank, h->nranks, p.d_peer_red[par], p.d_peer_rflag, p.my_red[par],
-                                           p.flags + h->nranks, epoch, p.d_err);
+                                           p.flags + h->nranks, epoch, p.d_err, p.d_herr);
   P2P_KCHECK(h);
+  return NLS_OK;
+}
+
+// After a stream synchronisation: did any exchange so far time out? Reads mapped pinned memory, no copy. Sticky.
+int nls_p2p_failed(nls_context *h) {
+  if (!h->p2p.on || !h->p2p.h_err) return NLS_OK;
+  if (*h->p2p.h_err) NLS_FAIL(h, NLS_ERR_NCCL, "peer-memory exchange timed out waiting for a neighbour's flag (results since then are invalid)");
   return NLS_OK;
 }
 
 int nls_p2p_check(nls_context *h) {
   if (!h->p2p.on) return NLS_OK;
-  int e = 0;
-  NLS_CUDA(h, cudaMemcpyAsync(&e, h->p2p.d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (e) NLS_FAIL(h, NLS_ERR_NCCL, "peer-memory exchange timed out waiting for a neighbour's flag");
-  return NLS_OK;
+  return nls_p2p_failed(h);
 }

@@ -420,7 +420,19 @@ static int check_ready(nls_context *h, const char *who) {
 }
 
 // (::Residual)(fem,U,R,ctx) and/or (::Jacobian)(fem,U,K,ctx) on the device-resident U
-static int assemble(nls_context *h, bool want_r, bool want_k) {
+// pure = compute_internalforce / compute_dinternalforce (defaults.jl:29-46, 68-82) alone: U is left as given (no Dirichlet
+// overwrite) and no external force is subtracted -- what the material-level dispatch point of the reference means
+static int assemble(nls_context *h, bool want_r, bool want_k, bool pure = false) {
+  if (pure) {
+    NLS_TRY(nls_halo_exchange(h, h->d_U));
+    if (!nls_assembly_overwrites(h)) {
+      if (want_r) NLS_CUDA(h, cudaMemsetAsync(h->d_R, 0, sizeof(double) * h->nrows, h->stream));
+      if (want_k) NLS_CUDA(h, cudaMemsetAsync(h->d_vals, 0, sizeof(double) * h->nnz, h->stream));
+    }
+    NLS_TRY(nls_launch_assembly(h, want_r, want_k));
+    if (want_k) h->vals_version++;
+    return NLS_OK;
+  }
   NLS_TRY(nls_launch_apply_dirichlet(h, h->d_U));              // residual.jl:13 / jacobian.jl:11
   // multi-GPU, 2-D row-owner kernel: the ghost exchange runs on a second stream while the clusters that touch no
   // ghost node are assembled; the few clusters at the slab faces follow once it has landed
@@ -491,6 +503,30 @@ extern "C" int32_t nls_residual_jacobian(nls_handle h, double *U, double *R, dou
   NLS_ENTER(h);
   if (!R || !vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_residual_jacobian: null output");
   return host_assemble(h, U, R, vals);
+}
+
+// compute_internalforce(material, fem, U, Fint, ctx; mode=:set) / compute_dinternalforce(...; mode=:set) -- the element
+// loops alone (defaults.jl:29-46, 68-82): U is NOT modified, no Dirichlet values are applied, no external force enters.
+// For stateful materials the internal-force pass updates the trial state like the reference (defaults.jl:40-42).
+extern "C" int32_t nls_internal_force(nls_handle h, const double *U, double *Fint) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_internal_force"));
+  if (!U || !Fint) NLS_FAIL(h, NLS_ERR_ARG, "nls_internal_force: null argument");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(assemble(h, true, false, true));
+  NLS_CUDA(h, cudaMemcpyAsync(Fint, h->d_R, sizeof(double) * h->nrows, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
+}
+extern "C" int32_t nls_internal_force_jacobian(nls_handle h, const double *U, double *vals) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_internal_force_jacobian"));
+  if (!U || !vals) NLS_FAIL(h, NLS_ERR_ARG, "nls_internal_force_jacobian: null argument");
+  NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
+  NLS_TRY(assemble(h, false, true, true));
+  NLS_CUDA(h, cudaMemcpyAsync(vals, h->d_vals, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NLS_OK;
 }
 
 // ---- Krylov hooks -----------------------------------------------------------------------
@@ -627,6 +663,7 @@ static int newton_loop(nls_context *h, const nls_newton_opts *o, double *hist, n
   if (!finished && its >= o->maxits) reason = NLS_REASON_DIVERGED_MAXITS;  // :184-187
   NLS_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  NLS_TRY(nls_p2p_failed(h));
   res->ms_total = elapsed(h->ev0, h->ev1);
   res->reason = reason; res->iterations = its; res->lin_its_total = lin_total; res->nhist = nh;
   res->norm_r = norm_r; res->norm_r0 = norm_r0;
@@ -903,6 +940,18 @@ extern "C" int32_t nls_debug_counters(nls_handle h, int64_t *out8) {
   return NLS_OK;
 }
 
+// the 3-D line kernel's per-warp phase-B cycles follow the 8 shared counters: 24 values in all
+extern "C" int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24) {
+  NLS_ENTER(h);
+  if (!out24) NLS_FAIL(h, NLS_ERR_ARG, "nls_debug_counters_ext: null output");
+  for (int i = 0; i < 24; ++i) out24[i] = 0;
+  if (h->d_prof) {
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    NLS_CUDA(h, cudaMemcpy(out24, h->d_prof, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  return NLS_OK;
+}
+
 extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) {
   NLS_ENTER(h);
   if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
@@ -921,8 +970,8 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   }
   if (!std::strcmp(key, "gather_ctas")) { h->opt_gather_ctas = value; return NLS_OK; }
   if (!std::strcmp(key, "profile_phases")) {
-    if (!h->d_prof) NLS_CUDA(h, cudaMalloc((void **)&h->d_prof, 8 * sizeof(uint64_t)));
-    NLS_CUDA(h, cudaMemset(h->d_prof, 0, 8 * sizeof(uint64_t)));
+    if (!h->d_prof) NLS_CUDA(h, cudaMalloc((void **)&h->d_prof, 24 * sizeof(uint64_t)));
+    NLS_CUDA(h, cudaMemset(h->d_prof, 0, 24 * sizeof(uint64_t)));
     h->opt_profile_phases = value;
     return NLS_OK;
   }
@@ -945,6 +994,7 @@ extern "C" int32_t nls_set_halo(nls_handle h, int64_t n_owned_nodes, int32_t nne
   h->send_ptr.assign(1, 0); h->recv_ptr.assign(1, 0);
   if (nneigh > 0) { h->send_ptr.assign(send_ptr, send_ptr + nneigh + 1); h->recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1); }
   const int64_t ns = h->send_ptr.back(), nr = h->recv_ptr.back();
+  if ((ns > 0 && !send_nodes) || (nr > 0 && !recv_nodes)) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: null node list with a positive count");
   for (int64_t k = 0; k < ns; ++k) if (send_nodes[k] < 0 || send_nodes[k] >= h->n_owned) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: send node is not an owned node");
   for (int64_t k = 0; k < nr; ++k) if (recv_nodes[k] < h->n_owned || recv_nodes[k] >= h->nn) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_halo: recv node is not a ghost node");
   NLS_TRY(dev_alloc(h, &h->d_send_nodes, (size_t)ns)); NLS_TRY(dev_alloc(h, &h->d_recv_nodes, (size_t)nr));

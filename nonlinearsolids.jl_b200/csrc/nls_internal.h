@@ -135,7 +135,9 @@ struct P2PState {
   const double *my_red[2] = {nullptr, nullptr};
   unsigned long long halo_epoch = 0, red_epoch = 0;
   unsigned int *d_done = nullptr;
-  int *d_err = nullptr;
+  int *d_err = nullptr;                        // device-side sticky error flag
+  volatile int *h_err = nullptr;               // its twin in mapped pinned memory (host pointer)
+  volatile int *d_herr = nullptr;              // ... and the device pointer to it
   std::vector<void *> opened;
 };
 
@@ -326,4 +328,5 @@ void nls_p2p_free(nls_context *h);
 int nls_p2p_halo_exchange(nls_context *h, double *v);
 int nls_p2p_allreduce(nls_context *h, double *dptr, int count);
 int nls_p2p_check(nls_context *h);
+int nls_p2p_failed(nls_context *h);   // after a stream synchronisation: NLS_ERR_NCCL if an exchange has timed out
 int nls_allreduce_sum(nls_context *h, double *dptr, int count);

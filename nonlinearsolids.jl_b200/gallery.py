@@ -40,6 +40,34 @@ class DistributedForce:
         return f
 
 
+def compute_internalforce(material, fem, U, Fint, ctx=None, mode="add"):
+    """compute_internalforce(material, fem, U, Fint, ctx; mode) (defaults.jl:29-46): the element loop alone. U is not
+    modified (no Dirichlet overwrite) and no external force enters; `mode` is "add" or "set", anything else raises
+    like the reference's ArgumentError (defaults.jl:30-32)."""
+    if mode not in ("add", "set"):
+        raise ValueError("Invalid mode: %s" % mode)
+    tmp = np.zeros(fem.nrows)
+    fem.handle(material).call("nls_internal_force", dptr(np.ascontiguousarray(U, dtype=np.float64)), dptr(tmp))
+    if mode == "set":
+        Fint[:] = tmp
+    else:
+        Fint += tmp
+    return Fint
+
+
+def compute_dinternalforce(material, fem, U, K, ctx=None, mode="add"):
+    """compute_dinternalforce(material, fem, U, K, ctx; mode) (defaults.jl:68-82) into the CSR values of K."""
+    if mode not in ("add", "set"):
+        raise ValueError("Invalid mode: %s" % mode)
+    tmp = np.zeros(len(K.vals))
+    fem.handle(material).call("nls_internal_force_jacobian", dptr(np.ascontiguousarray(U, dtype=np.float64)), dptr(tmp))
+    if mode == "set":
+        K.vals[:] = tmp
+    else:
+        K.vals += tmp
+    return K
+
+
 def _sync_external_forces(H, fem, forces, ctx):
     total = np.zeros(fem.mesh.dim)
     for f in forces:

@@ -117,12 +117,15 @@ end
 
 # ---- dispatch point (2): material-level global loops on a device model -------------------------
 """compute_internalforce(material, ::B200Model, U, Fint, ctx; mode): F_int via the element kernel.
-`mode=:add` adds to Fint like the reference (defaults.jl:29-46)."""
+`mode=:add` adds to Fint like the reference (defaults.jl:29-46). Pure internal force: `nls_internal_force` leaves U
+untouched and subtracts no external load, so the reference's own `Residual` functor (which applies the Dirichlet
+values and the external forces itself, residual.jl:12-26) can sit on top of it without counting them twice.
+NOTE: this shim has never been executed (no `julia` in the build image); it is derived from include/nls_b200.h."""
 function compute_internalforce(material, m::B200Model, U::Vector{Float64}, Fint::Vector{Float64}, ctx; mode=:add)
     mode in (:add, :set) || throw(ArgumentError("Invalid mode: $mode"))
     sync_material!(m, material)
     tmp = similar(Fint)
-    check(m.h, ccall((:nls_residual, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, U, tmp))
+    check(m.h, ccall((:nls_internal_force, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, U, tmp))
     mode == :set ? (Fint .= tmp) : (Fint .+= tmp)
 end
 
@@ -131,7 +134,7 @@ function compute_dinternalforce(material, m::B200Model, U::Vector{Float64}, vals
     mode in (:add, :set) || throw(ArgumentError("Invalid mode: $mode"))
     sync_material!(m, material)
     tmp = similar(vals)
-    check(m.h, ccall((:nls_jacobian, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, U, tmp))
+    check(m.h, ccall((:nls_internal_force_jacobian, libnls), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.h, U, tmp))
     mode == :set ? (vals .= tmp) : (vals .+= tmp)
 end
 

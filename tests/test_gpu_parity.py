@@ -405,3 +405,46 @@ def test_distributed_force(nls, orc):
         nls.Residual(mat2)(fem2, U.copy(), R0)                    # removing the force restores the plain residual
         om2.set_body_force(None)
         assert rel_err(R0, om2.residual(U)[1]) <= RTOL and np.abs(R0 - R).max() > 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_compute_internalforce_is_pure(nls, orc, dim):
+    """The material-level dispatch point (defaults.jl:29-46, 68-82): F_int and dF_int/dU alone -- U untouched, Dirichlet
+    values not applied, Neumann / body loads not subtracted, mode add/set, invalid mode raises."""
+    if dim == 1:
+        mat = nls.ExponentialMaterial(sigma_sat=1.0, b=2.0)
+        mesh = nls.bar_mesh(7, 2)
+        fem = nls.FEMModel(mesh, 3, 2, data={"A": 1.0})
+        om = orc.OracleModel(1, mesh.conn, mesh.coords, p=2, nq=3, mat_kind=mat.kind, mat=mat.params(), area=1.0)
+        U = 0.01 * np.arange(mesh.nn, dtype=np.float64) ** 1.5
+    else:
+        mat = nls.NeoHookean(E=1.0, nu=0.3)
+        mesh = nls.grid_mesh(5, dim)
+        mesh.coords[:] = distorted(mesh)
+        fem = nls.FEMModel(mesh)
+        om = orc.OracleModel(dim, mesh.conn, mesh.coords, mat_kind=orc.MAT_NEOHOOKEAN, mat=(mat.mu, mat.lam))
+        U = nls.smooth_field(mesh.coords, amp=0.03)
+    fem.addboundary(nls.Dirichlet([0, 1], [0.5, -0.25]))          # must NOT be applied by the pure loops
+    fem.addboundary(nls.Neumann([fem.ndof - 1], [3.0]))           # must NOT be subtracted
+    _, Ro = om.residual(U); Ko = om.jacobian_csr(U)                # the oracle model carries no boundary: pure F_int
+    U0 = U.copy()
+    F = np.full(fem.ndof, 2.0)
+    nls.compute_internalforce(mat, fem, U, F, mode="add")
+    assert np.array_equal(U, U0)
+    assert rel_err(F - 2.0, Ro) <= RTOL
+    nls.compute_internalforce(mat, fem, U, F, mode="set")
+    assert rel_err(F, Ro) <= RTOL
+    K = nls.CSRMatrix(fem)
+    K.vals[:] = 1.0
+    nls.compute_dinternalforce(mat, fem, U, K, mode="add")
+    assert np.array_equal(U, U0) and rel_err(K.vals - 1.0, Ko) <= RTOL
+    nls.compute_dinternalforce(mat, fem, U, K, mode="set")
+    assert rel_err(K.vals, Ko) <= RTOL
+    with pytest.raises(ValueError):
+        nls.compute_internalforce(mat, fem, U, F, mode="replace")
+    # the functors on top still apply the boundaries
+    R = np.zeros(fem.ndof)
+    U1 = U.copy()
+    nls.Residual(mat)(fem, U1, R)
+    assert U1[0] == 0.5 and U1[1] == -0.25
