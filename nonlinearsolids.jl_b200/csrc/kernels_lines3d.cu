@@ -1,28 +1,34 @@
-// kernels_lines3d.cu -- atomic-free ("pair-owner") assembly of the 3-D Q1 Neo-Hookean residual and CSR Jacobian on
-// meshes with grid topology (lexicographic hexahedral grids and their slab partitions, coordinates arbitrary).
+// kernels_lines3d.cu -- atomic-free, row-owner assembly of the 3-D Q1 Neo-Hookean residual and CSR Jacobian on meshes
+// with grid topology (lexicographic hexahedral grids and their slab partitions, coordinates arbitrary).
 //
 // Replaces, like kernels_assembly.cu:  compute_internalforce / compute_dinternalforce (src/materials/defaults.jl:29-46,
 // 68-82) with restrict! / unrestrict! / assemble! (src/fem/element.jl:64-70) folded in. The 24 x 24 element matrix is
 // never formed: every 3 x 3 CSR block K_AB = sum over the elements e that hold both nodes, over their 8 quadrature
 // points, of
 //     c2 g_A (x) g_B + c3 g_B (x) g_A   (+ mu * L_AB on the diagonal, L = reference-configuration Laplacian, built once per mesh)
-// is summed by ONE thread in a fixed order and stored once, together with its transpose K_BA (K is symmetric): no
-// atomics, no zero-fill of the CSR values, no element-matrix exchange, bit-reproducible run to run.
+// is summed by one thread in a fixed order, together with its transpose K_BA (K is symmetric): no atomics, no zero-fill
+// of the CSR values, no element-matrix exchange, bit-reproducible run to run.
 //
-// Work decomposition. Node lines run along x (the fastest node index). A CTA owns a tile of L3_TY x L3_TZ lines and
-// marches along x; per x-interval i (the elements between node planes i and i+1 of the (TY+1) x (TZ+1) element columns
-// that touch the tile):
+// Work decomposition. Node lines run along x (the fastest node index), so the CSR rows of one line are ONE contiguous
+// stream of doubles. A CTA owns the rows of a tile of L3_TY x L3_TZ lines and marches along x; per x-interval i (the
+// elements between node planes i and i+1 of the (TY+1) x (TZ+1) element columns that touch the tile), in two halves of
+// four quadrature points each (the records of eight do not fit beside the row staging):
 //   phase A  one thread per (element column, quadrature point): J, H = sum u (x) dN, M = J + H, M^-1, ln det F,
 //            g_a = M^-T dN_a (spatial gradients) and the scalars -> shared-memory records (SoA, 16-byte columns:
 //            every LDS.128 / STS.128 of a warp is conflict-free)
-//   phase B  one thread per (line, half-stencil offset): the line pair (L, L + d), d in {(0,0), (1,0), (-1,1), (0,1), (1,1)}
-//            in (y, z). It accumulates the four blocks between nodes {i, i+1} of L and {i, i+1} of L + d over the one or
-//            two (self: four) element columns that hold both lines -- symmetric and skew parts separately, 15 DFMA per
-//            block and point instead of 18 -- writes the blocks that interval i completes (rows of L and, transposed, rows
-//            of L + d) and carries the (i+1, i+1) block into the next interval. The self pair also sums f_int.
-// Every CSR block is written by exactly one thread of the grid; a tile only recomputes the quadrature-point records of the
-// element columns on its border (81 columns per 64 lines). Row addresses are closed-form per line (host tables,
-// verified against the CSR pattern when the plan is built); meshes without grid topology keep the atomic scatter.
+//   phase B  one thread per line pair (L, L + d), d in {(0,0), (1,0), (-1,1), (0,1), (1,1)} in (y, z), with at least one
+//            line in the tile (pairs across the tile border are evaluated by both tiles: 366 pair threads per 64 lines).
+//            It accumulates the four blocks between nodes {i, i+1} of L and {i, i+1} of L + d over the one or two
+//            (self: four) element columns that hold both lines -- symmetric and skew parts separately, 15 DFMA per block
+//            and point instead of 18 -- and carries the (i+1, i+1) block and the two x-off-diagonal blocks into the next
+//            interval, where they complete the rows of node i+1.
+//   staging  at the end of the interval every pair thread drops its blocks of node plane i -- direct into the row of L,
+//            transposed into the row of L + d -- into a shared-memory image of the tile's 64 complete CSR rows, and one
+//            thread per line hands the row to the TMA unit: cp.async.bulk shared -> global of the 16-byte aligned part
+//            (~1.9 KB per line and interval; the odd leading / trailing double is carried to the next interval's copy).
+//            The copy drains while the next interval is computed; the SM issues no global store for the Jacobian.
+// Every CSR row is written once, in full 16-byte units, by exactly one CTA. Row addresses are closed-form per line (host
+// tables, verified against the CSR pattern when the plan is built); meshes without grid topology keep the atomic scatter.
 #include <algorithm>
 #include <cstring>
 #include "asm_common.cuh"
@@ -37,8 +43,10 @@
 #define L3_NY2 (L3_TY + 2)               // node lines cached per row
 #define L3_NLC (L3_NY2 * (L3_TZ + 2))    // 100 node lines touch those columns
 #define L3_NLCP 104
-#define L3_THREADS 384                   // 12 warps; 10 of them own line pairs in phase B
-#define L3_NPT (5 * L3_NL)               // pair threads per tile
+#define L3_THREADS 384                   // 12 warps: 2 of self pairs, 5 of two-column pairs, 5 of one-column pairs
+#define L3_NPT L3_THREADS                // Laplacian-table slots per interval: one per thread
+#define L3_QH 4                          // quadrature points per half interval
+#define L3_SLOT 246                      // staging doubles per line: 243 (27 blocks x 9) + alignment slack, 16-byte multiple
 
 struct L3Line {                          // per node line (y, z): closed-form CSR addressing of its rows
   int64_t lb;                            // block-row start of the line's first node
@@ -58,8 +66,9 @@ struct L3Args {
   const double *coords, *U;
   double *R, *vals;
   unsigned *counter;                     // [2] next unit, CTAs done
+  double *carry;                         // [grid][18][L3_THREADS] x-off-diagonal blocks on their way to the next node plane's rows (L2-resident)
   int dbg_nostore;                       // experiments only: 1 = skip the global stores
-  unsigned long long *prof;              // optional cycle counters (nls_set_option "profile_phases"): phase A, phase B, intervals, unit setup
+  unsigned long long *prof;              // optional cycle counters (nls_set_option "profile_phases"): phase A, phase B, intervals
 };
 
 __device__ __forceinline__ void l3_cp8(void *smem_dst, const void *gmem_src) {
@@ -69,8 +78,18 @@ __device__ __forceinline__ void l3_cp8(void *smem_dst, const void *gmem_src) {
 __device__ __forceinline__ void l3_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void l3_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// stores of 3 / 6 consecutive doubles at an 8-byte aligned address: 16-byte stores wherever the alignment allows.
-// Inline PTX on purpose: written as C++ the optimiser merges the stores of the two alignment branches into one
+// TMA bulk copy shared -> global (no tensor map: a flat run of 16-byte units), tracked by bulk async-groups
+__device__ __forceinline__ void l3_bulk_store(double *gdst, const double *ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l3_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void l3_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (the TMA unit) after the next barrier
+__device__ __forceinline__ void l3_fence_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// stores of 3 consecutive doubles at an 8-byte aligned address (the residual): 16-byte stores wherever the alignment
+// allows. Inline PTX on purpose: written as C++ the optimiser merges the stores of the two alignment branches into one
 // unconditional 16-byte store that is misaligned for half of the addresses (seen in the SASS of the first version).
 __device__ __forceinline__ void l3_stg1(double *p, double a) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(a)); }
 __device__ __forceinline__ void l3_stg2(double *p, double a, double b) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b)); }
@@ -78,9 +97,23 @@ __device__ __forceinline__ void l3_st3(double *p, double a, double b, double c) 
   if ((reinterpret_cast<uintptr_t>(p) & 8) == 0) { l3_stg2(p, a, b); l3_stg1(p + 2, c); }
   else { l3_stg1(p, a); l3_stg2(p + 1, b, c); }
 }
-__device__ __forceinline__ void l3_st6(double *p, double a, double b, double c, double d, double e, double f) {
-  if ((reinterpret_cast<uintptr_t>(p) & 8) == 0) { l3_stg2(p, a, b); l3_stg2(p + 2, c, d); l3_stg2(p + 4, e, f); }
-  else { l3_stg1(p, a); l3_stg2(p + 1, b, c); l3_stg2(p + 3, d, e); l3_stg1(p + 5, f); }
+
+// 6 consecutive doubles into the staging image at an 8-byte aligned shared address: 16-byte stores where the alignment allows
+// (conflict-free across the lines of a warp: the line slots are an odd number of 16-byte units apart)
+__device__ __forceinline__ void l3_sts6(double *p, double a, double b, double c, double d, double e, double f) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(p);
+  if ((s & 8u) == 0) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n\tst.shared.v2.f64 [%0+16], {%3, %4};\n\tst.shared.v2.f64 [%0+32], {%5, %6};"
+                 ::"r"(s), "d"(a), "d"(b), "d"(c), "d"(d), "d"(e), "d"(f) : "memory");
+  } else {
+    asm volatile("st.shared.f64 [%0], %1;\n\tst.shared.v2.f64 [%0+8], {%2, %3};\n\tst.shared.v2.f64 [%0+24], {%4, %5};\n\tst.shared.f64 [%0+40], %6;"
+                 ::"r"(s), "d"(a), "d"(b), "d"(c), "d"(d), "d"(e), "d"(f) : "memory");
+  }
+}
+__device__ __forceinline__ void l3_sts3(double *p, double a, double b, double c) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(p);
+  if ((s & 8u) == 0) asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n\tst.shared.f64 [%0+16], %3;" ::"r"(s), "d"(a), "d"(b), "d"(c) : "memory");
+  else asm volatile("st.shared.f64 [%0], %1;\n\tst.shared.v2.f64 [%0+8], {%2, %3};" ::"r"(s), "d"(a), "d"(b), "d"(c) : "memory");
 }
 
 // one block accumulator: {D0, D1, D2, S01, S02, S12, W01, W02, W12}; K_ik = S_ik + W_ik, K_ki = S_ik - W_ik, K_ii = 2 D_i
@@ -100,112 +133,170 @@ __device__ __forceinline__ void l3_full(const double (&K)[9], const double dl, d
   F[1][2] = K[5] + K[8]; F[2][1] = K[5] - K[8];
 }
 
-struct L3Row { double *p; int64_t stride; };   // first entry of a block in scalar row 0, distance between the scalar rows
-// block at x-offset dx (-1, 0, +1) of the neighbour-line triple `rank` in the row of node i of a line
-__device__ __forceinline__ L3Row l3_row(double *vals, const int64_t lb, const int nl, const int rank, const int i, const int nxm1, const int dx) {
-  const int w = (i == 0 || i == nxm1) ? 2 : 3;
-  const int64_t b0 = lb + (int64_t)nl * (i == 0 ? 0 : 3 * i - 1);
-  const int pos = rank * w + dx + (i == 0 ? 0 : 1);
-  L3Row r;
-  r.stride = 3 * (int64_t)nl * w;
-  r.p = vals + 9 * b0 + 3 * pos;
-  return r;
+// adjugate (transposed cofactors) and determinant of a 3 x 3 matrix: inverse = adj / det
+__device__ __forceinline__ double l3_adj(const double (&M)[9], double (&A)[9]) {
+  A[0] = M[4] * M[8] - M[5] * M[7]; A[1] = M[2] * M[7] - M[1] * M[8]; A[2] = M[1] * M[5] - M[2] * M[4];
+  A[3] = M[5] * M[6] - M[3] * M[8]; A[4] = M[0] * M[8] - M[2] * M[6]; A[5] = M[2] * M[3] - M[0] * M[5];
+  A[6] = M[3] * M[7] - M[4] * M[6]; A[7] = M[1] * M[6] - M[0] * M[7]; A[8] = M[0] * M[4] - M[1] * M[3];
+  return M[0] * A[0] + M[1] * A[3] + M[2] * A[6];
+}
+
+// CSR geometry of the row of node i of a line: parity of its first double, blocks per neighbour line
+struct L3RowGeo { int par, w; };
+__device__ __forceinline__ L3RowGeo l3_geo(const int lbpar, const int nl, const int i, const int nxm1) {
+  L3RowGeo g;
+  g.w = (i == 0 || i == nxm1) ? 2 : 3;
+  g.par = (i == 0) ? lbpar : ((lbpar + nl * (3 * i - 1)) & 1);
+  return g;
 }
 
 template <bool DO_R, bool DO_K, bool LAP_BUILD>
 __global__ void __launch_bounds__(L3_THREADS, 1)
 k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
   constexpr int NARR = DO_R ? 16 : 13;          // double2 arrays per quadrature point: 4 corner pairs x 3, scalars, stress x 3
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2 *REC = reinterpret_cast<double2 *>(smem_raw);                 // [8][NARR][L3_NCOLP]
-  double *XU = reinterpret_cast<double *>(REC + 8 * NARR * L3_NCOLP);   // [3 planes][6][L3_NLCP]: X, u of the cached node lines
-  double *TAB = XU + 3 * 6 * L3_NLCP;                                   // dN[8][8][3], w[8]
+  constexpr bool STAGE = DO_K && !LAP_BUILD;    // the Jacobian rows go through the staging image and the TMA unit
+  constexpr int CC = 12 * L3_NCOLP, PR = 3 * L3_NCOLP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *STG = reinterpret_cast<double *>(smem_raw);                                  // [L3_NL][L3_SLOT]
+  double2 *REC = reinterpret_cast<double2 *>(STG + L3_NL * L3_SLOT);                    // [L3_QH][NARR][L3_NCOLP]
+  double *XU = reinterpret_cast<double *>(REC + L3_QH * 16 * L3_NCOLP);                 // [2 planes][6][L3_NLCP]: X, u of the cached node lines
+  double *LAPS = XU + 2 * 6 * L3_NLCP;                                                  // [3][L3_THREADS] Laplacian parts of this interval's blocks
+  double *TAB = LAPS + 3 * L3_THREADS;                                                  // dN[8][8][3], w[8]
   __shared__ int s_unit;
+  __shared__ long long s_lapoff;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int k = tid; k < 192; k += L3_THREADS) TAB[k] = T.dN[k / 24][(k / 3) & 7][k % 3];
   if (tid < 8) TAB[192 + tid] = T.w[tid];
-  for (int k = tid; k < 8 * NARR; k += L3_THREADS) REC[k * L3_NCOLP + L3_ZCOL] = make_double2(0.0, 0.0);
+  for (int k = tid; k < L3_QH * NARR; k += L3_THREADS) REC[k * L3_NCOLP + L3_ZCOL] = make_double2(0.0, 0.0);
   const double mu = LAP_BUILD ? 0.0 : mp.p[0], lam = mp.p[1];
   const int nx = P.nx, ny = P.ny, nzp = P.nzp, nxm1 = nx - 1;
 
-  // phase-B role of this warp: {self, self, (0,1), (0,1), (1,0), (1,0), (-1,1), (-1,1), none, none, (1,1), (1,1)} -- per SM
-  // sub-partition (warp & 3) the roles add up to about the same DFMA count
-  int ptype, dy, dz;
-  switch (warp >> 1) {
-    case 0: ptype = 0; dy = 0; dz = 0; break;
-    case 1: ptype = 3; dy = 0; dz = 1; break;
-    case 2: ptype = 1; dy = 1; dz = 0; break;
-    case 3: ptype = 2; dy = -1; dz = 1; break;
-    case 5: ptype = 4; dy = 1; dz = 1; break;
-    default: ptype = -1; dy = 0; dz = 0; break;
+  // ---- phase-B role of this thread (fixed for the whole launch): pair type and the tile-relative line A = (ay, az) ----
+  // warps {0,1} self pairs; {2,3,6,7,11} pairs with two common element columns, d = (1,0) and (0,1); {4,5,8,9,10} pairs with
+  // one, d = (1,1) and (-1,1): per SM sub-partition (warp & 3) the roles add up to about the same DFMA count
+  int ptype = -1, ay = 0, az = 0;
+  {
+    int role, ord;
+    switch (warp) {
+      case 0: role = 0; ord = 0; break;  case 1: role = 0; ord = 1; break;
+      case 2: role = 1; ord = 0; break;  case 3: role = 1; ord = 1; break;
+      case 6: role = 1; ord = 2; break;  case 7: role = 1; ord = 3; break;  case 11: role = 1; ord = 4; break;
+      case 4: role = 2; ord = 0; break;  case 5: role = 2; ord = 1; break;
+      case 8: role = 2; ord = 2; break;  case 9: role = 2; ord = 3; break;  default: role = 2; ord = 4; break;
+    }
+    int k = ord * 32 + lane;
+    if (role == 0) { ptype = 0; ay = k & 7; az = k >> 3; }
+    else if (role == 1) {
+      if (k < 72) { ptype = 1; ay = k % 9 - 1; az = k / 9; }                       // A from y = -1: the pair (-1, 0) belongs to line 0's rows
+      else if (k < 144) { k -= 72; ptype = 3; ay = k & 7; az = (k >> 3) - 1; }
+    } else if (k < 158) {
+      if (k < 79) ptype = 4; else { ptype = 2; k -= 79; }
+      if (k < 64) { ay = k & 7; az = k >> 3; }
+      else if (k < 72) { ay = ptype == 4 ? -1 : 8; az = k - 65; }                  // B in the tile, A beside it
+      else { az = -1; ay = ptype == 4 ? k - 72 : k - 71; }                         // ... A below it
+    }
   }
-  const int ll = (warp & 1) * 32 + lane, ly = ll & (L3_TY - 1), lz = ll / L3_TY;
-  const int pidx = ptype * L3_NL + ll;
+  const int dy = (ptype == 1 || ptype == 4) ? 1 : (ptype == 2 ? -1 : 0), dz = ptype >= 2 ? 1 : 0;
+  const bool two = (ptype == 1 || ptype == 3);
+  // corner pair (dy' + 2 dz') of line A and of line B inside the first and the second common element column
+  const int oa0 = (ptype == 1 ? 2 : (ptype == 4 ? 0 : 1)) * PR, ob0 = (ptype == 2 ? 2 : 3) * PR, ob1 = (ptype == 1 ? 1 : 2) * PR;   // oa1 = 0
+  // row issuers: cp.async.bulk blocks its issuer while the TMA queue (about eight requests) is full, and one interval's rows
+  // keep the SM's store path busy for about 4 k cycles (profiles/r2_ubench_bulk.txt). The hand-off therefore sits where
+  // warps would otherwise idle: the five warps of one-column pairs finish the first half of phase B long before the others,
+  // and issue the previous interval's 64 rows there (13 lines per warp).
+  const int oord = (warp == 4) ? 0 : (warp == 5) ? 1 : (warp == 8) ? 2 : (warp == 9) ? 3 : (warp == 10) ? 4 : -1;
+  const int iline = oord * 13 + lane;
+  const bool isslot = STAGE && oord >= 0 && lane < 13 && iline < L3_NL;
+  double cv = 0.0;                 // issuer: the odd trailing double of the last copy, waiting for the next
+  bool have_cv = false;
 
   for (;;) {
-    if (tid == 0) s_unit = (int)atomicAdd(P.counter, 1u);
+    if (tid == 0) { const int uu = (int)atomicAdd(P.counter, 1u); s_unit = uu; s_lapoff = uu < P.nunits ? (long long)P.lapoff[uu] : 0ll; }
     __syncthreads();
     const int u = s_unit;
     if (u >= P.nunits) break;
     const int4 un = P.units[u];
     const int y0 = un.x, z0 = un.y, i0 = un.z, i1 = un.w;
+    const int ifirst = i0 > 0 ? i0 - 1 : 0;    // a chunk that starts inside the line first runs one interval without stores
+    const int ilast = (i1 == nxm1) ? nxm1 : i1 - 1;   // last node plane whose rows this unit writes
 
     // ---- per-unit role of this thread in phase B ----
-    bool wd = false, wm = false;
-    int colv[4] = {L3_ZCOL, L3_ZCOL, L3_ZCOL, L3_ZCOL}, offA[4] = {0, 0, 0, 0}, offB[2] = {0, 0};
-    int64_t lbA = 0, lbB = 0;
-    int nlA = 0, nlB = 0, rA = 0, rB = 0;
-    int64_t nodeA0 = 0;
+    // geoA / geoB: where the pair's blocks go in the staging image -- staging offset of the line | neighbour lines << 16 |
+    // rank of the other line among them << 20 | parity of the line's first block row << 24; -1 = that line is not this tile's
+    int geoA = -1, geoB = -1;
+    int c0 = L3_ZCOL, c1 = L3_ZCOL, c2 = L3_ZCOL, c3 = L3_ZCOL;     // element columns that hold both lines
+    int nodeA0 = 0;
     if (ptype >= 0 && (DO_K || ptype == 0)) {
-      const int y = y0 + ly, z = z0 + lz, y2 = y + dy, z2 = z + dz;
-      const bool e1 = y < ny && z < nzp, e2 = e1 && y2 >= 0 && y2 < ny && z2 < nzp;
-      if (e1 && e2) {
-        wd = P.pown[z] != 0;
-        wm = ptype != 0 && P.pown[z2] != 0;
-      }
-      if (wd || wm) {
+      const int y = y0 + ay, z = z0 + az, y2 = y + dy, z2 = z + dz;
+      const bool ex = y >= 0 && y < ny && z >= 0 && z < nzp && y2 >= 0 && y2 < ny && z2 < nzp;
+      const bool stA = ex && ay >= 0 && ay < L3_TY && az >= 0 && P.pown[z] != 0;
+      const bool stB = ex && ptype != 0 && ay + dy >= 0 && ay + dy < L3_TY && az + dz < L3_TZ && P.pown[z2] != 0;
+      if (stA || stB) {
         auto col_of = [&](int ey, int ez) -> int {
           return (ey >= 0 && ey < ny - 1 && ez >= 0 && ez < nzp - 1) ? (ez - z0 + 1) * L3_CY + (ey - y0 + 1) : L3_ZCOL;
         };
-        // element columns that hold both lines, with the corner pair (dy' + 2 dz') of each line inside the column
-        if (ptype == 0) {
-          colv[0] = col_of(y - 1, z - 1); offA[0] = 3; colv[1] = col_of(y, z - 1); offA[1] = 2;
-          colv[2] = col_of(y - 1, z); offA[2] = 1;     colv[3] = col_of(y, z); offA[3] = 0;
-        } else if (ptype == 1) {
-          colv[0] = col_of(y, z - 1); offA[0] = 2; offB[0] = 3; colv[1] = col_of(y, z); offA[1] = 0; offB[1] = 1;
-        } else if (ptype == 2) {
-          colv[0] = col_of(y - 1, z); offA[0] = 1; offB[0] = 2;
-        } else if (ptype == 3) {
-          colv[0] = col_of(y - 1, z); offA[0] = 1; offB[0] = 3; colv[1] = col_of(y, z); offA[1] = 0; offB[1] = 2;
-        } else {
-          colv[0] = col_of(y, z); offA[0] = 0; offB[0] = 3;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) offA[k] *= 3 * L3_NCOLP;
-        offB[0] *= 3 * L3_NCOLP; offB[1] *= 3 * L3_NCOLP;
-        if (wd) {
+        if (ptype == 0) { c0 = col_of(y - 1, z - 1); c1 = col_of(y, z - 1); c2 = col_of(y - 1, z); c3 = col_of(y, z); }
+        else if (ptype == 1) { c0 = col_of(y, z - 1); c1 = col_of(y, z); }
+        else if (ptype == 2) { c0 = col_of(y - 1, z); }
+        else if (ptype == 3) { c0 = col_of(y - 1, z); c1 = col_of(y, z); }
+        else { c0 = col_of(y, z); }
+        if (stA) {
           const L3Line a = P.info[z * ny + y];
-          lbA = a.lb; nlA = a.nl; rA = a.rank[(dz + 1) * 3 + (dy + 1)];
-          nodeA0 = (int64_t)P.pbase[z] + (int64_t)y * nx;
+          geoA = ((az * L3_TY + ay) * L3_SLOT) | (a.nl << 16) | ((int)a.rank[(dz + 1) * 3 + (dy + 1)] << 20) | ((int)(a.lb & 1) << 24);
+          nodeA0 = P.pbase[z] + y * nx;
         }
-        if (wm) {
+        if (stB) {
           const L3Line b = P.info[z2 * ny + y2];
-          lbB = b.lb; nlB = b.nl; rB = b.rank[(1 - dz) * 3 + (1 - dy)];
+          geoB = (((az + dz) * L3_TY + ay + dy) * L3_SLOT) | (b.nl << 16) | ((int)b.rank[(1 - dz) * 3 + (1 - dy)] << 20) | ((int)(b.lb & 1) << 24);
         }
       }
     }
-    const bool on = wd || wm;
-    const bool two = (ptype == 1 || ptype == 3);
-    double *lapu = P.lap + P.lapoff[u] + pidx;
+    const bool on = (geoA & geoB) >= 0;     // at least one of them is not -1
+    // first double of the pair's piece in the row of node ip, and the distance between the three scalar rows
+    auto piece = [&](const int geo, const int ip, int &rs) -> double * {
+      const int nl = (geo >> 16) & 15, w = (ip == 0 || ip == nxm1) ? 2 : 3;
+      const int par = (ip == 0) ? (geo >> 24) & 1 : ((geo >> 24) + nl * (3 * ip - 1)) & 1;
+      rs = nl * 3 * w;
+      return STG + (geo & 0xffff) + par + ((geo >> 20) & 15) * w * 3;
+    };
+    // issuer state
+    bool iss = false;
+    int64_t ilb = 0;
+    int inl = 0;
+    if (isslot) {
+      const int y = y0 + (iline & (L3_TY - 1)), z = z0 + iline / L3_TY;
+      if (y < ny && z < nzp && P.pown[z] != 0) { const L3Line a = P.info[z * ny + y]; iss = true; ilb = a.lb; inl = a.nl; }
+    }
+    have_cv = false;
+    int pend = -1;                 // node plane whose rows still wait for their hand-off to the TMA unit
 
-    // accumulators: Kd = (A_i, B_i), Ku = (A_i, B_i+1), Kl = (A_i+1, B_i), Kn = (A_i+1, B_i+1); self: Kd, Kn hold 6 symmetric sums
+    // accumulators: Kd = (A_i, B_i), Ku = (A_i, B_i+1), Kl = (A_i+1, B_i), Kn = (A_i+1, B_i+1); self: Kd, Kn hold 6 symmetric sums.
+    // The two x-off-diagonal blocks finished in interval i-1, (A_i, B_i-1) and (A_i-1, B_i), belong to the rows of node plane
+    // i: they wait in the CTA's carry scratch (global, L2-resident, one coalesced column per thread) -- not in registers --
+    // and cp.async drops them into the staging image while the second half of interval i is computed.
     double Kd[9], Ku[9], Kl[9], Kn[9], fd[3] = {0, 0, 0}, fn[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 9; ++k) { Kd[k] = 0.0; Ku[k] = 0.0; Kl[k] = 0.0; Kn[k] = 0.0; }
+    // carried blocks -> dx = -1 pieces of the rows of node plane ip (asynchronous; completion: l3_wait_all)
+    auto fetch_carry = [&](const int ip) {
+      const double *cry = P.carry + (size_t)blockIdx.x * 18 * L3_THREADS + tid;
+      if (geoA >= 0) {
+        int rs;
+        double *p = piece(geoA, ip, rs);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) l3_cp8(p + (k / 3) * rs + k % 3, cry + k * L3_THREADS);
+      }
+      if (geoB >= 0) {
+        int rs;
+        double *p = piece(geoB, ip, rs);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) l3_cp8(p + (k / 3) * rs + k % 3, cry + (9 + k) * L3_THREADS);
+      }
+    };
 
-    auto load_plane = [&](int ip) {            // X, u of node plane ip of the cached lines -> ring slot ip % 3
+    auto load_plane = [&](int ip) {            // X, u of node plane ip of the cached lines -> ring slot ip & 1
       if (ip > nxm1) return;
-      const int slot = ip % 3;
+      const int slot = ip & 1;
       for (int k = tid; k < 2 * L3_NLC; k += L3_THREADS) {
         const int c = k >> 1, half = k & 1;
         const int y = y0 - 1 + c % L3_NY2, z = z0 - 1 + c / L3_NY2;
@@ -217,212 +308,267 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       }
     };
 
-    const int ifirst = i0 > 0 ? i0 - 1 : 0;    // a chunk that starts inside the line first runs one interval without stores
+    // the row of node plane ip of line `iline`: 16-byte aligned part by one bulk copy, odd ends carried or stored singly
+    auto flush_row = [&](const int ip) {
+      const L3RowGeo g = l3_geo((int)(ilb & 1), inl, ip, nxm1);
+      const int64_t g0 = 9 * (ilb + (int64_t)inl * (ip == 0 ? 0 : 3 * ip - 1));   // first double of the row in vals
+      double *sm = STG + iline * L3_SLOT;                                           // the row sits at sm[par .. par + len)
+      int lo = g.par, hi = g.par + 9 * inl * g.w;
+      if (lo) {
+        if (have_cv) { sm[0] = cv; lo = 0; l3_fence_async(); }
+        else { l3_stg1(P.vals + g0, sm[1]); lo = 2; }
+      }
+      have_cv = false;
+      if (hi & 1) {
+        --hi;
+        if (ip < ilast) { cv = sm[hi]; have_cv = true; }
+        else l3_stg1(P.vals + (g0 - g.par + hi), sm[hi]);
+      }
+      if (hi > lo) l3_bulk_store(P.vals + (g0 - g.par + lo), sm + lo, (unsigned)(hi - lo) * 8u);
+      l3_bulk_commit();
+    };
+
     load_plane(ifirst); load_plane(ifirst + 1);
     l3_commit(); l3_wait_all();
     __syncthreads();
 
     for (int i = ifirst; i < i1; ++i) {
       const long long tp0 = P.prof ? clock64() : 0;
-      load_plane(i + 2);
-      l3_commit();
-      double lp0 = 0.0, lp1 = 0.0, lp2 = 0.0;
+      long long tA = 0, tB = 0;
       const bool store = i >= i0 && !P.dbg_nostore;
-      if (!LAP_BUILD && DO_K && on && store) {
-        const double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
-        lp0 = lq[0]; lp1 = lq[L3_NPT]; lp2 = lq[2 * L3_NPT];
+      if (!LAP_BUILD && DO_K && on) {            // this interval's Laplacian parts -> shared memory, read when the blocks are finished
+        const double *lq = P.lap + s_lapoff + tid + (int64_t)(i - ifirst) * 3 * L3_NPT;
+        l3_cp8(LAPS + tid, lq); l3_cp8(LAPS + L3_THREADS + tid, lq + L3_NPT); l3_cp8(LAPS + 2 * L3_THREADS + tid, lq + 2 * L3_NPT);
       }
-      // ---------------- phase A: quadrature-point records of interval i ----------------
-      {
-        const int slo = i % 3, shi = (i + 1) % 3;
+      l3_commit();
 #pragma unroll 1
-        for (int item = tid; item < 8 * L3_NCOL; item += L3_THREADS) {
-          const int q = item / L3_NCOL, col = item - q * L3_NCOL;
+      for (int half = 0; half < 2; ++half) {
+        const long long ta0 = P.prof ? clock64() : 0;
+        // ---------------- phase A: quadrature-point records 4 half .. 4 half + 3 of interval i ----------------
+        if (tid < L3_QH * L3_NCOL) {
+          const int slo = i & 1, shi = slo ^ 1;
+          const int ql = tid / L3_NCOL, col = tid - ql * L3_NCOL, q = half * L3_QH + ql;
           const int cyi = col % L3_CY, czi = col / L3_CY;
           const int ey = y0 - 1 + cyi, ez = z0 - 1 + czi;
-          if (ey < 0 || ey >= ny - 1 || ez < 0 || ez >= nzp - 1) continue;
-          const double *tq = TAB + q * 24;
-          double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          if (ey >= 0 && ey < ny - 1 && ez >= 0 && ez < nzp - 1) {
+            const double *tq = TAB + q * 24;
+            double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-          for (int a = 0; a < 8; ++a) {
-            const int cl = (czi + (a >> 2)) * L3_NY2 + cyi + ((a >> 1) & 1);
-            const double *xs = XU + ((a & 1) ? shi : slo) * 6 * L3_NLCP + cl;
-            const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const double x = xs[d * L3_NLCP];
-              J[d * 3 + 0] = fma(x, dn0, J[d * 3 + 0]); J[d * 3 + 1] = fma(x, dn1, J[d * 3 + 1]); J[d * 3 + 2] = fma(x, dn2, J[d * 3 + 2]);
-            }
-            if (!LAP_BUILD) {
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                const double v = xs[(3 + d) * L3_NLCP];
-                H[d * 3 + 0] = fma(v, dn0, H[d * 3 + 0]); H[d * 3 + 1] = fma(v, dn1, H[d * 3 + 1]); H[d * 3 + 2] = fma(v, dn2, H[d * 3 + 2]);
-              }
-            }
-          }
-          double Ji[9], Mi[9];
-          const double detJ = inv3(J, Ji);
-          const double wdet = TAB[192 + q] * detJ;
-          double cs, cw, lnJ = 0.0, c1 = 0.0, c2 = 0.0;
-          if (LAP_BUILD) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) Mi[k] = Ji[k];
-            cs = 0.5 * wdet; cw = 0.5 * wdet;
-          } else {
-            double M[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) M[k] = J[k] + H[k];
-            const double detM = inv3(M, Mi);
-            lnJ = log(detM / detJ);
-            c1 = wdet * mu; c2 = wdet * lam;
-            const double c3 = c1 - c2 * lnJ;
-            cs = 0.5 * (c2 + c3); cw = 0.5 * (c2 - c3);
-          }
-          double2 *rq = REC + q * NARR * L3_NCOLP + col;
-          rq[12 * L3_NCOLP] = make_double2(cs, cw);
-#pragma unroll
-          for (int pr = 0; pr < 4; ++pr) {
-            double g[2][3];
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              const int a = 2 * pr + s;
+            for (int a = 0; a < 8; ++a) {
+              const int cl = (czi + (a >> 2)) * L3_NY2 + cyi + ((a >> 1) & 1);
+              const double *xs = XU + ((a & 1) ? shi : slo) * 6 * L3_NLCP + cl;
               const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
 #pragma unroll
-              for (int k = 0; k < 3; ++k) g[s][k] = fma(dn0, Mi[k], fma(dn1, Mi[3 + k], dn2 * Mi[6 + k]));
+              for (int d = 0; d < 3; ++d) {
+                const double x = xs[d * L3_NLCP];
+                J[d * 3 + 0] = fma(x, dn0, J[d * 3 + 0]); J[d * 3 + 1] = fma(x, dn1, J[d * 3 + 1]); J[d * 3 + 2] = fma(x, dn2, J[d * 3 + 2]);
+              }
+              if (!LAP_BUILD) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                  const double v = xs[(3 + d) * L3_NLCP];
+                  H[d * 3 + 0] = fma(v, dn0, H[d * 3 + 0]); H[d * 3 + 1] = fma(v, dn1, H[d * 3 + 1]); H[d * 3 + 2] = fma(v, dn2, H[d * 3 + 2]);
+                }
+              }
             }
-            rq[(pr * 3 + 0) * L3_NCOLP] = make_double2(g[0][0], g[0][1]);
-            rq[(pr * 3 + 1) * L3_NCOLP] = make_double2(g[0][2], g[1][0]);
-            rq[(pr * 3 + 2) * L3_NCOLP] = make_double2(g[1][1], g[1][2]);
+            // one division for both inverses: r = 1 / (det J det M), J^-1 = adj J (det M r), M^-1 = adj M (det J r), det F = det M^2 r
+            double Ji[9], Mi[9];
+            const double detJ = l3_adj(J, Ji);
+            double cs, cw, lnJ = 0.0, c1 = 0.0, c2 = 0.0, wdet;
+            if (LAP_BUILD) {
+              const double id = 1.0 / detJ;
+#pragma unroll
+              for (int k = 0; k < 9; ++k) Mi[k] = Ji[k] * id;
+              wdet = TAB[192 + q] * detJ;
+              cs = 0.5 * wdet; cw = 0.5 * wdet;
+            } else {
+              double M[9];
+#pragma unroll
+              for (int k = 0; k < 9; ++k) M[k] = J[k] + H[k];
+              const double detM = l3_adj(M, Mi);
+              const double r = 1.0 / (detJ * detM);
+              const double sj = detM * r, sm_ = detJ * r;
+#pragma unroll
+              for (int k = 0; k < 9; ++k) { Ji[k] *= sj; Mi[k] *= sm_; }
+              wdet = TAB[192 + q] * detJ;
+              lnJ = log(detM * sj);
+              c1 = wdet * mu; c2 = wdet * lam;
+              const double c3 = c1 - c2 * lnJ;
+              cs = 0.5 * (c2 + c3); cw = 0.5 * (c2 - c3);
+            }
+            double2 *rq = REC + ql * NARR * L3_NCOLP + col;
+            rq[CC] = make_double2(cs, cw);
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+              double g[2][3];
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                const int a = 2 * pr + s;
+                const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[s][k] = fma(dn0, Mi[k], fma(dn1, Mi[3 + k], dn2 * Mi[6 + k]));
+              }
+              rq[(pr * 3 + 0) * L3_NCOLP] = make_double2(g[0][0], g[0][1]);
+              rq[(pr * 3 + 1) * L3_NCOLP] = make_double2(g[0][2], g[1][0]);
+              rq[(pr * 3 + 2) * L3_NCOLP] = make_double2(g[1][1], g[1][2]);
+            }
+            if (DO_R && !LAP_BUILD) {
+              // Kirchhoff stress times w detJ: tau = mu (b - I) + lam lnJ I, b - I = Hp + Hp^T + Hp Hp^T, Hp = H J^-1 = F - I
+              double Hp[9];
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Hp[r * 3 + c] = fma(H[r * 3], Ji[c], fma(H[r * 3 + 1], Ji[3 + c], H[r * 3 + 2] * Ji[6 + c]));
+              const double cl = c2 * lnJ;
+              auto ee = [&](int r, int c) {
+                return (Hp[r * 3 + c] + Hp[c * 3 + r]) + fma(Hp[r * 3], Hp[c * 3], fma(Hp[r * 3 + 1], Hp[c * 3 + 1], Hp[r * 3 + 2] * Hp[c * 3 + 2]));
+              };
+              rq[13 * L3_NCOLP] = make_double2(fma(c1, ee(0, 0), cl), fma(c1, ee(1, 1), cl));
+              rq[14 * L3_NCOLP] = make_double2(fma(c1, ee(2, 2), cl), c1 * ee(0, 1));
+              rq[15 * L3_NCOLP] = make_double2(c1 * ee(0, 2), c1 * ee(1, 2));
+            }
           }
-          if (DO_R && !LAP_BUILD) {
-            // Kirchhoff stress times w detJ: tau = mu (b - I) + lam lnJ I, b - I = Hp + Hp^T + Hp Hp^T, Hp = H J^-1 = F - I
-            double Hp[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) Hp[r * 3 + c] = fma(H[r * 3], Ji[c], fma(H[r * 3 + 1], Ji[3 + c], H[r * 3 + 2] * Ji[6 + c]));
-            const double cl = c2 * lnJ;
-            auto ee = [&](int r, int c) {
-              return (Hp[r * 3 + c] + Hp[c * 3 + r]) + fma(Hp[r * 3], Hp[c * 3], fma(Hp[r * 3 + 1], Hp[c * 3 + 1], Hp[r * 3 + 2] * Hp[c * 3 + 2]));
+        }
+        // last interval's bulk copies have long finished reading the staging image; make that a fact before anyone rewrites it
+        if (half == 1 && isslot) l3_bulk_wait_read();
+        // The fence is required, not decoration: without it the phase-B loads of some warps returned the previous
+        // interval's records although every STS above precedes this barrier in program order (found on a 3 x 2 x 3-node
+        // mesh by the parity tests; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
+        __threadfence_block();
+        __syncthreads();
+        if (P.prof) tA += clock64() - ta0;
+        if (half == 1) {
+          load_plane(i + 2);       // both halves have read node plane i: its slot takes plane i+2
+          if (STAGE && on && store && i > 0) fetch_carry(i);
+          l3_commit();
+        }
+        const long long tb0 = P.prof ? clock64() : 0;
+        // ---------------- phase B: line pairs, four quadrature points ----------------
+        if (on) {
+          if (ptype == 0) {
+            auto self_col = [&](const int col, const int oa) {
+              if (col == L3_ZCOL) return;
+              const double2 *base = REC + col;
+#pragma unroll 1
+              for (int q = 0; q < L3_QH; ++q) {
+                const double2 *rq = base + q * NARR * L3_NCOLP;
+                const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
+                const double2 cc = rq[CC];
+                const double glo[3] = {a0.x, a0.y, a1.x}, ghi[3] = {a1.y, a2.x, a2.y};
+                if (DO_K) {
+                  const double plo[3] = {cc.x * glo[0], cc.x * glo[1], cc.x * glo[2]};
+                  const double mlo[3] = {cc.y * glo[0], cc.y * glo[1], cc.y * glo[2]};
+                  const double phi[3] = {cc.x * ghi[0], cc.x * ghi[1], cc.x * ghi[2]};
+                  // (lo, lo) and (hi, hi): symmetric, K_ik = 2 cs g_i g_k
+                  Kd[0] = fma(plo[0], glo[0], Kd[0]); Kd[1] = fma(plo[1], glo[1], Kd[1]); Kd[2] = fma(plo[2], glo[2], Kd[2]);
+                  Kd[3] = fma(plo[0], glo[1], Kd[3]); Kd[4] = fma(plo[0], glo[2], Kd[4]); Kd[5] = fma(plo[1], glo[2], Kd[5]);
+                  Kn[0] = fma(phi[0], ghi[0], Kn[0]); Kn[1] = fma(phi[1], ghi[1], Kn[1]); Kn[2] = fma(phi[2], ghi[2], Kn[2]);
+                  Kn[3] = fma(phi[0], ghi[1], Kn[3]); Kn[4] = fma(phi[0], ghi[2], Kn[4]); Kn[5] = fma(phi[1], ghi[2], Kn[5]);
+                  l3_acc(Ku, plo, mlo, ghi);
+                }
+                if (DO_R && !LAP_BUILD) {
+                  const double2 t0 = rq[13 * L3_NCOLP], t1 = rq[14 * L3_NCOLP], t2 = rq[15 * L3_NCOLP];
+                  // tau = {xx, yy | zz, xy | xz, yz}
+                  fd[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], fd[0])));
+                  fd[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], fd[1])));
+                  fd[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], fd[2])));
+                  fn[0] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], fn[0])));
+                  fn[1] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], fn[1])));
+                  fn[2] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], fn[2])));
+                }
+              }
             };
-            rq[13 * L3_NCOLP] = make_double2(fma(c1, ee(0, 0), cl), fma(c1, ee(1, 1), cl));
-            rq[14 * L3_NCOLP] = make_double2(fma(c1, ee(2, 2), cl), c1 * ee(0, 1));
-            rq[15 * L3_NCOLP] = make_double2(c1 * ee(0, 2), c1 * ee(1, 2));
+            self_col(c0, 3 * PR); self_col(c1, 2 * PR); self_col(c2, PR); self_col(c3, 0);
+          } else if (DO_K) {
+            auto pair_col = [&](const int col, const int oa, const int ob) {
+              const double2 *base = REC + col;
+#pragma unroll 1
+              for (int q = 0; q < L3_QH; ++q) {
+                const double2 *rq = base + q * NARR * L3_NCOLP;
+                const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
+                const double2 b0 = rq[ob], b1 = rq[ob + L3_NCOLP], b2 = rq[ob + 2 * L3_NCOLP];
+                const double2 cc = rq[CC];
+                const double blo[3] = {b0.x, b0.y, b1.x}, bhi[3] = {b1.y, b2.x, b2.y};
+                const double plo[3] = {cc.x * a0.x, cc.x * a0.y, cc.x * a1.x}, mlo[3] = {cc.y * a0.x, cc.y * a0.y, cc.y * a1.x};
+                const double phi[3] = {cc.x * a1.y, cc.x * a2.x, cc.x * a2.y}, mhi[3] = {cc.y * a1.y, cc.y * a2.x, cc.y * a2.y};
+                l3_acc(Kd, plo, mlo, blo); l3_acc(Ku, plo, mlo, bhi);
+                l3_acc(Kl, phi, mhi, blo); l3_acc(Kn, phi, mhi, bhi);
+              }
+            };
+            pair_col(c0, oa0, ob0);
+            if (two) pair_col(c1, 0, ob1);
           }
+        }
+        if (P.prof) tB += clock64() - tb0;
+        if (half == 0) {
+          if (iss && pend >= 0) flush_row(pend);
+          pend = -1;
+          __threadfence_block(); __syncthreads();      // the records are rewritten by the second half
         }
       }
-      // The fence is required, not decoration: without it the phase-B loads of some warps returned the previous
-      // interval's records although every STS above precedes this barrier in program order (found on a 3 x 2 x 3-node
-      // mesh by the parity tests; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
-      __threadfence_block();
-      __syncthreads();
-      const long long tp1 = P.prof ? clock64() : 0;
-      // ---------------- phase B: line pairs ----------------
+      // ---- interval i completes (A_i, B_i), (A_i, B_i+1), (A_i+1, B_i): with the two blocks carried from interval i-1 they
+      //      fill the rows of node plane i, direct and transposed ----
+      const long long tf0 = P.prof ? clock64() : 0;
+      l3_wait_all();      // node plane i+2 and the Laplacian parts are in; the carried blocks have left the scratch rewritten below
+      const long long tf1 = P.prof ? clock64() : 0;
       if (on) {
+        const int tslot = (i - ifirst) * 3 * L3_NPT;
+        double *lapu = P.lap + s_lapoff + tid;
+        double *cry = P.carry + (size_t)blockIdx.x * 18 * L3_THREADS + tid;
+        const int skip = i > 0 ? 3 : 0;      // the dx = -1 piece comes from the carry scratch
         if (ptype == 0) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (colv[k] == L3_ZCOL) continue;
-            const double2 *base = REC + colv[k] + offA[k];
-#pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-              const double2 *rq = base + q * NARR * L3_NCOLP;
-              const double2 a0 = rq[0], a1 = rq[L3_NCOLP], a2 = rq[2 * L3_NCOLP];
-              const double2 cc = rq[12 * L3_NCOLP - offA[k]];
-              const double glo[3] = {a0.x, a0.y, a1.x}, ghi[3] = {a1.y, a2.x, a2.y};
-              if (DO_K) {
-                const double plo[3] = {cc.x * glo[0], cc.x * glo[1], cc.x * glo[2]};
-                const double mlo[3] = {cc.y * glo[0], cc.y * glo[1], cc.y * glo[2]};
-                const double phi[3] = {cc.x * ghi[0], cc.x * ghi[1], cc.x * ghi[2]};
-                // (lo, lo) and (hi, hi): symmetric, K_ik = 2 cs g_i g_k
-                Kd[0] = fma(plo[0], glo[0], Kd[0]); Kd[1] = fma(plo[1], glo[1], Kd[1]); Kd[2] = fma(plo[2], glo[2], Kd[2]);
-                Kd[3] = fma(plo[0], glo[1], Kd[3]); Kd[4] = fma(plo[0], glo[2], Kd[4]); Kd[5] = fma(plo[1], glo[2], Kd[5]);
-                Kn[0] = fma(phi[0], ghi[0], Kn[0]); Kn[1] = fma(phi[1], ghi[1], Kn[1]); Kn[2] = fma(phi[2], ghi[2], Kn[2]);
-                Kn[3] = fma(phi[0], ghi[1], Kn[3]); Kn[4] = fma(phi[0], ghi[2], Kn[4]); Kn[5] = fma(phi[1], ghi[2], Kn[5]);
-                l3_acc(Ku, plo, mlo, ghi);
-              }
-              if (DO_R && !LAP_BUILD) {
-                const double2 t0 = rq[13 * L3_NCOLP - offA[k]], t1 = rq[14 * L3_NCOLP - offA[k]], t2 = rq[15 * L3_NCOLP - offA[k]];
-                // tau = {xx, yy | zz, xy | xz, yz}
-                fd[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], fd[0])));
-                fd[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], fd[1])));
-                fd[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], fd[2])));
-                fn[0] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], fn[0])));
-                fn[1] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], fn[1])));
-                fn[2] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], fn[2])));
-              }
-            }
-          }
-        } else {
-          auto pair_col = [&](const int col, const int oa, const int ob) {
-            const double2 *base = REC + col;
-#pragma unroll 1
-            for (int q = 0; q < 8; ++q) {
-              const double2 *rq = base + q * NARR * L3_NCOLP;
-              const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
-              const double2 b0 = rq[ob], b1 = rq[ob + L3_NCOLP], b2 = rq[ob + 2 * L3_NCOLP];
-              const double2 cc = rq[12 * L3_NCOLP];
-              const double blo[3] = {b0.x, b0.y, b1.x}, bhi[3] = {b1.y, b2.x, b2.y};
-              const double plo[3] = {cc.x * a0.x, cc.x * a0.y, cc.x * a1.x}, mlo[3] = {cc.y * a0.x, cc.y * a0.y, cc.y * a1.x};
-              const double phi[3] = {cc.x * a1.y, cc.x * a2.x, cc.x * a2.y}, mhi[3] = {cc.y * a1.y, cc.y * a2.x, cc.y * a2.y};
-              l3_acc(Kd, plo, mlo, blo); l3_acc(Ku, plo, mlo, bhi);
-              l3_acc(Kl, phi, mhi, blo); l3_acc(Kn, phi, mhi, bhi);
-            }
-          };
           if (DO_K) {
-            pair_col(colv[0], offA[0], offB[0]);
-            if (two) pair_col(colv[1], offA[1], offB[1]);
+            double Fu[3][3];
+            l3_full(Ku, 0.0, Fu);
+            if (LAP_BUILD) {
+              lapu[tslot] = 2.0 * (Kd[0] + Kd[1] + Kd[2]); lapu[tslot + L3_NPT] = Fu[0][0] + Fu[1][1] + Fu[2][2]; lapu[tslot + 2 * L3_NPT] = 0.0;
+            } else {
+              const double l0 = mu * LAPS[tid], l1 = mu * LAPS[L3_THREADS + tid];
+              Fu[0][0] += l1; Fu[1][1] += l1; Fu[2][2] += l1;
+              if (store) {
+                const double D[3][3] = {{fma(2.0, Kd[0], l0), 2.0 * Kd[3], 2.0 * Kd[4]}, {2.0 * Kd[3], fma(2.0, Kd[1], l0), 2.0 * Kd[5]},
+                                        {2.0 * Kd[4], 2.0 * Kd[5], fma(2.0, Kd[2], l0)}};
+                int rs;
+                double *p = piece(geoA, i, rs) + skip;
+#pragma unroll
+                for (int r = 0; r < 3; ++r, p += rs) l3_sts6(p, D[r][0], D[r][1], D[r][2], Fu[r][0], Fu[r][1], Fu[r][2]);
+              }
+              // (A_i+1, A_i) = (A_i, A_i+1)^T waits for the row of node i+1
+#pragma unroll
+              for (int k = 0; k < 9; ++k) cry[k * L3_THREADS] = Fu[k % 3][k / 3];
+            }
           }
-        }
-        // ---- interval i completes (A_i, B_i), (A_i, B_i+1), (A_i+1, B_i): store them, direct and transposed ----
-        if (store) {
-          if (ptype == 0) {
-            if (DO_K) {
-              double Fu[3][3];
-              l3_full(Ku, 0.0, Fu);
-              if (LAP_BUILD) {
-                double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
-                lq[0] = 2.0 * (Kd[0] + Kd[1] + Kd[2]); lq[L3_NPT] = Fu[0][0] + Fu[1][1] + Fu[2][2]; lq[2 * L3_NPT] = 0.0;
-              } else {
-                const double l0 = mu * lp0, l1 = mu * lp1;
-                Fu[0][0] += l1; Fu[1][1] += l1; Fu[2][2] += l1;
-                const double d00 = fma(2.0, Kd[0], l0), d11 = fma(2.0, Kd[1], l0), d22 = fma(2.0, Kd[2], l0);
-                const double d01 = 2.0 * Kd[3], d02 = 2.0 * Kd[4], d12 = 2.0 * Kd[5];
-                const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
-                l3_st6(ra.p, d00, d01, d02, Fu[0][0], Fu[0][1], Fu[0][2]);
-                l3_st6(ra.p + ra.stride, d01, d11, d12, Fu[1][0], Fu[1][1], Fu[1][2]);
-                l3_st6(ra.p + 2 * ra.stride, d02, d12, d22, Fu[2][0], Fu[2][1], Fu[2][2]);
-                const L3Row rn = l3_row(P.vals, lbA, nlA, rA, i + 1, nxm1, -1);
-                l3_st3(rn.p, Fu[0][0], Fu[1][0], Fu[2][0]);
-                l3_st3(rn.p + rn.stride, Fu[0][1], Fu[1][1], Fu[2][1]);
-                l3_st3(rn.p + 2 * rn.stride, Fu[0][2], Fu[1][2], Fu[2][2]);
+          if (DO_R && !LAP_BUILD && store) l3_st3(P.R + 3 * ((int64_t)nodeA0 + i), fd[0], fd[1], fd[2]);
+        } else if (DO_K) {
+          double Fd[3][3], Fu[3][3], Fl[3][3];
+          if (LAP_BUILD) {
+            l3_full(Kd, 0.0, Fd); l3_full(Ku, 0.0, Fu); l3_full(Kl, 0.0, Fl);
+            lapu[tslot] = Fd[0][0] + Fd[1][1] + Fd[2][2]; lapu[tslot + L3_NPT] = Fu[0][0] + Fu[1][1] + Fu[2][2];
+            lapu[tslot + 2 * L3_NPT] = Fl[0][0] + Fl[1][1] + Fl[2][2];
+          } else {
+            l3_full(Kd, mu * LAPS[tid], Fd); l3_full(Ku, mu * LAPS[L3_THREADS + tid], Fu); l3_full(Kl, mu * LAPS[2 * L3_THREADS + tid], Fl);
+            if (store) {
+              if (geoA >= 0) {
+                int rs;
+                double *p = piece(geoA, i, rs) + skip;
+#pragma unroll
+                for (int r = 0; r < 3; ++r, p += rs) l3_sts6(p, Fd[r][0], Fd[r][1], Fd[r][2], Fu[r][0], Fu[r][1], Fu[r][2]);
+              }
+              if (geoB >= 0) {
+                int rs;
+                double *p = piece(geoB, i, rs) + skip;
+#pragma unroll
+                for (int r = 0; r < 3; ++r, p += rs) l3_sts6(p, Fd[0][r], Fd[1][r], Fd[2][r], Fl[0][r], Fl[1][r], Fl[2][r]);
               }
             }
-            if (DO_R && !LAP_BUILD) l3_st3(P.R + 3 * (nodeA0 + i), fd[0], fd[1], fd[2]);
-          } else if (DO_K) {
-            double Fd[3][3], Fu[3][3], Fl[3][3];
-            l3_full(Kd, mu * lp0, Fd); l3_full(Ku, mu * lp1, Fu); l3_full(Kl, mu * lp2, Fl);
-            if (LAP_BUILD) {
-              double *lq = lapu + (int64_t)(i - i0) * 3 * L3_NPT;
-              lq[0] = Fd[0][0] + Fd[1][1] + Fd[2][2]; lq[L3_NPT] = Fu[0][0] + Fu[1][1] + Fu[2][2]; lq[2 * L3_NPT] = Fl[0][0] + Fl[1][1] + Fl[2][2];
-            } else {
-              if (wd) {
-                const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
+            // (A_i+1, B_i) waits for the row of A's node i+1, (B_i+1, A_i) = (A_i, B_i+1)^T for the row of B's
+            if (geoA >= 0) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r) l3_st6(ra.p + r * ra.stride, Fd[r][0], Fd[r][1], Fd[r][2], Fu[r][0], Fu[r][1], Fu[r][2]);
-                const L3Row rn = l3_row(P.vals, lbA, nlA, rA, i + 1, nxm1, -1);
+              for (int k = 0; k < 9; ++k) cry[k * L3_THREADS] = Fl[k / 3][k % 3];
+            }
+            if (geoB >= 0) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r) l3_st3(rn.p + r * rn.stride, Fl[r][0], Fl[r][1], Fl[r][2]);
-              }
-              if (wm) {
-                const L3Row rb = l3_row(P.vals, lbB, nlB, rB, i, nxm1, 0);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) l3_st6(rb.p + r * rb.stride, Fd[0][r], Fd[1][r], Fd[2][r], Fl[0][r], Fl[1][r], Fl[2][r]);
-                const L3Row rn = l3_row(P.vals, lbB, nlB, rB, i + 1, nxm1, -1);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) l3_st3(rn.p + r * rn.stride, Fu[0][r], Fu[1][r], Fu[2][r]);
-              }
+              for (int k = 0; k < 9; ++k) cry[(9 + k) * L3_THREADS] = Fu[k % 3][k / 3];
             }
           }
         }
@@ -432,54 +578,85 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
 #pragma unroll
         for (int k = 0; k < 3; ++k) { fd[k] = fn[k]; fn[k] = 0.0; }
       }
-      const long long tp2 = P.prof ? clock64() : 0;
-      l3_wait_all();
+      const long long tf2 = P.prof ? clock64() : 0;
+      if (STAGE) l3_fence_async();
       __threadfence_block();
       __syncthreads();
-      if (P.prof && lane == 0) {      // per warp: phase A (to the barrier), own phase-B work, wait for the slowest warp
+      const long long tf3 = P.prof ? clock64() : 0;
+      // the rows are complete; their hand-off to the TMA unit waits for the idle time of the next interval (see the issuers above)
+      pend = (STAGE && store) ? i : -1;
+      if (P.prof && lane == 0) {      // per warp: own phase-B work; warp 0 also: phase A to its barrier, the rest, cp.async wait, finalize, last barrier, row hand-off
         const long long tp3 = clock64();
-        if (tid == 0) { atomicAdd(P.prof + 0, (unsigned long long)(tp1 - tp0)); atomicAdd(P.prof + 1, (unsigned long long)(tp3 - tp1)); atomicAdd(P.prof + 2, 1ull); }
-        atomicAdd(P.prof + 8 + warp, (unsigned long long)(tp2 - tp1));
+        atomicAdd(P.prof + 8 + warp, (unsigned long long)tB);
+        if (tid == 0) {
+          atomicAdd(P.prof + 0, (unsigned long long)tA); atomicAdd(P.prof + 1, (unsigned long long)(tp3 - tp0 - tA)); atomicAdd(P.prof + 2, 1ull);
+          atomicAdd(P.prof + 3, (unsigned long long)(tf1 - tf0)); atomicAdd(P.prof + 4, (unsigned long long)(tf2 - tf1));
+          atomicAdd(P.prof + 5, (unsigned long long)(tf3 - tf2)); atomicAdd(P.prof + 6, (unsigned long long)(tp3 - tf3));
+        }
       }
     }
-    // ---- the last node of the line: its diagonal-offset block has no further interval ----
-    if (on && i1 == nxm1) {
+    if (iss && pend >= 0) flush_row(pend);       // the unit's last interval: hand its rows over now
+    pend = -1;
+    // ---- the last node of the line: its row has no further interval ----
+    if (i1 == nxm1) {
       const int i = nxm1;
-      double lp0 = 0.0;
-      if (!LAP_BUILD && DO_K) lp0 = lapu[(int64_t)(i1 - i0) * 3 * L3_NPT];
-      if (ptype == 0) {
-        if (DO_K) {
+      if (STAGE) {
+        if (isslot) l3_bulk_wait_read();
+        __syncthreads();
+      }
+      if (on) {
+        double lp0 = 0.0;
+        const int tslot = (i1 - ifirst) * 3 * L3_NPT;
+        double *lapu = P.lap + s_lapoff + tid;
+        if (!LAP_BUILD && DO_K) lp0 = lapu[tslot];
+        if (STAGE && !P.dbg_nostore) { fetch_carry(i); l3_commit(); }      // the dx = -1 pieces
+        if (ptype == 0) {
+          if (DO_K) {
+            if (LAP_BUILD) {
+              lapu[tslot] = 2.0 * (Kd[0] + Kd[1] + Kd[2]);
+            } else if (!P.dbg_nostore) {
+              const double l0 = mu * lp0;
+              int rs;
+              double *p = piece(geoA, i, rs) + 3;
+              l3_sts3(p, fma(2.0, Kd[0], l0), 2.0 * Kd[3], 2.0 * Kd[4]);
+              l3_sts3(p + rs, 2.0 * Kd[3], fma(2.0, Kd[1], l0), 2.0 * Kd[5]);
+              l3_sts3(p + 2 * rs, 2.0 * Kd[4], 2.0 * Kd[5], fma(2.0, Kd[2], l0));
+            }
+          }
+          if (DO_R && !LAP_BUILD && !P.dbg_nostore) l3_st3(P.R + 3 * ((int64_t)nodeA0 + i), fd[0], fd[1], fd[2]);
+        } else if (DO_K) {
+          double Fd[3][3];
+          l3_full(Kd, mu * lp0, Fd);
           if (LAP_BUILD) {
-            lapu[(int64_t)(i1 - i0) * 3 * L3_NPT] = 2.0 * (Kd[0] + Kd[1] + Kd[2]);
-          } else {
-            const double l0 = mu * lp0;
-            const double d00 = fma(2.0, Kd[0], l0), d11 = fma(2.0, Kd[1], l0), d22 = fma(2.0, Kd[2], l0);
-            const double d01 = 2.0 * Kd[3], d02 = 2.0 * Kd[4], d12 = 2.0 * Kd[5];
-            const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
-            l3_st3(ra.p, d00, d01, d02); l3_st3(ra.p + ra.stride, d01, d11, d12); l3_st3(ra.p + 2 * ra.stride, d02, d12, d22);
+            lapu[tslot] = Fd[0][0] + Fd[1][1] + Fd[2][2];
+          } else if (!P.dbg_nostore) {
+            if (geoA >= 0) {
+              int rs;
+              double *p = piece(geoA, i, rs) + 3;
+#pragma unroll
+              for (int r = 0; r < 3; ++r, p += rs) l3_sts3(p, Fd[r][0], Fd[r][1], Fd[r][2]);
+            }
+            if (geoB >= 0) {
+              int rs;
+              double *p = piece(geoB, i, rs) + 3;
+#pragma unroll
+              for (int r = 0; r < 3; ++r, p += rs) l3_sts3(p, Fd[0][r], Fd[1][r], Fd[2][r]);
+            }
           }
         }
-        if (DO_R && !LAP_BUILD) l3_st3(P.R + 3 * (nodeA0 + i), fd[0], fd[1], fd[2]);
-      } else if (DO_K) {
-        double Fd[3][3];
-        l3_full(Kd, mu * lp0, Fd);
-        if (LAP_BUILD) {
-          lapu[(int64_t)(i1 - i0) * 3 * L3_NPT] = Fd[0][0] + Fd[1][1] + Fd[2][2];
-        } else {
-          if (wd) {
-            const L3Row ra = l3_row(P.vals, lbA, nlA, rA, i, nxm1, 0);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) l3_st3(ra.p + r * ra.stride, Fd[r][0], Fd[r][1], Fd[r][2]);
-          }
-          if (wm) {
-            const L3Row rb = l3_row(P.vals, lbB, nlB, rB, i, nxm1, 0);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) l3_st3(rb.p + r * rb.stride, Fd[0][r], Fd[1][r], Fd[2][r]);
-          }
-        }
+        l3_wait_all();
+      }
+      if (STAGE) {
+        l3_fence_async();
+        __threadfence_block();
+        __syncthreads();
+        if (iss && !P.dbg_nostore) flush_row(i);
       }
     }
+    // the staging image is next rewritten at the end of the next unit's first interval; its issuers wait for these copies
+    // in the second half of that interval (above), and the barrier that follows holds everyone else back
   }
+  if (isslot) l3_bulk_wait_read();
   // the last CTA to run out of units rearms the counters for the next launch
   if (tid == 0) {
     __threadfence();
@@ -498,11 +675,12 @@ void nls_lines3_free(nls_context *h) {
   if (p.d_lapoff) cudaFree(p.d_lapoff);
   if (p.d_lap) cudaFree(p.d_lap);
   if (p.d_counter) cudaFree(p.d_counter);
+  if (p.d_carry) cudaFree(p.d_carry);
   p = Lines3Plan();
 }
 
-static size_t lines3_smem(bool do_r) {
-  return (size_t)8 * (do_r ? 16 : 13) * L3_NCOLP * 16 + (size_t)3 * 6 * L3_NLCP * 8 + 200 * 8;
+static size_t lines3_smem(bool) {   // one layout for every instantiation: staging image, records (16 arrays), node ring, tables
+  return (size_t)L3_NL * L3_SLOT * 8 + (size_t)L3_QH * 16 * L3_NCOLP * 16 + (size_t)2 * 6 * L3_NLCP * 8 + (size_t)3 * L3_THREADS * 8 + 200 * 8;
 }
 
 // Detects grid topology (x-fastest lines, planes with arbitrary base ids: full grids and slab-local meshes), builds the
@@ -587,7 +765,7 @@ int nls_lines3_build(nls_context *h) {
   for (int64_t z0 = 0; z0 < nzp; z0 += L3_TZ)
     for (int64_t y0 = 0; y0 < ny; y0 += L3_TY) {
       bool work = false;
-      for (int64_t z = z0; z < std::min<int64_t>(z0 + L3_TZ, nzp); ++z) work = work || pown[z] || (z + 1 < nzp && pown[z + 1]);
+      for (int64_t z = z0; z < std::min<int64_t>(z0 + L3_TZ, nzp); ++z) work = work || pown[z];   // a tile writes the rows of its own lines only
       if (work) ++ntiles;
     }
   if (ntiles == 0) return NLS_OK;
@@ -598,7 +776,7 @@ int nls_lines3_build(nls_context *h) {
     for (int64_t y0 = 0; y0 < ny; y0 += L3_TY) {
       int64_t nlines = 0;
       for (int64_t z = z0; z < std::min<int64_t>(z0 + L3_TZ, nzp); ++z)
-        if (pown[z] || (z + 1 < nzp && pown[z + 1])) nlines += std::min<int64_t>(L3_TY, ny - y0);
+        if (pown[z]) nlines += std::min<int64_t>(L3_TY, ny - y0);
       if (nlines == 0) continue;
       for (int64_t ch = 0; ch < nch; ++ch) {
         const int64_t i0 = ch * clen, i1 = std::min(nxi, i0 + clen);
@@ -612,13 +790,14 @@ int nls_lines3_build(nls_context *h) {
   for (size_t k = 0; k < units.size(); ++k) {
     uv[k] = units[k].second;
     lapoff[k] = lapn;
-    lapn += (int64_t)(uv[k].w - uv[k].z + 1) * 3 * L3_NPT;
+    lapn += (int64_t)(uv[k].w - (uv[k].z > 0 ? uv[k].z - 1 : 0) + 1) * 3 * L3_NPT;   // warm-up interval included
   }
   p.nx = (int)nx; p.ny = (int)ny; p.nzp = (int)nzp; p.nunits = (int)uv.size(); p.lap_doubles = lapn;
 #define UP(field, vec) do { NLS_CUDA(h, cudaMalloc((void **)&p.field, sizeof(vec[0]) * vec.size())); \
   NLS_CUDA(h, cudaMemcpyAsync(p.field, vec.data(), sizeof(vec[0]) * vec.size(), cudaMemcpyHostToDevice, h->stream)); } while (0)
   UP(d_pbase, pbase); UP(d_pown, pown); UP(d_info, info); UP(d_units, uv); UP(d_lapoff, lapoff);
 #undef UP
+  NLS_CUDA(h, cudaMalloc((void **)&p.d_carry, sizeof(double) * 18 * L3_THREADS * (size_t)h->sm_count));
   NLS_CUDA(h, cudaMalloc((void **)&p.d_counter, 2 * sizeof(unsigned)));
   NLS_CUDA(h, cudaMemsetAsync(p.d_counter, 0, 2 * sizeof(unsigned), h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -650,7 +829,7 @@ int nls_launch_lines3(nls_context *h, bool want_r, bool want_k) {
   a.nx = p.nx; a.ny = p.ny; a.nzp = p.nzp; a.nunits = p.nunits;
   a.pbase = p.d_pbase; a.pown = p.d_pown; a.info = reinterpret_cast<const L3Line *>(p.d_info);
   a.units = reinterpret_cast<const int4 *>(p.d_units); a.lapoff = p.d_lapoff; a.lap = p.d_lap;
-  a.coords = h->d_coords; a.U = h->d_U; a.R = h->d_R; a.vals = h->d_vals; a.counter = p.d_counter;
+  a.coords = h->d_coords; a.U = h->d_U; a.R = h->d_R; a.vals = h->d_vals; a.counter = p.d_counter; a.carry = p.d_carry;
   a.dbg_nostore = h->opt_profile_phases == 2;
   a.prof = h->opt_profile_phases ? reinterpret_cast<unsigned long long *>(h->d_prof) : nullptr;
   const unsigned grid = (unsigned)std::min<int64_t>(p.nunits, h->sm_count);

@@ -97,6 +97,7 @@ struct Lines3Plan {
   int64_t *d_lapoff = nullptr;
   double *d_lap = nullptr;
   unsigned *d_counter = nullptr;
+  double *d_carry = nullptr;       // [sm_count][18][384] per-CTA carry scratch of the line kernel
 };
 
 // ---- device control block of the PCG loop (lives in device memory) ----
