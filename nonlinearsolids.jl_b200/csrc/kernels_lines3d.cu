@@ -201,15 +201,12 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
   // corner pair (dy' + 2 dz') of line A and of line B inside the first and the second common element column
   const int oa0 = (ptype == 1 ? 2 : (ptype == 4 ? 0 : 1)) * PR, ob0 = (ptype == 2 ? 2 : 3) * PR, ob1 = (ptype == 1 ? 1 : 2) * PR;   // oa1 = 0
   // row issuers: cp.async.bulk blocks its issuer while the TMA queue (about eight requests) is full, and one interval's rows
-  // keep the SM's store path busy for about 4 k cycles (profiles/r2_ubench_bulk.txt). The hand-off therefore sits where
-  // warps would otherwise idle: the five warps of one-column pairs finish the first half of phase B long before the others,
-  // and issue the previous interval's 64 rows there (13 lines per warp).
+  // keep the SM's store path busy for about 4 k cycles (32 B per clock; profiles/r2_ubench_bulk.txt). The hand-off therefore
+  // sits where warps idle anyway: warp 11 holds none of the 324 phase-A items and issues 24 rows during the first half of
+  // phase A; the five warps of one-column pairs finish the first half of phase B long before the others and issue 8 rows each.
   const int oord = (warp == 4) ? 0 : (warp == 5) ? 1 : (warp == 8) ? 2 : (warp == 9) ? 3 : (warp == 10) ? 4 : -1;
-  const int iline = oord * 13 + lane;
-  const bool isslot = STAGE && oord >= 0 && lane < 13 && iline < L3_NL;
-  double cv = 0.0;                 // issuer: the odd trailing double of the last copy, waiting for the next
-  bool have_cv = false;
-
+  const int iline = (warp == 11) ? lane : 24 + oord * 8 + lane;
+  const bool isslot = STAGE && ((warp == 11 && lane < 24) || (oord >= 0 && lane < 8));
   for (;;) {
     if (tid == 0) { const int uu = (int)atomicAdd(P.counter, 1u); s_unit = uu; s_lapoff = uu < P.nunits ? (long long)P.lapoff[uu] : 0ll; }
     __syncthreads();
@@ -259,15 +256,12 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       rs = nl * 3 * w;
       return STG + (geo & 0xffff) + par + ((geo >> 20) & 15) * w * 3;
     };
-    // issuer state
+    // issuer: does its line exist and belong to this rank?
     bool iss = false;
-    int64_t ilb = 0;
-    int inl = 0;
     if (isslot) {
       const int y = y0 + (iline & (L3_TY - 1)), z = z0 + iline / L3_TY;
-      if (y < ny && z < nzp && P.pown[z] != 0) { const L3Line a = P.info[z * ny + y]; iss = true; ilb = a.lb; inl = a.nl; }
+      iss = y < ny && z < nzp && P.pown[z] != 0;
     }
-    have_cv = false;
     int pend = -1;                 // node plane whose rows still wait for their hand-off to the TMA unit
 
     // accumulators: Kd = (A_i, B_i), Ku = (A_i, B_i+1), Kl = (A_i+1, B_i), Kn = (A_i+1, B_i+1); self: Kd, Kn hold 6 symmetric sums.
@@ -308,20 +302,22 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       }
     };
 
-    // the row of node plane ip of line `iline`: 16-byte aligned part by one bulk copy, odd ends carried or stored singly
+    // the row of node plane ip of line `iline`: 16-byte aligned part by one bulk copy. A row that starts on an odd double
+    // takes the last double of the previous row with it (parked in the slot's spare double 245 when that row was handed over);
+    // the first and the last row of the unit store their odd end singly. Stateless: everything follows from the line's table.
     auto flush_row = [&](const int ip) {
-      const L3RowGeo g = l3_geo((int)(ilb & 1), inl, ip, nxm1);
-      const int64_t g0 = 9 * (ilb + (int64_t)inl * (ip == 0 ? 0 : 3 * ip - 1));   // first double of the row in vals
-      double *sm = STG + iline * L3_SLOT;                                           // the row sits at sm[par .. par + len)
-      int lo = g.par, hi = g.par + 9 * inl * g.w;
+      const L3Line a = P.info[(z0 + iline / L3_TY) * ny + y0 + (iline & (L3_TY - 1))];
+      const L3RowGeo g = l3_geo((int)(a.lb & 1), a.nl, ip, nxm1);
+      const int64_t g0 = 9 * (a.lb + (int64_t)a.nl * (ip == 0 ? 0 : 3 * ip - 1));   // first double of the row in vals
+      double *sm = STG + iline * L3_SLOT;                                              // the row sits at sm[par .. par + len)
+      int lo = g.par, hi = g.par + 9 * a.nl * g.w;
       if (lo) {
-        if (have_cv) { sm[0] = cv; lo = 0; l3_fence_async(); }
+        if (ip > i0) { sm[0] = sm[L3_SLOT - 1]; lo = 0; l3_fence_async(); }
         else { l3_stg1(P.vals + g0, sm[1]); lo = 2; }
       }
-      have_cv = false;
       if (hi & 1) {
         --hi;
-        if (ip < ilast) { cv = sm[hi]; have_cv = true; }
+        if (ip < ilast) sm[L3_SLOT - 1] = sm[hi];
         else l3_stg1(P.vals + (g0 - g.par + hi), sm[hi]);
       }
       if (hi > lo) l3_bulk_store(P.vals + (g0 - g.par + lo), sm + lo, (unsigned)(hi - lo) * 8u);
@@ -345,6 +341,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       for (int half = 0; half < 2; ++half) {
         const long long ta0 = P.prof ? clock64() : 0;
         // ---------------- phase A: quadrature-point records 4 half .. 4 half + 3 of interval i ----------------
+        if (half == 0 && iss && pend >= 0 && warp == 11) flush_row(pend);    // warp 11 first: it has no phase-A item
         if (tid < L3_QH * L3_NCOL) {
           const int slo = i & 1, shi = slo ^ 1;
           const int ql = tid / L3_NCOL, col = tid - ql * L3_NCOL, q = half * L3_QH + ql;
@@ -449,7 +446,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
             auto self_col = [&](const int col, const int oa) {
               if (col == L3_ZCOL) return;
               const double2 *base = REC + col;
-#pragma unroll 1
+#pragma unroll 2
               for (int q = 0; q < L3_QH; ++q) {
                 const double2 *rq = base + q * NARR * L3_NCOLP;
                 const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
@@ -480,28 +477,29 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
             };
             self_col(c0, 3 * PR); self_col(c1, 2 * PR); self_col(c2, PR); self_col(c3, 0);
           } else if (DO_K) {
-            auto pair_col = [&](const int col, const int oa, const int ob) {
-              const double2 *base = REC + col;
+            // one loop over the (column, point) pairs of the pair's one or two columns; the A-side operands and the scalars
+            // of the next pair are loaded as soon as the products that consume the current ones have been formed
+            const int n = two ? 2 * L3_QH : L3_QH;
+            const double2 *rq = REC + c0;
+            int oa = oa0, ob = ob0;
+            double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP], cc = rq[CC];
 #pragma unroll 1
-              for (int q = 0; q < L3_QH; ++q) {
-                const double2 *rq = base + q * NARR * L3_NCOLP;
-                const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
-                const double2 b0 = rq[ob], b1 = rq[ob + L3_NCOLP], b2 = rq[ob + 2 * L3_NCOLP];
-                const double2 cc = rq[CC];
-                const double blo[3] = {b0.x, b0.y, b1.x}, bhi[3] = {b1.y, b2.x, b2.y};
-                const double plo[3] = {cc.x * a0.x, cc.x * a0.y, cc.x * a1.x}, mlo[3] = {cc.y * a0.x, cc.y * a0.y, cc.y * a1.x};
-                const double phi[3] = {cc.x * a1.y, cc.x * a2.x, cc.x * a2.y}, mhi[3] = {cc.y * a1.y, cc.y * a2.x, cc.y * a2.y};
-                l3_acc(Kd, plo, mlo, blo); l3_acc(Ku, plo, mlo, bhi);
-                l3_acc(Kl, phi, mhi, blo); l3_acc(Kn, phi, mhi, bhi);
-              }
-            };
-            pair_col(c0, oa0, ob0);
-            if (two) pair_col(c1, 0, ob1);
+            for (int it = 0; it < n; ++it) {
+              const double2 b0 = rq[ob], b1 = rq[ob + L3_NCOLP], b2 = rq[ob + 2 * L3_NCOLP];
+              const double plo[3] = {cc.x * a0.x, cc.x * a0.y, cc.x * a1.x}, mlo[3] = {cc.y * a0.x, cc.y * a0.y, cc.y * a1.x};
+              const double phi[3] = {cc.x * a1.y, cc.x * a2.x, cc.x * a2.y}, mhi[3] = {cc.y * a1.y, cc.y * a2.x, cc.y * a2.y};
+              if (it + 1 == L3_QH) { rq = REC + c1; oa = 0; ob = ob1; }       // second column (read past the end only when n == 4: the zero column)
+              else rq += NARR * L3_NCOLP;
+              if (it + 1 < n) { a0 = rq[oa]; a1 = rq[oa + L3_NCOLP]; a2 = rq[oa + 2 * L3_NCOLP]; cc = rq[CC]; }
+              const double blo[3] = {b0.x, b0.y, b1.x}, bhi[3] = {b1.y, b2.x, b2.y};
+              l3_acc(Kd, plo, mlo, blo); l3_acc(Ku, plo, mlo, bhi);
+              l3_acc(Kl, phi, mhi, blo); l3_acc(Kn, phi, mhi, bhi);
+            }
           }
         }
         if (P.prof) tB += clock64() - tb0;
         if (half == 0) {
-          if (iss && pend >= 0) flush_row(pend);
+          if (iss && pend >= 0 && warp != 11) flush_row(pend);
           pend = -1;
           __threadfence_block(); __syncthreads();      // the records are rewritten by the second half
         }
