@@ -202,11 +202,11 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
   const int oa0 = (ptype == 1 ? 2 : (ptype == 4 ? 0 : 1)) * PR, ob0 = (ptype == 2 ? 2 : 3) * PR, ob1 = (ptype == 1 ? 1 : 2) * PR;   // oa1 = 0
   // row issuers: cp.async.bulk blocks its issuer while the TMA queue (about eight requests) is full, and one interval's rows
   // keep the SM's store path busy for about 4 k cycles (32 B per clock; profiles/r2_ubench_bulk.txt). The hand-off therefore
-  // sits where warps idle anyway: warp 11 holds none of the 324 phase-A items and issues 24 rows during the first half of
-  // phase A; the five warps of one-column pairs finish the first half of phase B long before the others and issue 8 rows each.
+  // sits where warps idle anyway: warp 11 holds none of the 324 phase-A items and issues 32 rows during the first half of
+  // phase A; the five warps of one-column pairs finish the first half of phase B long before the others and issue 6-7 rows each.
   const int oord = (warp == 4) ? 0 : (warp == 5) ? 1 : (warp == 8) ? 2 : (warp == 9) ? 3 : (warp == 10) ? 4 : -1;
-  const int iline = (warp == 11) ? lane : 24 + oord * 8 + lane;
-  const bool isslot = STAGE && ((warp == 11 && lane < 24) || (oord >= 0 && lane < 8));
+  const int iline = (warp == 11) ? lane : 32 + oord * 7 + lane;
+  const bool isslot = STAGE && (warp == 11 || (oord >= 0 && lane < 7 && iline < L3_NL));
   for (;;) {
     if (tid == 0) { const int uu = (int)atomicAdd(P.counter, 1u); s_unit = uu; s_lapoff = uu < P.nunits ? (long long)P.lapoff[uu] : 0ll; }
     __syncthreads();
