@@ -150,7 +150,7 @@ __device__ __forceinline__ L3RowGeo l3_geo(const int lbpar, const int nl, const 
   return g;
 }
 
-template <bool DO_R, bool DO_K, bool LAP_BUILD>
+template <bool DO_R, bool DO_K, bool LAP_BUILD, bool PROF>
 __global__ void __launch_bounds__(L3_THREADS, 1)
 k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_constant__ MatParams mp) {
   constexpr int NARR = DO_R ? 16 : 13;          // double2 arrays per quadrature point: 4 corner pairs x 3, scalars, stress x 3
@@ -238,13 +238,13 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         else if (ptype == 3) { c0 = col_of(y - 1, z); c1 = col_of(y, z); }
         else { c0 = col_of(y, z); }
         if (stA) {
-          const L3Line a = P.info[z * ny + y];
-          geoA = ((az * L3_TY + ay) * L3_SLOT) | (a.nl << 16) | ((int)a.rank[(dz + 1) * 3 + (dy + 1)] << 20) | ((int)(a.lb & 1) << 24);
+          const L3Line *a = P.info + (z * ny + y);
+          geoA = ((az * L3_TY + ay) * L3_SLOT) | (a->nl << 16) | ((int)a->rank[(dz + 1) * 3 + (dy + 1)] << 20) | ((int)(a->lb & 1) << 24);
           nodeA0 = P.pbase[z] + y * nx;
         }
         if (stB) {
-          const L3Line b = P.info[z2 * ny + y2];
-          geoB = (((az + dz) * L3_TY + ay + dy) * L3_SLOT) | (b.nl << 16) | ((int)b.rank[(1 - dz) * 3 + (1 - dy)] << 20) | ((int)(b.lb & 1) << 24);
+          const L3Line *b = P.info + (z2 * ny + y2);
+          geoB = (((az + dz) * L3_TY + ay + dy) * L3_SLOT) | (b->nl << 16) | ((int)b->rank[(1 - dz) * 3 + (1 - dy)] << 20) | ((int)(b->lb & 1) << 24);
         }
       }
     }
@@ -268,7 +268,8 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     // The two x-off-diagonal blocks finished in interval i-1, (A_i, B_i-1) and (A_i-1, B_i), belong to the rows of node plane
     // i: they wait in the CTA's carry scratch (global, L2-resident, one coalesced column per thread) -- not in registers --
     // and cp.async drops them into the staging image while the second half of interval i is computed.
-    double Kd[9], Ku[9], Kl[9], Kn[9], fd[3] = {0, 0, 0}, fn[3] = {0, 0, 0};
+    // (self pairs have no use for Kl: its first six entries carry their internal-force sums, node i and node i+1)
+    double Kd[9], Ku[9], Kl[9], Kn[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { Kd[k] = 0.0; Ku[k] = 0.0; Kl[k] = 0.0; Kn[k] = 0.0; }
     // carried blocks -> dx = -1 pieces of the rows of node plane ip (asynchronous; completion: l3_wait_all)
@@ -306,11 +307,13 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     // takes the last double of the previous row with it (parked in the slot's spare double 245 when that row was handed over);
     // the first and the last row of the unit store their odd end singly. Stateless: everything follows from the line's table.
     auto flush_row = [&](const int ip) {
-      const L3Line a = P.info[(z0 + iline / L3_TY) * ny + y0 + (iline & (L3_TY - 1))];
-      const L3RowGeo g = l3_geo((int)(a.lb & 1), a.nl, ip, nxm1);
-      const int64_t g0 = 9 * (a.lb + (int64_t)a.nl * (ip == 0 ? 0 : 3 * ip - 1));   // first double of the row in vals
-      double *sm = STG + iline * L3_SLOT;                                              // the row sits at sm[par .. par + len)
-      int lo = g.par, hi = g.par + 9 * a.nl * g.w;
+      const L3Line *a = P.info + ((z0 + iline / L3_TY) * ny + y0 + (iline & (L3_TY - 1)));
+      const int64_t alb = a->lb;
+      const int anl = a->nl;
+      const L3RowGeo g = l3_geo((int)(alb & 1), anl, ip, nxm1);
+      const int64_t g0 = 9 * (alb + (int64_t)anl * (ip == 0 ? 0 : 3 * ip - 1));   // first double of the row in vals
+      double *sm = STG + iline * L3_SLOT;                                            // the row sits at sm[par .. par + len)
+      int lo = g.par, hi = g.par + 9 * anl * g.w;
       if (lo) {
         if (ip > i0) { sm[0] = sm[L3_SLOT - 1]; lo = 0; l3_fence_async(); }
         else { l3_stg1(P.vals + g0, sm[1]); lo = 2; }
@@ -329,7 +332,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     __syncthreads();
 
     for (int i = ifirst; i < i1; ++i) {
-      const long long tp0 = P.prof ? clock64() : 0;
+      const long long tp0 = PROF ? clock64() : 0;
       long long tA = 0, tB = 0;
       const bool store = i >= i0 && !P.dbg_nostore;
       if (!LAP_BUILD && DO_K && on) {            // this interval's Laplacian parts -> shared memory, read when the blocks are finished
@@ -339,7 +342,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       l3_commit();
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        const long long ta0 = P.prof ? clock64() : 0;
+        const long long ta0 = PROF ? clock64() : 0;
         // ---------------- phase A: quadrature-point records 4 half .. 4 half + 3 of interval i ----------------
         if (half == 0 && iss && pend >= 0 && warp == 11) flush_row(pend);    // warp 11 first: it has no phase-A item
         if (tid < L3_QH * L3_NCOL) {
@@ -433,13 +436,13 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         // mesh by the parity tests; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
         __threadfence_block();
         __syncthreads();
-        if (P.prof) tA += clock64() - ta0;
+        if (PROF) tA += clock64() - ta0;
         if (half == 1) {
           load_plane(i + 2);       // both halves have read node plane i: its slot takes plane i+2
           if (STAGE && on && store && i > 0) fetch_carry(i);
           l3_commit();
         }
-        const long long tb0 = P.prof ? clock64() : 0;
+        const long long tb0 = PROF ? clock64() : 0;
         // ---------------- phase B: line pairs, four quadrature points ----------------
         if (on) {
           if (ptype == 0) {
@@ -466,12 +469,12 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
                 if (DO_R && !LAP_BUILD) {
                   const double2 t0 = rq[13 * L3_NCOLP], t1 = rq[14 * L3_NCOLP], t2 = rq[15 * L3_NCOLP];
                   // tau = {xx, yy | zz, xy | xz, yz}
-                  fd[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], fd[0])));
-                  fd[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], fd[1])));
-                  fd[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], fd[2])));
-                  fn[0] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], fn[0])));
-                  fn[1] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], fn[1])));
-                  fn[2] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], fn[2])));
+                  Kl[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], Kl[0])));
+                  Kl[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], Kl[1])));
+                  Kl[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], Kl[2])));
+                  Kl[3] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], Kl[3])));
+                  Kl[4] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], Kl[4])));
+                  Kl[5] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], Kl[5])));
                 }
               }
             };
@@ -497,7 +500,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
             }
           }
         }
-        if (P.prof) tB += clock64() - tb0;
+        if (PROF) tB += clock64() - tb0;
         if (half == 0) {
           if (iss && pend >= 0 && warp != 11) flush_row(pend);
           pend = -1;
@@ -506,9 +509,9 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       }
       // ---- interval i completes (A_i, B_i), (A_i, B_i+1), (A_i+1, B_i): with the two blocks carried from interval i-1 they
       //      fill the rows of node plane i, direct and transposed ----
-      const long long tf0 = P.prof ? clock64() : 0;
+      const long long tf0 = PROF ? clock64() : 0;
       l3_wait_all();      // node plane i+2 and the Laplacian parts are in; the carried blocks have left the scratch rewritten below
-      const long long tf1 = P.prof ? clock64() : 0;
+      const long long tf1 = PROF ? clock64() : 0;
       if (on) {
         const int tslot = (i - ifirst) * 3 * L3_NPT;
         double *lapu = P.lap + s_lapoff + tid;
@@ -536,7 +539,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
               for (int k = 0; k < 9; ++k) cry[k * L3_THREADS] = Fu[k % 3][k / 3];
             }
           }
-          if (DO_R && !LAP_BUILD && store) l3_st3(P.R + 3 * ((int64_t)nodeA0 + i), fd[0], fd[1], fd[2]);
+          if (DO_R && !LAP_BUILD && store) l3_st3(P.R + 3 * ((int64_t)nodeA0 + i), Kl[0], Kl[1], Kl[2]);
         } else if (DO_K) {
           double Fd[3][3], Fu[3][3], Fl[3][3];
           if (LAP_BUILD) {
@@ -572,18 +575,19 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         }
         // shift: node i+1 becomes node i
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { Kd[k] = Kn[k]; Kn[k] = 0.0; Ku[k] = 0.0; Kl[k] = 0.0; }
+        for (int k = 0; k < 9; ++k) { Kd[k] = Kn[k]; Kn[k] = 0.0; Ku[k] = 0.0; }
+        const bool self = ptype == 0;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { fd[k] = fn[k]; fn[k] = 0.0; }
+        for (int k = 0; k < 3; ++k) { Kl[k] = self ? Kl[3 + k] : 0.0; Kl[3 + k] = 0.0; Kl[6 + k] = 0.0; }
       }
-      const long long tf2 = P.prof ? clock64() : 0;
+      const long long tf2 = PROF ? clock64() : 0;
       if (STAGE) l3_fence_async();
       __threadfence_block();
       __syncthreads();
-      const long long tf3 = P.prof ? clock64() : 0;
+      const long long tf3 = PROF ? clock64() : 0;
       // the rows are complete; their hand-off to the TMA unit waits for the idle time of the next interval (see the issuers above)
       pend = (STAGE && store) ? i : -1;
-      if (P.prof && lane == 0) {      // per warp: own phase-B work; warp 0 also: phase A to its barrier, the rest, cp.async wait, finalize, last barrier, row hand-off
+      if (PROF && lane == 0) {      // per warp: own phase-B work; warp 0 also: phase A to its barrier, the rest, cp.async wait, finalize, last barrier, row hand-off
         const long long tp3 = clock64();
         atomicAdd(P.prof + 8 + warp, (unsigned long long)tB);
         if (tid == 0) {
@@ -621,7 +625,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
               l3_sts3(p + 2 * rs, 2.0 * Kd[4], 2.0 * Kd[5], fma(2.0, Kd[2], l0));
             }
           }
-          if (DO_R && !LAP_BUILD && !P.dbg_nostore) l3_st3(P.R + 3 * ((int64_t)nodeA0 + i), fd[0], fd[1], fd[2]);
+          if (DO_R && !LAP_BUILD && !P.dbg_nostore) l3_st3(P.R + 3 * ((int64_t)nodeA0 + i), Kl[0], Kl[1], Kl[2]);
         } else if (DO_K) {
           double Fd[3][3];
           l3_full(Kd, mu * lp0, Fd);
@@ -803,9 +807,9 @@ int nls_lines3_build(nls_context *h) {
   return NLS_OK;
 }
 
-template <bool R, bool K, bool LB>
+template <bool R, bool K, bool LB, bool PF = false>
 static void lines3_launch(nls_context *h, const L3Args &a, unsigned grid, size_t shm) {
-  k_asm_q1_3d_lines<R, K, LB><<<grid, L3_THREADS, shm, h->stream>>>(a, h->tabq, h->mat);
+  k_asm_q1_3d_lines<R, K, LB, PF><<<grid, L3_THREADS, shm, h->stream>>>(a, h->tabq, h->mat);
 }
 
 int nls_launch_lines3(nls_context *h, bool want_r, bool want_k) {
@@ -813,11 +817,12 @@ int nls_launch_lines3(nls_context *h, bool want_r, bool want_k) {
   if (!p.ok) NLS_FAIL(h, NLS_ERR_STATE, "lines assembly: no plan");
   if (!h->attr_lines3) {       // the kernel also holds a few bytes of static shared memory: ask for what it needs, not the opt-in maximum
     const int need = (int)lines3_smem(true);
-    cudaError_t e1 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-    cudaError_t e2 = cudaFuncSetAttribute(k_asm_q1_3d_lines<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-    cudaError_t e3 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-    cudaError_t e4 = cudaFuncSetAttribute(k_asm_q1_3d_lines<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    cudaError_t e1 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e2 = cudaFuncSetAttribute(k_asm_q1_3d_lines<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e3 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e4 = cudaFuncSetAttribute(k_asm_q1_3d_lines<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    cudaError_t e5 = cudaFuncSetAttribute(k_asm_q1_3d_lines<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
       cudaGetLastError();
       NLS_FAIL(h, NLS_ERR_CUDA, "lines assembly: cannot raise the dynamic shared-memory limit");
     }
@@ -843,7 +848,8 @@ int nls_launch_lines3(nls_context *h, bool want_r, bool want_k) {
     h->launches++;
     p.lap_valid = true;
   }
-  if (want_r && want_k) lines3_launch<true, true, false>(h, a, grid, lines3_smem(true));
+  if (want_r && want_k && a.prof) lines3_launch<true, true, false, true>(h, a, grid, lines3_smem(true));   // instrumented build: tools/lines_probe.py
+  else if (want_r && want_k) lines3_launch<true, true, false>(h, a, grid, lines3_smem(true));
   else if (want_k)      lines3_launch<false, true, false>(h, a, grid, lines3_smem(false));
   else                  lines3_launch<true, false, false>(h, a, grid, lines3_smem(true));
   cudaError_t e = cudaGetLastError();

@@ -387,8 +387,15 @@ static void orc_element_q1(const orc_model *mo, const orc_tabq1 *t, int64_t e, c
       for (int a = 0; a < nen; ++a)
         for (int i = 0; i < dim; ++i) {
           double s = 0.0;
+          if (orc_absmode) {   /* every summand of the expression above by absolute value: mu F, mu F^-T and lam lnJ F^-T are
+                                  added separately, and for small strains the first two cancel almost completely */
+            for (int Jc = 0; Jc < dim; ++Jc)
+              s += (fabs(mu * F[i * dim + Jc]) + fabs(mu * Fi[Jc * dim + i]) + fabs(lam * lnJ * Fi[Jc * dim + i])) * fabs(G[a][Jc]);
+            fe[a * dim + i] += s * fabs(wd);
+            continue;
+          }
           for (int Jc = 0; Jc < dim; ++Jc) s += P[i * dim + Jc] * G[a][Jc];
-          fe[a * dim + i] += orc_absmode ? fabs(s * wd) : s * wd;
+          fe[a * dim + i] += s * wd;
         }
     }
     if (Ke) {
@@ -613,7 +620,7 @@ void orc_jacobian_csr(orc_model *mo, double *U, const int64_t *rowptr, const int
 }
 
 /* Test metric, not a reference function: per entry of R and of the CSR Jacobian the sum of the ABSOLUTE contributions
-   (Q1: per quadrature point and element; 1-D: per element) -- the scale an entry-wise relative error is judged against (entries that cancel to ~0 are made of
+   (Q1: per quadrature point and element, R: per summand of the stress expression; 1-D: per element) -- the scale an entry-wise relative error is judged against (entries that cancel to ~0 are made of
    contributions of this size). Not for stateful materials (the element pass runs twice). */
 void orc_assemble_abs(orc_model *mo, double *U, double *Rabs, const int64_t *rowptr, const int32_t *colind, double *vabs) {
   int64_t n = orc_ndof(mo);
