@@ -515,12 +515,12 @@ if __name__ == "__main__":
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
     ap.add_argument("--assembly", type=int, default=None, help="0 atomic scatter, 1 best atomic-free scheme (default)")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--cpu-planes", dest="cpu_planes", type=int, default=0, help="node planes of the CPU sample (0: 9 in 3-D, 708 in 2-D)")
+    ap.add_argument("--cpu-planes", dest="cpu_planes", type=int, default=0, help="node planes of the CPU sample (0: 33 in 3-D, 708 in 2-D)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
     if a.cpu_planes <= 0:
-        a.cpu_planes = 9 if CONFIGS[a.config]["dim"] == 3 else CONFIGS[a.config]["n"]
+        a.cpu_planes = 33 if CONFIGS[a.config]["dim"] == 3 else CONFIGS[a.config]["n"]
     if a.impl == "reference":
         run_reference(a)
     else:
