@@ -126,10 +126,10 @@ k_spmv(int64_t nrows, const int64_t *__restrict__ rowptr, const int32_t *__restr
 // per node walk its blocks: one int32 block column per dim*dim values instead of dim*dim int32
 // scalar columns (index traffic 4/dim^2 B per nonzero instead of 4 B), x gathered as a dim-vector.
 // ------------------------------------------------------------------------------------
-template <int DIM, int T, bool DOT>
+template <int DIM, int T, bool DOT, typename VT = double>
 __global__ void __launch_bounds__(256)
 k_bspmv(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
-        const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+        const VT *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
         const uint8_t *__restrict__ con, PcgCtl *ctl, RedScratch rs) {
   if (DOT) {
     if (ctl->done) return;
@@ -148,13 +148,13 @@ k_bspmv(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__r
     if (valid) {
       const int64_t b0 = browptr[node];
       const int deg = (int)(browptr[node + 1] - b0);
-      const double *v0 = vals + (int64_t)DIM * DIM * b0;
+      const VT *v0 = vals + (int64_t)DIM * DIM * b0;
       for (int j = lane; j < deg; j += T) {
         const int c = bcol[b0 + j];
-        if (DIM == 2) {
+        if (DIM == 2 && sizeof(VT) == 8) {
           const double2 xv = reinterpret_cast<const double2 *>(x)[c];
-          const double2 a0 = *reinterpret_cast<const double2 *>(v0 + 2 * j);
-          const double2 a1 = *reinterpret_cast<const double2 *>(v0 + 2 * deg + 2 * j);
+          const double2 a0 = *reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(v0) + 2 * j);
+          const double2 a1 = *reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(v0) + 2 * deg + 2 * j);
           acc[0] = fma(a0.x, xv.x, fma(a0.y, xv.y, acc[0]));
           acc[1] = fma(a1.x, xv.x, fma(a1.y, xv.y, acc[1]));
         } else {
@@ -164,7 +164,7 @@ k_bspmv(int64_t n_owned, const int64_t *__restrict__ browptr, const int32_t *__r
 #pragma unroll
           for (int i = 0; i < DIM; ++i)
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) acc[i] = fma(v0[(int64_t)i * DIM * deg + DIM * j + k], xv[k], acc[i]);
+            for (int k = 0; k < DIM; ++k) acc[i] = fma((double)v0[(int64_t)i * DIM * deg + DIM * j + k], xv[k], acc[i]);
         }
       }
     }
@@ -567,6 +567,27 @@ int nls_launch_spmv(nls_context *h, const double *x, double *y, bool masked, boo
   return spmv_t<16>(h, x, y, con, with_dot);
 }
 
+// y = K x with the single-precision copy of the CSR values (the smoother of the multigrid preconditioner: half the HBM
+// traffic of the product; accumulation and vectors stay FP64)
+__global__ void __launch_bounds__(256) k_vals_to_f32(int64_t n, const double *__restrict__ v, float *__restrict__ o) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = (float)v[i];
+}
+int nls_launch_vals_to_f32(nls_context *h, float *out) {
+  k_vals_to_f32<<<vec_grid(h, h->nnz), 256, 0, h->stream>>>(h->nnz, h->d_vals, out);
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+int nls_launch_spmv_f32(nls_context *h, const float *vals32, const double *x, double *y) {
+  if (h->dim != 3 || h->nrows == 0) NLS_FAIL(h, NLS_ERR_STATE, "single-precision product: 3-D only");
+  int64_t g = (h->n_owned * 4 + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  k_bspmv<3, 4, false, float><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, vals32, x, y, h->d_con, h->d_ctl, red_of(h));
+  NLS_KCHECK(h);
+  return NLS_OK;
+}
+
 int nls_launch_extract_dinv(nls_context *h) {
   if (h->nrows == 0) return NLS_OK;
   k_extract_dinv<<<(unsigned)((h->nrows + 255) / 256), 256, 0, h->stream>>>(h->nrows, h->d_rowptr, h->d_diag, h->d_vals, h->d_con, h->d_dinv);
@@ -582,6 +603,15 @@ int nls_dev_dot(nls_context *h, int64_t n, const double *x, const double *y, dou
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   *out = h->h_scal[0];
   return nls_p2p_failed(h);       // a timed-out peer exchange leaves stale ghosts / partial sums: never report NLS_OK over it
+}
+
+int nls_dev_dot_local(nls_context *h, int64_t n, const double *x, const double *y, double *out) {
+  k_dot<<<vec_grid(h, n), 256, 0, h->stream>>>(n, x, y, nullptr, h->d_scal, red_of(h));
+  NLS_KCHECK(h);
+  NLS_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  *out = h->h_scal[0];
+  return NLS_OK;
 }
 
 // sqrt(sum v_i^2) over owned rows, optionally skipping constrained DoFs -- norm(dofs(fem, R))
@@ -757,6 +787,11 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
   int rc;
   const int64_t n = h->nrows;
   RedScratch rs = red_of(h);
+  // grid-topology 3-D meshes: multigrid (or block-Jacobi) preconditioner, kernels_mg.cu
+  if (fixed_iters == 0 && h->mg.ok && (h->opt_precond >= 1 || (h->opt_precond < 0 && n >= 30000))) {
+    h->mg.mode = h->opt_precond == 1 ? 1 : 2;
+    return nls_pcg_solve_mg(h, rtol, maxits, its, relres, status);
+  }
   if (!h->distributed && h->opt_pcg_small && fixed_iters == 0 && n > 0 && n <= (int64_t)PCG_SMALL_THREADS * PCG_SMALL_RPT &&
       h->nnz <= (int64_t)1 << 21) {
     const int nthr = (int)std::min<int64_t>(PCG_SMALL_THREADS, std::max<int64_t>(64, ((n + PCG_SMALL_RPT - 1) / PCG_SMALL_RPT + 31) / 32 * 32 * 2));

@@ -669,6 +669,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
 
 // ---- host side -----------------------------------------------------------------------------------------------
 void nls_lines3_free(nls_context *h) {
+  nls_mg_free(h);
   Lines3Plan &p = h->lplan;
   if (p.d_pbase) cudaFree(p.d_pbase);
   if (p.d_pown) cudaFree(p.d_pown);
@@ -804,7 +805,8 @@ int nls_lines3_build(nls_context *h) {
   NLS_CUDA(h, cudaMemsetAsync(p.d_counter, 0, 2 * sizeof(unsigned), h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   p.ok = true;
-  return NLS_OK;
+  p.h_pown = pown; p.h_pbase = pbase;
+  return nls_mg_build(h);
 }
 
 template <bool R, bool K, bool LB, bool PF = false>

@@ -956,6 +956,14 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   NLS_ENTER(h);
   if (!key) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_option: null key");
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
+  // preconditioner of the Krylov solve: -1 auto, 0 Jacobi, 1 block-Jacobi, 2 multigrid V-cycle (1, 2: grid-topology 3-D meshes)
+  if (!std::strcmp(key, "precond")) { h->opt_precond = value; return NLS_OK; }
+  if (!std::strcmp(key, "mg_degree")) { h->mg.degree = value < 1 ? 1 : value; return NLS_OK; }
+  if (!std::strcmp(key, "mg_coarse_degree")) { h->mg.coarse_degree = value < 1 ? 1 : value; return NLS_OK; }
+  if (!std::strcmp(key, "mg_ratio_x10")) { h->mg.ratio = value < 11 ? 1.1 : value / 10.0; return NLS_OK; }
+  if (!std::strcmp(key, "mg_coarse_ratio")) { h->mg.coarse_ratio = value < 2 ? 2.0 : (double)value; return NLS_OK; }
+  if (!std::strcmp(key, "mg_fp32")) { h->mg.fp32 = value; h->mg.version = -1; return NLS_OK; }
+  if (!std::strcmp(key, "mg_power_its")) { h->mg.power_its = value < 1 ? 1 : value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }
   if (!std::strcmp(key, "twophase_3d")) { h->opt_twophase_3d = value; return NLS_OK; }
   if (!std::strcmp(key, "lap3d")) { h->opt_lap3d = value; return NLS_OK; }

@@ -98,6 +98,31 @@ struct Lines3Plan {
   double *d_lap = nullptr;
   unsigned *d_counter = nullptr;
   double *d_carry = nullptr;       // [sm_count][18][384] per-CTA carry scratch of the line kernel
+  std::vector<uint8_t> h_pown;     // host copies for the multigrid hierarchy (kernels_mg.cu)
+  std::vector<int32_t> h_pbase;
+};
+
+// geometric multigrid preconditioner on grid-topology meshes (kernels_mg.cu)
+#define MG_MAX_LEVELS 10
+struct MgLevel {
+  int nx = 0, ny = 0, nz = 0;
+  int64_t nn = 0;
+  double *K = nullptr;             // [nn][27][9] Galerkin operator (levels >= 1; level 0 is the CSR Jacobian)
+  double *dinv = nullptr;          // [nn][9] inverse node blocks
+  double *x = nullptr, *b = nullptr, *y = nullptr, *d = nullptr;
+  double lmax = 1.0;               // largest eigenvalue of D^-1 K (power iteration, inflated)
+};
+struct MgPlan {
+  bool ok = false;
+  int nlev = 0, z0 = 0;
+  int64_t version = -1;            // vals_version the operators were built for
+  int mode = 2;                    // 1 block-Jacobi alone, 2 V-cycle
+  int degree = 2, coarse_degree = 24, power_its = 10;
+  double ratio = 8.0, coarse_ratio = 60.0;
+  int fp32 = 1;                    // the smoother's level-0 products read a single-precision copy of the CSR values
+  float *vals32 = nullptr;
+  int64_t power_version = -1000;   // vals_version of the last full power iteration
+  MgLevel lev[MG_MAX_LEVELS];
 };
 
 // ---- device control block of the PCG loop (lives in device memory) ----
@@ -217,6 +242,8 @@ struct nls_context {
   GatherPlanDev gplan;
   TwoPhasePlan tplan;
   Lines3Plan lplan;
+  MgPlan mg;
+  int opt_precond = -1;    // -1 auto (multigrid on large grid-topology 3-D meshes, else Jacobi), 0 Jacobi, 1 block-Jacobi, 2 multigrid
   std::vector<double> h_coords;
 
   // vectors (ndof_local unless noted)
@@ -331,3 +358,10 @@ int nls_p2p_allreduce(nls_context *h, double *dptr, int count);
 int nls_p2p_check(nls_context *h);
 int nls_p2p_failed(nls_context *h);   // after a stream synchronisation: NLS_ERR_NCCL if an exchange has timed out
 int nls_allreduce_sum(nls_context *h, double *dptr, int count);
+int nls_dev_dot_local(nls_context *h, int64_t n, const double *x, const double *y, double *out);   // this rank's part only
+int nls_launch_vals_to_f32(nls_context *h, float *out);
+int nls_launch_spmv_f32(nls_context *h, const float *vals32, const double *x, double *y);
+void nls_mg_free(nls_context *h);
+int nls_mg_build(nls_context *h);
+int nls_mg_setup(nls_context *h);
+int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status);
