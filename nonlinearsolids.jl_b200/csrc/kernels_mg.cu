@@ -154,6 +154,71 @@ __global__ void __launch_bounds__(128) k_mg_rap(const MgFine F, const double *__
   }
 }
 
+// The same product for level 1 (fine operator = the CSR Jacobian, 3/4 of the whole set-up), one WARP per coarse node: lane s
+// owns stencil slot s. For every fine node i under the coarse node (<= 27) the 27 lanes first fetch the 27 blocks of i's CSR
+// block row -- one contiguous 1.9 KB row, each block once -- into shared memory; then every lane adds the <= 8 of them whose
+// column node interpolates from its coarse neighbour. Same terms and the same order as k_mg_rap<true>.
+__global__ void __launch_bounds__(128) k_mg_rap_fine_warp(const MgFine F, int cnx, int cny, int cnz, double *__restrict__ Kc) {
+  __shared__ double sB[4][27][9];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int fnx = F.nx, fny = F.ny, fnz = F.nz;
+  const int64_t ncoarse = (int64_t)cnx * cny * cnz;
+  const int dxs = lane % 3 - 1, dys = (lane / 3) % 3 - 1, dzs = lane / 9 - 1;      // lane < 27: both the block it fetches and its slot
+  for (int64_t I = blockIdx.x * 4ll + wib; I < ncoarse; I += (int64_t)gridDim.x * 4) {
+    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = (int)(I / ((int64_t)cnx * cny));
+    const int X2 = X + dxs, Y2 = Y + dys, Z2 = Z + dzs;
+    const bool jok = lane < 27 && X2 >= 0 && X2 < cnx && Y2 >= 0 && Y2 < cny && Z2 >= 0 && Z2 < cnz;
+    const int fxI = mg_fx(X, fnx), fyI = mg_fx(Y, fny), fzI = mg_fx(Z, fnz);
+    const int fxJ = jok ? mg_fx(X2, fnx) : 0, fyJ = jok ? mg_fx(Y2, fny) : 0, fzJ = jok ? mg_fx(Z2, fnz) : 0;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int z = max(fzI - 1, 0); z <= min(fzI + 1, fnz - 1); ++z) {
+      const double wz = mg_w(z, Z, fnz);
+      if (wz == 0.0) continue;
+      for (int y = max(fyI - 1, 0); y <= min(fyI + 1, fny - 1); ++y) {
+        const double wy = wz * mg_w(y, Y, fny);
+        if (wy == 0.0) continue;
+        for (int x = max(fxI - 1, 0); x <= min(fxI + 1, fnx - 1); ++x) {
+          const double wi = wy * mg_w(x, X, fnx);
+          if (wi == 0.0) continue;
+          __syncwarp();
+          if (lane < 27) {
+            double B[9];
+            if (!mg_fine_block(F, x, y, z, dxs, dys, dzs, B)) {
+#pragma unroll
+              for (int k = 0; k < 9; ++k) B[k] = 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sB[wib][lane][k] = B[k];
+          }
+          __syncwarp();
+          if (jok) {
+            for (int z2 = max(max(fzJ - 1, 0), z - 1); z2 <= min(min(fzJ + 1, fnz - 1), z + 1); ++z2) {
+              const double wz2 = wi * mg_w(z2, Z2, fnz);
+              if (wz2 == 0.0) continue;
+              for (int y2 = max(max(fyJ - 1, 0), y - 1); y2 <= min(min(fyJ + 1, fny - 1), y + 1); ++y2) {
+                const double wy2 = wz2 * mg_w(y2, Y2, fny);
+                if (wy2 == 0.0) continue;
+                for (int x2 = max(max(fxJ - 1, 0), x - 1); x2 <= min(min(fxJ + 1, fnx - 1), x + 1); ++x2) {
+                  const double w = wy2 * mg_w(x2, X2, fnx);
+                  if (w == 0.0) continue;
+                  const double *B = sB[wib][(z2 - z + 1) * 9 + (y2 - y + 1) * 3 + (x2 - x + 1)];
+#pragma unroll
+                  for (int k = 0; k < 9; ++k) acc[k] = fma(w, B[k], acc[k]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane < 27) {
+      double *o = Kc + (I * 27 + lane) * 9;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[k] = acc[k];
+    }
+  }
+}
+
 // coarse levels: inverse of the diagonal blocks (slot 13); a singular block (a coarse node whose fine nodes are all
 // constrained) gets zero
 __global__ void __launch_bounds__(256) k_mg_dinv(int64_t nn, const double *__restrict__ K, double *__restrict__ dinv) {
@@ -404,7 +469,8 @@ int nls_mg_setup(nls_context *h) {
   k_mg_fine_dinv<<<mg_grid(h, m.lev[0].nn), 256, 0, h->stream>>>(F, m.lev[0].dinv); MG_KCHECK(h);
   for (int l = 1; l < m.nlev; ++l) {
     MgLevel &Lf = m.lev[l - 1], &Lc = m.lev[l];
-    if (l == 1) k_mg_rap<true><<<mg_grid(h, Lc.nn * 27, 128), 128, 0, h->stream>>>(F, nullptr, Lf.nx, Lf.ny, Lf.nz, Lc.nx, Lc.ny, Lc.nz, Lc.K);
+    if (l == 1 && m.rap_warp) k_mg_rap_fine_warp<<<mg_grid(h, Lc.nn * 32, 128), 128, 0, h->stream>>>(F, Lc.nx, Lc.ny, Lc.nz, Lc.K);
+    else if (l == 1) k_mg_rap<true><<<mg_grid(h, Lc.nn * 27, 128), 128, 0, h->stream>>>(F, nullptr, Lf.nx, Lf.ny, Lf.nz, Lc.nx, Lc.ny, Lc.nz, Lc.K);
     else k_mg_rap<false><<<mg_grid(h, Lc.nn * 27, 128), 128, 0, h->stream>>>(F, Lf.K, Lf.nx, Lf.ny, Lf.nz, Lc.nx, Lc.ny, Lc.nz, Lc.K);
     MG_KCHECK(h);
     k_mg_dinv<<<mg_grid(h, Lc.nn), 256, 0, h->stream>>>(Lc.nn, Lc.K, Lc.dinv); MG_KCHECK(h);

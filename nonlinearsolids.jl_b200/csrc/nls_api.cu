@@ -962,6 +962,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "mg_coarse_degree")) { h->mg.coarse_degree = value < 1 ? 1 : value; return NLS_OK; }
   if (!std::strcmp(key, "mg_ratio_x10")) { h->mg.ratio = value < 11 ? 1.1 : value / 10.0; return NLS_OK; }
   if (!std::strcmp(key, "mg_coarse_ratio")) { h->mg.coarse_ratio = value < 2 ? 2.0 : (double)value; return NLS_OK; }
+  if (!std::strcmp(key, "mg_rap_warp")) { h->mg.rap_warp = value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "mg_fp32")) { h->mg.fp32 = value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "mg_power_its")) { h->mg.power_its = value < 1 ? 1 : value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }

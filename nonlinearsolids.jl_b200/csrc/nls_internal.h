@@ -119,6 +119,7 @@ struct MgPlan {
   int mode = 2;                    // 1 block-Jacobi alone, 2 V-cycle
   int degree = 2, coarse_degree = 24, power_its = 10;
   double ratio = 8.0, coarse_ratio = 60.0;
+  int rap_warp = 1;                // level-1 Galerkin product: one warp per coarse node (0: one thread per stencil slot)
   int fp32 = 1;                    // the smoother's level-0 products read a single-precision copy of the CSR values
   float *vals32 = nullptr;
   int64_t power_version = -1000;   // vals_version of the last full power iteration
