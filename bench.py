@@ -368,6 +368,7 @@ def run_ours(args):
         Uaff = np.zeros((mesh.nn, dim)); Uaff[:, dim - 1] = -0.1 * LOAD_T * mesh.coords[:, dim - 1]
         Uaff = Uaff.ravel()
         H.call("nls_dev_upload_u", dp(Uaff))
+        H.call("nls_solver_prepare")          # work space of the Krylov preconditioner: allocated once per model, not per solve
         opts = nls._lib.NewtonOpts(rtol=1e-10, atol=1e-14, dtol=1e6, maxits=25, type_modified=0,
                                    lin_rtol=args.lin_rtol, lin_maxits=100000)
         res = nls._lib.NewtonResult()

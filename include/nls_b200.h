@@ -217,6 +217,9 @@ int32_t nls_assembly_scheme(nls_handle h);
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
  * {staging, element phase, 0, block-task phase, clusters, cp.async wait, barrier, issue of the next stage}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);
+/* optional, collective after nls_comm_init: allocate the solver's work space (the multigrid hierarchy of the Krylov
+ * preconditioner on grid-topology 3-D meshes) now instead of inside the first solve */
+int32_t nls_solver_prepare(nls_handle h);
 int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24); /* + per-warp phase cycles of the 3-D line kernel */
 /* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 the default row-owner scheme
  * (2-D: shared-memory gather; 3-D: atomic scatter unless "twophase_3d" = 1), 2 element records + row owners;

@@ -788,7 +788,8 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
   const int64_t n = h->nrows;
   RedScratch rs = red_of(h);
   // grid-topology 3-D meshes: multigrid (or block-Jacobi) preconditioner, kernels_mg.cu
-  if (fixed_iters == 0 && h->mg.ok && (h->opt_precond >= 1 || (h->opt_precond < 0 && n >= 30000))) {
+  if (fixed_iters == 0 && h->mg.ok && (h->distributed || !(h->mg.ghost_below || h->mg.ghost_above)) &&
+      (h->opt_precond >= 1 || (h->opt_precond < 0 && h->nn >= 10000))) {
     h->mg.mode = h->opt_precond == 1 ? 1 : 2;
     return nls_pcg_solve_mg(h, rtol, maxits, its, relres, status);
   }

@@ -806,7 +806,8 @@ int nls_lines3_build(nls_context *h) {
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   p.ok = true;
   p.h_pown = pown; p.h_pbase = pbase;
-  return nls_mg_build(h);
+  { const int rc = nls_mg_build(h); if (rc) return rc; }
+  return nls_mg_prepare(h, false);
 }
 
 template <bool R, bool K, bool LB, bool PF = false>

@@ -7,16 +7,20 @@
 //     even node count), P = trilinear interpolation (weights 1, 1/2 per axis), the same for the three displacement components;
 //   * level 0 is the assembled CSR Jacobian itself (block positions from the line tables of kernels_lines3d.cu, Dirichlet
 //     rows and columns masked out = the free block dofs(K)); coarser operators are stored as 27 dense 3 x 3 blocks per node;
-//   * smoother: Chebyshev polynomial in D^-1 K (D = the 3 x 3 node blocks), largest eigenvalue by a few power iterations
-//     whenever the values change; the coarsest grid (<= 6 nodes per axis) gets a long Chebyshev run instead of a factorisation;
-//   * the Galerkin products are gathers: one thread per (coarse node, stencil slot) sums its <= 343 weighted fine blocks in a
-//     fixed order: deterministic, no atomics.
-// Multi-GPU: every rank runs the V-cycle on its own slab with the couplings to ghost nodes dropped (a non-overlapping
-// Schwarz layer on top of the multigrid); the Krylov loop around it exchanges halos and reduces as before.
+//   * smoother: Chebyshev polynomial in D^-1 K (D = the 3 x 3 node blocks), largest eigenvalue by a few power iterations;
+//     the coarsest grid (<= 6 nodes per axis) gets a long Chebyshev run instead of a factorisation;
+//   * the Galerkin products are gathers: every coarse block is the sum of its <= 343 weighted fine blocks in a fixed order:
+//     deterministic, no atomics.
+// Multi-GPU (z-slabs): levels 0 and 1 are distributed like the mesh -- every rank owns the coarse planes whose fine plane it
+// owns, one ghost plane either side, filled by neighbour send/recv (vectors before every product, operator rows once per
+// set-up) -- so smoothing, restriction and prolongation are the single-GPU operations. From level 2 on (1/64 of the nodes) the
+// grids are global and replicated: operator rows and right-hand sides are summed over the ranks (every rank contributes its
+// planes, zeros elsewhere) and every rank runs the same coarse cycle. The iteration count does not depend on the rank count.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include "nls_internal.h"
+#include "nccl_dyn.h"
 
 #ifndef NLS_TRY
 #define NLS_TRY(call) do { int rc_ = (call); if (rc_ != NLS_OK) return rc_; } while (0)
@@ -26,18 +30,24 @@
 
 struct MgL3Line { int64_t lb; int32_t nl; int8_t rank[9]; int8_t pad[3]; };   // = L3Line of kernels_lines3d.cu
 
-struct MgFine {          // level 0: the CSR Jacobian of a grid-topology mesh, owned planes [z0, z0 + nz)
-  int nx, ny, nz, z0, nzp;
+struct MgFine {          // level 0: the CSR Jacobian of a grid-topology mesh
+  int nx, ny, nzo;       // owned planes
+  int z0;                // line-table index of the first owned plane
+  int p0, NZ;            // global index of the first owned plane, global plane count
   const int32_t *pbase;
-  const uint8_t *pown;
   const MgL3Line *info;
   const double *vals;
   const uint8_t *con;
+  const double *gbelow, *gabove;   // stencil-format rows [ny * nx][27][9] of the neighbours' boundary planes (global p0 - 1, p0 + nzo)
 };
 
+// a grid level stored as a box of z-planes: planes [zbase, zbase + nzb) of a global grid with NZ planes; the kernel works on
+// the planes [zown0, zown1) (global indices), the rest of the box is read only. Replicated levels: the box is the whole grid.
+struct MgBox { int nx, ny, nzb, zbase, NZ, zown0, zown1; };
+
 __host__ __device__ __forceinline__ int mg_coarse_n(int n) { return n <= 2 ? n : ((n & 1) ? (n + 1) / 2 : n / 2 + 1); }
-// fine index of coarse node X, and the interpolation weight of fine node x on it (0 if none)
-__device__ __forceinline__ int mg_fx(int X, int n) { return n <= 2 ? X : min(2 * X, n - 1); }
+// fine index of coarse node X, and the interpolation weight of fine node x on it (0 if none); n = fine node count of the axis
+__host__ __device__ __forceinline__ int mg_fx(int X, int n) { return n <= 2 ? X : (2 * X < n - 1 ? 2 * X : n - 1); }
 __device__ __forceinline__ double mg_w(int x, int X, int n) {
   const int f = mg_fx(X, n);
   if (x == f) return 1.0;
@@ -58,12 +68,22 @@ __device__ __forceinline__ bool mg_inv3(const double *M, double *Mi) {
   return true;
 }
 
-// block (i, j) of the free block of the fine CSR matrix, i = (x, y, z), j = i + (dx, dy, dz); z counts owned planes.
-// Returns false (B untouched) when j does not exist or is a ghost node.
-__device__ __forceinline__ bool mg_fine_block(const MgFine &F, int x, int y, int z, int dx, int dy, int dz, double (&B)[9]) {
-  const int x2 = x + dx, y2 = y + dy, z2 = z + dz;
-  if (x2 < 0 || x2 >= F.nx || y2 < 0 || y2 >= F.ny || z2 < 0 || z2 >= F.nz) return false;
-  const int zp = F.z0 + z;
+// block (i, j) of the free block of the fine matrix, i = (x, y, zg), j = i + (dx, dy, dz); zg = GLOBAL plane index. Rows of
+// owned planes come from the CSR values, rows of the two neighbouring planes from the exchanged stencil copies.
+// Returns false (B untouched) when j does not exist.
+__device__ __forceinline__ bool mg_fine_block(const MgFine &F, int x, int y, int zg, int dx, int dy, int dz, double (&B)[9]) {
+  const int x2 = x + dx, y2 = y + dy, z2 = zg + dz;
+  if (x2 < 0 || x2 >= F.nx || y2 < 0 || y2 >= F.ny || z2 < 0 || z2 >= F.NZ) return false;
+  const int zl = zg - F.p0;
+  if (zl < 0 || zl >= F.nzo) {
+    const double *g = zl < 0 ? F.gbelow : F.gabove;
+    if (!g || (zl != -1 && zl != F.nzo)) return false;
+    const double *p = g + (((int64_t)y * F.nx + x) * 27 + (dz + 1) * 9 + (dy + 1) * 3 + dx + 1) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B[k] = p[k];
+    return true;
+  }
+  const int zp = F.z0 + zl;
   const MgL3Line *li = F.info + ((int64_t)zp * F.ny + y);
   const int rank = li->rank[(dz + 1) * 3 + (dy + 1)];
   if (rank < 0) return false;
@@ -83,11 +103,11 @@ __device__ __forceinline__ bool mg_fine_block(const MgFine &F, int x, int y, int
 
 // ---- level 0: inverse of the masked 3 x 3 node blocks (block-Jacobi); constrained DoFs get zero rows and columns ----
 __global__ void __launch_bounds__(256) k_mg_fine_dinv(const MgFine F, double *__restrict__ dinv) {
-  const int64_t nn = (int64_t)F.nx * F.ny * F.nz;
+  const int64_t nn = (int64_t)F.nx * F.ny * F.nzo;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nn; t += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(t % F.nx), y = (int)((t / F.nx) % F.ny), z = (int)(t / ((int64_t)F.nx * F.ny));
     double B[9], Bi[9];
-    mg_fine_block(F, x, y, z, 0, 0, 0, B);
+    mg_fine_block(F, x, y, F.p0 + z, 0, 0, 0, B);
     const int64_t ni = (int64_t)F.pbase[F.z0 + z] + (int64_t)y * F.nx + x;
     const uint8_t *ci = F.con + 3 * ni;
     for (int r = 0; r < 3; ++r) if (ci[r]) B[r * 3 + r] = 1.0;
@@ -97,77 +117,33 @@ __global__ void __launch_bounds__(256) k_mg_fine_dinv(const MgFine F, double *__
   }
 }
 
-// ---- Galerkin product, one thread per (coarse node, stencil slot) ----
-// FINE: the fine operator is the CSR matrix (level 0), else a 27-slot stencil matrix on a (fnx, fny, fnz) grid
-template <bool FINE>
-__global__ void __launch_bounds__(128) k_mg_rap(const MgFine F, const double *__restrict__ Kf, int fnx, int fny, int fnz,
-                                                 int cnx, int cny, int cnz, double *__restrict__ Kc) {
-  const int64_t total = (int64_t)cnx * cny * cnz * 27;
+// level 0: the rows of owned plane zl in stencil format (for the neighbour rank's Galerkin product)
+__global__ void __launch_bounds__(256) k_mg_export_rows(const MgFine F, int zl, double *__restrict__ out) {
+  const int64_t total = (int64_t)F.nx * F.ny * 27;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(t % 27);
-    const int64_t I = t / 27;
-    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = (int)(I / ((int64_t)cnx * cny));
-    const int X2 = X + s % 3 - 1, Y2 = Y + (s / 3) % 3 - 1, Z2 = Z + s / 9 - 1;
-    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (X2 >= 0 && X2 < cnx && Y2 >= 0 && Y2 < cny && Z2 >= 0 && Z2 < cnz) {
-      const int fxI = mg_fx(X, fnx), fyI = mg_fx(Y, fny), fzI = mg_fx(Z, fnz);
-      const int fxJ = mg_fx(X2, fnx), fyJ = mg_fx(Y2, fny), fzJ = mg_fx(Z2, fnz);
-      for (int z = max(fzI - 1, 0); z <= min(fzI + 1, fnz - 1); ++z) {
-        const double wz = mg_w(z, Z, fnz);
-        if (wz == 0.0) continue;
-        for (int z2 = max(max(fzJ - 1, 0), z - 1); z2 <= min(min(fzJ + 1, fnz - 1), z + 1); ++z2) {
-          const double wz2 = wz * mg_w(z2, Z2, fnz);
-          if (wz2 == 0.0) continue;
-          for (int y = max(fyI - 1, 0); y <= min(fyI + 1, fny - 1); ++y) {
-            const double wy = wz2 * mg_w(y, Y, fny);
-            if (wy == 0.0) continue;
-            for (int y2 = max(max(fyJ - 1, 0), y - 1); y2 <= min(min(fyJ + 1, fny - 1), y + 1); ++y2) {
-              const double wy2 = wy * mg_w(y2, Y2, fny);
-              if (wy2 == 0.0) continue;
-              for (int x = max(fxI - 1, 0); x <= min(fxI + 1, fnx - 1); ++x) {
-                const double wx = wy2 * mg_w(x, X, fnx);
-                if (wx == 0.0) continue;
-                for (int x2 = max(max(fxJ - 1, 0), x - 1); x2 <= min(min(fxJ + 1, fnx - 1), x + 1); ++x2) {
-                  const double w = wx * mg_w(x2, X2, fnx);
-                  if (w == 0.0) continue;
-                  if (FINE) {
-                    double B[9];
-                    if (!mg_fine_block(F, x, y, z, x2 - x, y2 - y, z2 - z, B)) continue;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) acc[k] = fma(w, B[k], acc[k]);
-                  } else {
-                    const int sf = (z2 - z + 1) * 9 + (y2 - y + 1) * 3 + (x2 - x + 1);
-                    const double *B = Kf + ((((int64_t)z * fny + y) * fnx + x) * 27 + sf) * 9;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) acc[k] = fma(w, B[k], acc[k]);
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-    }
-    double *o = Kc + t * 9;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) o[k] = acc[k];
+    const int64_t node = t / 27;
+    const int x = (int)(node % F.nx), y = (int)(node / F.nx);
+    double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    mg_fine_block(F, x, y, F.p0 + zl, s % 3 - 1, (s / 3) % 3 - 1, s / 9 - 1, B);
+    for (int k = 0; k < 9; ++k) out[t * 9 + k] = B[k];
   }
 }
 
-// The same product for level 1 (fine operator = the CSR Jacobian, 3/4 of the whole set-up), one WARP per coarse node: lane s
-// owns stencil slot s. For every fine node i under the coarse node (<= 27) the 27 lanes first fetch the 27 blocks of i's CSR
-// block row -- one contiguous 1.9 KB row, each block once -- into shared memory; then every lane adds the <= 8 of them whose
-// column node interpolates from its coarse neighbour. Same terms and the same order as k_mg_rap<true>.
-__global__ void __launch_bounds__(128) k_mg_rap_fine_warp(const MgFine F, int cnx, int cny, int cnz, double *__restrict__ Kc) {
+// ---- Galerkin product level 1 <- level 0, one WARP per owned coarse node: lane s owns stencil slot s. For every fine node i
+// under the coarse node (<= 27) the 27 lanes first fetch the 27 blocks of i's block row -- one contiguous 1.9 KB CSR row, each
+// block once -- into shared memory; then every lane adds the <= 8 of them whose column node interpolates from its coarse
+// neighbour. Rows of the coarse box's owned planes only (ghost rows arrive by exchange).
+__global__ void __launch_bounds__(128) k_mg_rap_fine_warp(const MgFine F, const MgBox C, double *__restrict__ Kc) {
   __shared__ double sB[4][27][9];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int fnx = F.nx, fny = F.ny, fnz = F.nz;
-  const int64_t ncoarse = (int64_t)cnx * cny * cnz;
+  const int fnx = F.nx, fny = F.ny, fnz = F.NZ, cnx = C.nx, cny = C.ny;
+  const int64_t ncoarse = (int64_t)cnx * cny * (C.zown1 - C.zown0);
   const int dxs = lane % 3 - 1, dys = (lane / 3) % 3 - 1, dzs = lane / 9 - 1;      // lane < 27: both the block it fetches and its slot
   for (int64_t I = blockIdx.x * 4ll + wib; I < ncoarse; I += (int64_t)gridDim.x * 4) {
-    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = (int)(I / ((int64_t)cnx * cny));
+    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = C.zown0 + (int)(I / ((int64_t)cnx * cny));
     const int X2 = X + dxs, Y2 = Y + dys, Z2 = Z + dzs;
-    const bool jok = lane < 27 && X2 >= 0 && X2 < cnx && Y2 >= 0 && Y2 < cny && Z2 >= 0 && Z2 < cnz;
+    const bool jok = lane < 27 && X2 >= 0 && X2 < cnx && Y2 >= 0 && Y2 < cny && Z2 >= 0 && Z2 < C.NZ;
     const int fxI = mg_fx(X, fnx), fyI = mg_fx(Y, fny), fzI = mg_fx(Z, fnz);
     const int fxJ = jok ? mg_fx(X2, fnx) : 0, fyJ = jok ? mg_fx(Y2, fny) : 0, fzJ = jok ? mg_fx(Z2, fnz) : 0;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -212,15 +188,64 @@ __global__ void __launch_bounds__(128) k_mg_rap_fine_warp(const MgFine F, int cn
       }
     }
     if (lane < 27) {
-      double *o = Kc + (I * 27 + lane) * 9;
+      double *o = Kc + (((((int64_t)(Z - C.zbase)) * cny + Y) * cnx + X) * 27 + lane) * 9;
 #pragma unroll
       for (int k = 0; k < 9; ++k) o[k] = acc[k];
     }
   }
 }
 
-// coarse levels: inverse of the diagonal blocks (slot 13); a singular block (a coarse node whose fine nodes are all
-// constrained) gets zero
+// ---- Galerkin product between stencil levels, one thread per (coarse node of the planes [zown0, zown1), stencil slot). The
+// fine level is a box (rows of its ghost planes present); the coarse rows go to their place in the coarse box.
+__global__ void __launch_bounds__(128) k_mg_rap(const MgBox Fb, const double *__restrict__ Kf, const MgBox C, double *__restrict__ Kc) {
+  const int fnx = Fb.nx, fny = Fb.ny, fnz = Fb.NZ, cnx = C.nx, cny = C.ny;
+  const int64_t total = (int64_t)cnx * cny * (C.zown1 - C.zown0) * 27;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(t % 27);
+    const int64_t I = t / 27;
+    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = C.zown0 + (int)(I / ((int64_t)cnx * cny));
+    const int X2 = X + s % 3 - 1, Y2 = Y + (s / 3) % 3 - 1, Z2 = Z + s / 9 - 1;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (X2 >= 0 && X2 < cnx && Y2 >= 0 && Y2 < cny && Z2 >= 0 && Z2 < C.NZ) {
+      const int fxI = mg_fx(X, fnx), fyI = mg_fx(Y, fny), fzI = mg_fx(Z, fnz);
+      const int fxJ = mg_fx(X2, fnx), fyJ = mg_fx(Y2, fny), fzJ = mg_fx(Z2, fnz);
+      for (int z = max(fzI - 1, 0); z <= min(fzI + 1, fnz - 1); ++z) {
+        const double wz = mg_w(z, Z, fnz);
+        if (wz == 0.0) continue;
+        for (int z2 = max(max(fzJ - 1, 0), z - 1); z2 <= min(min(fzJ + 1, fnz - 1), z + 1); ++z2) {
+          const double wz2 = wz * mg_w(z2, Z2, fnz);
+          if (wz2 == 0.0) continue;
+          for (int y = max(fyI - 1, 0); y <= min(fyI + 1, fny - 1); ++y) {
+            const double wy = wz2 * mg_w(y, Y, fny);
+            if (wy == 0.0) continue;
+            for (int y2 = max(max(fyJ - 1, 0), y - 1); y2 <= min(min(fyJ + 1, fny - 1), y + 1); ++y2) {
+              const double wy2 = wy * mg_w(y2, Y2, fny);
+              if (wy2 == 0.0) continue;
+              for (int x = max(fxI - 1, 0); x <= min(fxI + 1, fnx - 1); ++x) {
+                const double wx = wy2 * mg_w(x, X, fnx);
+                if (wx == 0.0) continue;
+                for (int x2 = max(max(fxJ - 1, 0), x - 1); x2 <= min(min(fxJ + 1, fnx - 1), x + 1); ++x2) {
+                  const double w = wx * mg_w(x2, X2, fnx);
+                  if (w == 0.0) continue;
+                  const int sf = (z2 - z + 1) * 9 + (y2 - y + 1) * 3 + (x2 - x + 1);
+                  const double *B = Kf + ((((int64_t)(z - Fb.zbase) * fny + y) * fnx + x) * 27 + sf) * 9;
+#pragma unroll
+                  for (int k = 0; k < 9; ++k) acc[k] = fma(w, B[k], acc[k]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    double *o = Kc + (((((int64_t)(Z - C.zbase)) * cny + Y) * cnx + X) * 27 + s) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = acc[k];
+  }
+}
+
+// stencil levels: inverse of the diagonal blocks (slot 13) of nodes [0, nn); a singular block (a coarse node whose fine nodes
+// are all constrained) gets zero
 __global__ void __launch_bounds__(256) k_mg_dinv(int64_t nn, const double *__restrict__ K, double *__restrict__ dinv) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
     double Bi[9];
@@ -229,18 +254,18 @@ __global__ void __launch_bounds__(256) k_mg_dinv(int64_t nn, const double *__res
   }
 }
 
-// coarse levels: y = K x, three lanes per node (one per scalar row), 27 blocks each
-__global__ void __launch_bounds__(256) k_mg_spmv(int nx, int ny, int nz, const double *__restrict__ K, const double *__restrict__ x,
-                                                  double *__restrict__ y) {
-  const int64_t nrows = (int64_t)nx * ny * nz * 3;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nrows; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / 3;
+// stencil levels: y = K x on the planes [zown0, zown1) of a box, three lanes per node (one per scalar row), 27 blocks each
+__global__ void __launch_bounds__(256) k_mg_spmv(const MgBox B, const double *__restrict__ K, const double *__restrict__ x, double *__restrict__ y) {
+  const int nx = B.nx, ny = B.ny;
+  const int64_t first = (int64_t)(B.zown0 - B.zbase) * ny * nx * 3, nrows = (int64_t)(B.zown1 - B.zown0) * ny * nx * 3;
+  for (int64_t tt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tt < nrows; tt += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = first + tt, i = t / 3;
     const int r = (int)(t - 3 * i);
-    const int X = (int)(i % nx), Y = (int)((i / nx) % ny), Z = (int)(i / ((int64_t)nx * ny));
+    const int X = (int)(i % nx), Y = (int)((i / nx) % ny), Z = (int)(i / ((int64_t)nx * ny));      // Z: plane inside the box
     const double *Ki = K + i * 243 + r * 3;
     double s = 0.0;
     for (int dz = -1; dz <= 1; ++dz) {
-      if (Z + dz < 0 || Z + dz >= nz) continue;
+      if (Z + dz < 0 || Z + dz >= B.nzb) continue;
       for (int dy = -1; dy <= 1; ++dy) {
         if (Y + dy < 0 || Y + dy >= ny) continue;
         for (int dx = -1; dx <= 1; ++dx) {
@@ -257,10 +282,10 @@ __global__ void __launch_bounds__(256) k_mg_spmv(int nx, int ny, int nz, const d
 }
 
 // one Chebyshev step on nodes [0, nn): d = a d + c D^-1 (b - y), x += d  (y = K x of the current x, or absent while x = 0).
-// Vectors are indexed by node id; `dinv` too.
+// mode 1: x = 0 on entry (x = d), 2: new run (d restarts), 0: inside a run
 __global__ void __launch_bounds__(256) k_mg_cheb(int64_t nn, const double *__restrict__ dinv, const double *__restrict__ b,
                                                   const double *__restrict__ y, double *__restrict__ d, double *__restrict__ x,
-                                                  double a, double c, int mode) {   // mode 1: x = 0 on entry (x = d), 2: new run (d restarts), 0: inside a run
+                                                  double a, double c, int mode) {
   const bool first = mode == 1, restart = mode != 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
     double r0 = b[3 * i], r1 = b[3 * i + 1], r2 = b[3 * i + 2];
@@ -275,7 +300,7 @@ __global__ void __launch_bounds__(256) k_mg_cheb(int64_t nn, const double *__res
   }
 }
 
-// z = D^-1 r on the owned nodes (block-Jacobi alone, and the power iteration)
+// z = D^-1 r on nodes [0, nn) (block-Jacobi alone, and the power iteration)
 __global__ void __launch_bounds__(256) k_mg_apply_dinv(int64_t nn, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ z) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
     const double r0 = r[3 * i], r1 = r[3 * i + 1], r2 = r[3 * i + 2];
@@ -284,15 +309,22 @@ __global__ void __launch_bounds__(256) k_mg_apply_dinv(int64_t nn, const double 
   }
 }
 
-// restriction bc = P^T (b - y): one thread per coarse DoF gathers its <= 27 fine nodes. `pbase` maps the fine grid to node
-// ids on level 0 (owned planes z0 ..); null = lexicographic.
-__global__ void __launch_bounds__(256) k_mg_restrict(int fnx, int fny, int fnz, int cnx, int cny, int cnz, const int32_t *__restrict__ pbase, int z0,
-                                                      const double *__restrict__ b, const double *__restrict__ y, double *__restrict__ bc) {
-  const int64_t total = (int64_t)cnx * cny * cnz * 3;
+// r = b - y on n entries
+__global__ void __launch_bounds__(256) k_mg_residual(int64_t n, const double *__restrict__ b, const double *__restrict__ y, double *__restrict__ r) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) r[i] = b[i] - y[i];
+}
+
+// restriction bc = P^T r on the coarse planes [zown0, zown1): one thread per coarse DoF gathers its <= 27 fine nodes (ghost
+// planes of r filled beforehand). Level 0: r is indexed by node id through the line tables (pbase; z0 = table index of the
+// rank's first owned plane, global plane p0).
+__global__ void __launch_bounds__(256) k_mg_restrict(const MgBox Fb, const int32_t *__restrict__ pbase, int z0, int p0,
+                                                      const MgBox C, const double *__restrict__ r, double *__restrict__ bc) {
+  const int fnx = Fb.nx, fny = Fb.ny, fnz = Fb.NZ, cnx = C.nx, cny = C.ny;
+  const int64_t total = (int64_t)cnx * cny * (C.zown1 - C.zown0) * 3;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t I = t / 3;
-    const int r = (int)(t - 3 * I);
-    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = (int)(I / ((int64_t)cnx * cny));
+    const int c = (int)(t - 3 * I);
+    const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = C.zown0 + (int)(I / ((int64_t)cnx * cny));
     const int fx = mg_fx(X, fnx), fy = mg_fx(Y, fny), fz = mg_fx(Z, fnz);
     double s = 0.0;
     for (int z = max(fz - 1, 0); z <= min(fz + 1, fnz - 1); ++z) {
@@ -304,27 +336,29 @@ __global__ void __launch_bounds__(256) k_mg_restrict(int fnx, int fny, int fnz, 
         for (int x = max(fx - 1, 0); x <= min(fx + 1, fnx - 1); ++x) {
           const double w = wy * mg_w(x, X, fnx);
           if (w == 0.0) continue;
-          const int64_t i = pbase ? (int64_t)pbase[z0 + z] + (int64_t)yy * fnx + x : ((int64_t)z * fny + yy) * fnx + x;
-          s = fma(w, b[3 * i + r] - y[3 * i + r], s);
+          const int64_t i = pbase ? (int64_t)pbase[z0 + z - p0] + (int64_t)yy * fnx + x : ((int64_t)(z - Fb.zbase) * fny + yy) * fnx + x;
+          s = fma(w, r[3 * i + c], s);
         }
       }
     }
-    bc[t] = s;
+    bc[3 * ((((int64_t)(Z - C.zbase)) * cny + Y) * cnx + X) + c] = s;
   }
 }
 
-// prolongation x += P xc: one thread per fine DoF gathers its <= 8 coarse parents; constrained DoFs (level 0) stay zero
-__global__ void __launch_bounds__(256) k_mg_prolong(int fnx, int fny, int fnz, int cnx, int cny, int cnz, const int32_t *__restrict__ pbase, int z0,
-                                                     const uint8_t *__restrict__ con, const double *__restrict__ xc, double *__restrict__ x) {
-  const int64_t total = (int64_t)fnx * fny * fnz * 3;
+// prolongation x += P xc on the fine planes [zown0, zown1): one thread per fine DoF gathers its <= 8 coarse parents (ghost
+// planes of xc filled beforehand); constrained DoFs (level 0) stay zero
+__global__ void __launch_bounds__(256) k_mg_prolong(const MgBox Fb, const int32_t *__restrict__ pbase, int z0, int p0,
+                                                     const uint8_t *__restrict__ con, const MgBox C, const double *__restrict__ xc, double *__restrict__ x) {
+  const int fnx = Fb.nx, fny = Fb.ny, fnz = Fb.NZ, cnx = C.nx, cny = C.ny;
+  const int64_t total = (int64_t)fnx * fny * (Fb.zown1 - Fb.zown0) * 3;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t il = t / 3;
     const int r = (int)(t - 3 * il);
-    const int xx = (int)(il % fnx), yy = (int)((il / fnx) % fny), zz = (int)(il / ((int64_t)fnx * fny));
-    const int64_t i = pbase ? (int64_t)pbase[z0 + zz] + (int64_t)yy * fnx + xx : il;
+    const int xx = (int)(il % fnx), yy = (int)((il / fnx) % fny), zz = Fb.zown0 + (int)(il / ((int64_t)fnx * fny));     // zz: global plane
+    const int64_t i = pbase ? (int64_t)pbase[z0 + zz - p0] + (int64_t)yy * fnx + xx : ((int64_t)(zz - Fb.zbase) * fny + yy) * fnx + xx;
     if (con && con[3 * i + r]) continue;
-    // parents per axis: the coarse node at x (weight 1), or the two at x - 1 and x + 1 (weight 1/2 each)
-    int px[2], py[2], pz[2], npx, npy, npz;
+    // parents per axis: the coarse node at v (weight 1), or the two at v - 1 and v + 1 (weight 1/2 each)
+    int px[2], py[2], pz[2];
     auto parents = [](int v, int n, int *p) -> int {
       if (n <= 2) { p[0] = v; return 1; }
       if (!(v & 1)) { p[0] = v >> 1; return 1; }
@@ -332,12 +366,12 @@ __global__ void __launch_bounds__(256) k_mg_prolong(int fnx, int fny, int fnz, i
       p[0] = (v - 1) >> 1; p[1] = (v + 1 == n - 1) ? mg_coarse_n(n) - 1 : (v + 1) >> 1;
       return 2;
     };
-    npx = parents(xx, fnx, px); npy = parents(yy, fny, py); npz = parents(zz, fnz, pz);
+    const int npx = parents(xx, fnx, px), npy = parents(yy, fny, py), npz = parents(zz, fnz, pz);
     const double w = 1.0 / (double)(npx * npy * npz);
     double s = 0.0;
     for (int c = 0; c < npz; ++c)
       for (int bq = 0; bq < npy; ++bq)
-        for (int a = 0; a < npx; ++a) s += xc[3 * ((((int64_t)pz[c] * cny) + py[bq]) * cnx + px[a]) + r];
+        for (int a = 0; a < npx; ++a) s += xc[3 * ((((int64_t)(pz[c] - C.zbase) * cny) + py[bq]) * cnx + px[a]) + r];
     x[3 * i + r] += w * s;
   }
 }
@@ -348,9 +382,15 @@ __global__ void __launch_bounds__(256) k_mg_xpby(int64_t n, const double *__rest
 __global__ void __launch_bounds__(256) k_mg_mask_copy(int64_t n, const double *__restrict__ b, const uint8_t *__restrict__ con, double *__restrict__ r) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) r[i] = con[i] ? 0.0 : b[i];
 }
-__global__ void __launch_bounds__(256) k_mg_fill_hash(int64_t n, unsigned seed, double *__restrict__ v) {   // fixed pseudo-random start vector
+__global__ void __launch_bounds__(256) k_mg_con_to_f64(int64_t n, const uint8_t *__restrict__ con, double *__restrict__ v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = con[i] ? 1.0 : 0.0;
+}
+__global__ void __launch_bounds__(256) k_mg_f64_to_con(int64_t n, const double *__restrict__ v, uint8_t *__restrict__ con) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) con[i] = v[i] != 0.0;
+}
+__global__ void __launch_bounds__(256) k_mg_fill_hash(int64_t n, unsigned seed, int64_t gofs, double *__restrict__ v) {   // fixed pseudo-random start vector
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    unsigned long long s = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
+    unsigned long long s = (unsigned long long)(i + gofs) * 0x9E3779B97F4A7C15ull + seed;
     s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
     v[i] = (double)(s & 0xffff) / 65536.0 - 0.5;
   }
@@ -366,19 +406,33 @@ static unsigned mg_grid(nls_context *h, int64_t n, int threads = 256) {
   return (unsigned)std::max<int64_t>(1, std::min(g, cap));
 }
 
-void nls_mg_free(nls_context *h) {
+static void mg_free_levels(nls_context *h) {
   MgPlan &m = h->mg;
   for (int l = 0; l < MG_MAX_LEVELS; ++l) {
     MgLevel &L = m.lev[l];
     if (L.K) cudaFree(L.K);
     if (L.dinv) cudaFree(L.dinv);
     for (double *v : {L.x, L.b, L.y, L.d}) if (v) cudaFree(v);
+    L = MgLevel();
   }
   if (m.vals32) cudaFree(m.vals32);
-  m = MgPlan();
+  for (double *v : {m.gbelow, m.gabove, m.gsend, m.rf}) if (v) cudaFree(v);
+  if (m.conf) cudaFree(m.conf);
+  m.vals32 = nullptr; m.gbelow = m.gabove = m.gsend = m.rf = nullptr; m.conf = nullptr;
+  m.laid_out = false; m.version = -1; m.power_version = -1000; m.nlev = 0;
 }
 
-// the hierarchy of a grid-topology mesh (called when the line plan is built or on first use); no values yet
+void nls_mg_free(nls_context *h) {
+  mg_free_levels(h);
+  MgPlan &m = h->mg;
+  m.ok = false;
+}
+
+// the communicator changed (or appeared): the levels are laid out again at the next set-up
+void nls_mg_invalidate(nls_context *h) { mg_free_levels(h); }
+
+// can this mesh have a hierarchy? (called when the line plan is built; the levels themselves are laid out at the first
+// set-up, when the communicator -- if any -- exists)
 int nls_mg_build(nls_context *h) {
   nls_mg_free(h);
   MgPlan &m = h->mg;
@@ -389,90 +443,251 @@ int nls_mg_build(nls_context *h) {
   if (z0 < 0) return NLS_OK;
   for (int z = z0; z < z1; ++z) if (!p.h_pown[z]) return NLS_OK;       // owned planes must be contiguous
   if ((int64_t)p.nx * p.ny * (z1 - z0) != h->n_owned) return NLS_OK;
-  m.z0 = z0;
-  int nx = p.nx, ny = p.ny, nz = z1 - z0, l = 0;
+  if (z0 > 1 || p.nzp - z1 > 1) return NLS_OK;                          // at most one ghost plane either side
+  if (std::max(p.nx, std::max(p.ny, z1 - z0)) <= 6 && z0 == 0 && p.nzp == z1) return NLS_OK;   // too small for a second level
+  m.z0 = z0; m.nzo = z1 - z0;
+  m.ghost_below = z0 == 1; m.ghost_above = p.nzp - z1 == 1;
+  m.ok = true;
+  return NLS_OK;
+}
+
+// single GPU: lay the levels out right away (multi-GPU: at the first set-up, when the communicator exists, or through
+// nls_solver_prepare, which is collective)
+static int mg_layout(nls_context *h);
+int nls_mg_prepare(nls_context *h, bool collective) {
+  MgPlan &m = h->mg;
+  if (!m.ok || (m.laid_out && m.dist == (h->distributed && h->nranks > 1))) return NLS_OK;
+  const bool ghosts = m.ghost_below || m.ghost_above;
+  if (!h->distributed && ghosts) return NLS_OK;
+  if (h->distributed && !collective) return NLS_OK;
+  NLS_TRY(mg_layout(h));
+  if (m.fp32 && !m.vals32 && cudaMalloc((void **)&m.vals32, sizeof(float) * (size_t)h->nnz) != cudaSuccess) { cudaGetLastError(); m.vals32 = nullptr; }
+  return NLS_OK;
+}
+
+static MgBox mg_box(const MgLevel &L) { MgBox b; b.nx = L.nx; b.ny = L.ny; b.nzb = L.nzb; b.zbase = L.zbase; b.NZ = L.NZ; b.zown0 = L.zown0; b.zown1 = L.zown1; return b; }
+
+// levels, ownership of the coarse planes, buffers. Collective when distributed.
+static int mg_layout(nls_context *h) {
+  MgPlan &m = h->mg;
+  const Lines3Plan &p = h->lplan;
+  mg_free_levels(h);
+  m.dist = h->distributed && h->nranks > 1;
+  m.rank_below = m.rank_above = -1;
+  int p0 = 0, NZ = m.nzo;
+  if (m.dist) {
+    // plane counts of all ranks (slabs are stacked in rank order)
+    std::vector<double> cnt((size_t)h->nranks, 0.0);
+    double *d_cnt = nullptr;
+    NLS_CUDA(h, cudaMalloc((void **)&d_cnt, sizeof(double) * h->nranks));
+    cnt[h->rank] = (double)m.nzo;
+    NLS_CUDA(h, cudaMemcpyAsync(d_cnt, cnt.data(), sizeof(double) * h->nranks, cudaMemcpyHostToDevice, h->stream));
+    if (h->nccl->AllReduce(d_cnt, d_cnt, (size_t)h->nranks, NCCL_DYN_FLOAT64, NCCL_DYN_SUM, h->comm, h->stream) != 0)
+      NLS_FAIL(h, NLS_ERR_NCCL, "multigrid: ncclAllReduce (plane counts) failed");
+    NLS_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(double) * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_cnt);
+    NZ = 0;
+    for (int r = 0; r < h->nranks; ++r) { if (r == h->rank) p0 = NZ; NZ += (int)cnt[r]; }
+    if (m.ghost_below) m.rank_below = h->rank - 1;
+    if (m.ghost_above) m.rank_above = h->rank + 1;
+    if (m.ghost_below != (p0 > 0) || m.ghost_above != (p0 + m.nzo < NZ))
+      NLS_FAIL(h, NLS_ERR_STATE, "multigrid: the slabs are not stacked in rank order");
+  } else if (m.ghost_below || m.ghost_above) {
+    NLS_FAIL(h, NLS_ERR_STATE, "multigrid: ghost planes without a communicator");
+  }
+  m.p0 = p0; m.NZ0 = NZ;
+  int nx = p.nx, ny = p.ny, nz = NZ, l = 0;
+  int own0 = p0, own1 = p0 + m.nzo;       // owned global planes on the current level
   for (;;) {
     MgLevel &L = m.lev[l];
-    L.nx = nx; L.ny = ny; L.nz = nz; L.nn = (int64_t)nx * ny * nz;
+    L.nx = nx; L.ny = ny; L.NZ = nz;
+    L.rown0 = own0; L.rown1 = own1;
+    if (l <= 1) {                          // distributed levels: owned planes + ghost planes
+      L.zown0 = own0; L.zown1 = own1;
+      L.zbase = own0 - ((own0 > 0 && m.dist) ? 1 : 0);
+      const int ztop = own1 + ((own1 < nz && m.dist) ? 1 : 0);
+      L.nzb = ztop - L.zbase;
+    } else {                               // replicated levels: the whole grid on every rank
+      L.zown0 = 0; L.zown1 = nz; L.zbase = 0; L.nzb = nz;
+    }
+    L.nn = (int64_t)nx * ny * L.nzb;
     const size_t nd = (size_t)(l == 0 ? h->ndof_local() : 3 * L.nn);
     if (l > 0) NLS_CUDA(h, cudaMalloc((void **)&L.K, sizeof(double) * 243 * (size_t)L.nn));
     NLS_CUDA(h, cudaMalloc((void **)&L.dinv, sizeof(double) * 9 * (size_t)(l == 0 ? h->nn : L.nn)));
-    if (l == 0) NLS_CUDA(h, cudaMemsetAsync(L.dinv, 0, sizeof(double) * 9 * (size_t)h->nn, h->stream));
+    NLS_CUDA(h, cudaMemsetAsync(L.dinv, 0, sizeof(double) * 9 * (size_t)(l == 0 ? h->nn : L.nn), h->stream));
     for (double **v : {&L.x, &L.b, &L.y, &L.d}) {
       if (l == 0 && (v == &L.b)) continue;                  // level 0: b is the caller's residual
       NLS_CUDA(h, cudaMalloc((void **)v, sizeof(double) * nd));
-      NLS_CUDA(h, cudaMemsetAsync(*v, 0, sizeof(double) * nd, h->stream));   // ghost entries stay zero for ever
+      NLS_CUDA(h, cudaMemsetAsync(*v, 0, sizeof(double) * nd, h->stream));
     }
     ++l;
     const int cx = mg_coarse_n(nx), cy = mg_coarse_n(ny), cz = mg_coarse_n(nz);
     if (l >= MG_MAX_LEVELS || std::max(nx, std::max(ny, nz)) <= 6 || (cx == nx && cy == ny && cz == nz)) break;
+    // coarse planes of this rank: those whose fine plane it owns
+    int c0 = 0, c1 = 0;
+    while (c0 < cz && mg_fx(c0, nz) < own0) ++c0;
+    c1 = c0;
+    while (c1 < cz && mg_fx(c1, nz) < own1) ++c1;
+    if (m.dist && l == 1 && c1 == c0) NLS_FAIL(h, NLS_ERR_STATE, "multigrid: a rank owns no coarse plane (slab too thin)");
+    own0 = c0; own1 = c1;
     nx = cx; ny = cy; nz = cz;
   }
   m.nlev = l;
-  m.ok = m.nlev >= 2;
+  if (m.nlev < 2) { m.ok = false; NLS_FAIL(h, NLS_ERR_STATE, "multigrid: the grid is too small for a hierarchy"); }
+  const size_t plane_rows = (size_t)p.nx * p.ny * 243;
+  if (m.dist) {
+    if (m.ghost_below) NLS_CUDA(h, cudaMalloc((void **)&m.gbelow, sizeof(double) * plane_rows));
+    if (m.ghost_above) NLS_CUDA(h, cudaMalloc((void **)&m.gabove, sizeof(double) * plane_rows));
+    NLS_CUDA(h, cudaMalloc((void **)&m.gsend, sizeof(double) * 2 * plane_rows));
+  }
+  NLS_CUDA(h, cudaMalloc((void **)&m.rf, sizeof(double) * (size_t)h->ndof_local()));
+  NLS_CUDA(h, cudaMemsetAsync(m.rf, 0, sizeof(double) * (size_t)h->ndof_local(), h->stream));
+  NLS_CUDA(h, cudaMalloc((void **)&m.conf, (size_t)h->ndof_local()));
+  m.laid_out = true;
   m.version = -1;
   return NLS_OK;
 }
 
 static MgFine mg_fine_args(nls_context *h) {
   const Lines3Plan &p = h->lplan;
-  const MgLevel &L = h->mg.lev[0];
+  const MgPlan &m = h->mg;
   MgFine F;
-  F.nx = L.nx; F.ny = L.ny; F.nz = L.nz; F.z0 = h->mg.z0; F.nzp = p.nzp;
-  F.pbase = p.d_pbase; F.pown = p.d_pown; F.info = reinterpret_cast<const MgL3Line *>(p.d_info);
-  F.vals = h->d_vals; F.con = h->d_con;
+  F.nx = p.nx; F.ny = p.ny; F.nzo = m.nzo; F.z0 = m.z0; F.p0 = m.p0; F.NZ = m.NZ0;
+  F.pbase = p.d_pbase; F.info = reinterpret_cast<const MgL3Line *>(p.d_info);
+  F.vals = h->d_vals; F.con = m.conf;
+  F.gbelow = m.gbelow; F.gabove = m.gabove;
   return F;
 }
 
-static int mg_apply_K(nls_context *h, int l, const double *x, double *y) {
-  MgLevel &L = h->mg.lev[l];
-  if (l == 0) return (h->mg.fp32 && h->mg.vals32) ? nls_launch_spmv_f32(h, h->mg.vals32, x, y) : nls_launch_spmv(h, x, y, true, false);
-  k_mg_spmv<<<mg_grid(h, 3 * L.nn), 256, 0, h->stream>>>(L.nx, L.ny, L.nz, L.K, x, y);
+// ghost planes of a distributed stencil-level array (npd doubles per node) <- the neighbours' boundary planes
+static int mg_exchange(nls_context *h, int l, double *a, int npd) {
+  MgPlan &m = h->mg;
+  if (!m.dist || l != 1) return NLS_OK;
+  MgLevel &L = m.lev[l];
+  const size_t pl = (size_t)L.nx * L.ny * npd;
+  const int g0 = L.zown0 - L.zbase, nown = L.zown1 - L.zown0;
+  NcclApi *nc = h->nccl;
+  if (nc->GroupStart() != 0) NLS_FAIL(h, NLS_ERR_NCCL, "ncclGroupStart failed");
+  int e = 0;
+  if (m.rank_below >= 0) {
+    e |= nc->Send(a + (size_t)g0 * pl, pl, NCCL_DYN_FLOAT64, m.rank_below, h->comm, h->stream);
+    e |= nc->Recv(a, pl, NCCL_DYN_FLOAT64, m.rank_below, h->comm, h->stream);
+  }
+  if (m.rank_above >= 0) {
+    e |= nc->Send(a + (size_t)(g0 + nown - 1) * pl, pl, NCCL_DYN_FLOAT64, m.rank_above, h->comm, h->stream);
+    e |= nc->Recv(a + (size_t)(g0 + nown) * pl, pl, NCCL_DYN_FLOAT64, m.rank_above, h->comm, h->stream);
+  }
+  const int ge = nc->GroupEnd();
+  if (e || ge) NLS_FAIL(h, NLS_ERR_NCCL, "multigrid: plane exchange (ncclSend/Recv) failed");
+  return NLS_OK;
+}
+
+// sum over the ranks of a replicated-level array (every rank wrote its planes, zeros elsewhere)
+static int mg_allsum(nls_context *h, double *a, size_t n) {
+  if (!h->mg.dist) return NLS_OK;
+  if (h->nccl->AllReduce(a, a, n, NCCL_DYN_FLOAT64, NCCL_DYN_SUM, h->comm, h->stream) != 0) NLS_FAIL(h, NLS_ERR_NCCL, "multigrid: ncclAllReduce failed");
+  return NLS_OK;
+}
+
+// y = K_l x on the owned rows; x's ghost entries are brought in first on the distributed levels
+static int mg_apply_K(nls_context *h, int l, double *x, double *y) {
+  MgPlan &m = h->mg;
+  MgLevel &L = m.lev[l];
+  if (l == 0) {
+    if (m.dist) NLS_TRY(nls_halo_exchange(h, x));
+    return (m.fp32 && m.vals32) ? nls_launch_spmv_f32(h, m.vals32, x, y) : nls_launch_spmv(h, x, y, true, false);
+  }
+  NLS_TRY(mg_exchange(h, l, x, 3));
+  k_mg_spmv<<<mg_grid(h, 3 * (int64_t)L.nx * L.ny * (L.zown1 - L.zown0)), 256, 0, h->stream>>>(mg_box(L), L.K, x, y);
   MG_KCHECK(h);
   return NLS_OK;
 }
 
-// largest eigenvalue of D^-1 K on level l by power iteration (start vector: a fixed pseudo-random pattern via the smoother
-// vectors; the estimate is inflated by 10 %, the usual safeguard of a Chebyshev smoother)
+// owned part of a level's vectors: offset (doubles) and node count
+static void mg_owned(nls_context *h, int l, int64_t *ofs, int64_t *nn) {
+  const MgLevel &L = h->mg.lev[l];
+  if (l == 0) { *ofs = 0; *nn = h->n_owned; }
+  else { *ofs = 3 * (int64_t)(L.zown0 - L.zbase) * L.nx * L.ny; *nn = (int64_t)(L.zown1 - L.zown0) * L.nx * L.ny; }
+}
+
+static int mg_dot(nls_context *h, int l, int64_t n, const double *x, const double *y, double *out) {
+  return l <= 1 ? nls_dev_dot(h, n, x, y, out) : nls_dev_dot_local(h, n, x, y, out);     // replicated levels: same value on every rank
+}
+
+// largest eigenvalue of D^-1 K on level l by power iteration (fixed pseudo-random start vector; the estimate is inflated
+// by 10 %, the usual safeguard of a Chebyshev smoother)
 static int mg_lambda_max(nls_context *h, int l, double *out) {
-  MgLevel &L = h->mg.lev[l];
-  const int64_t nn = l == 0 ? h->n_owned : L.nn, n = 3 * nn;
-  k_mg_fill_hash<<<mg_grid(h, n), 256, 0, h->stream>>>(n, (unsigned)l, L.x); MG_KCHECK(h);
-  if (l == 0) { k_mg_mask_copy<<<mg_grid(h, n), 256, 0, h->stream>>>(n, L.x, h->d_con, L.x); MG_KCHECK(h); }
+  MgPlan &m = h->mg;
+  MgLevel &L = m.lev[l];
+  int64_t ofs, nn;
+  mg_owned(h, l, &ofs, &nn);
+  const int64_t n = 3 * nn;
+  const int64_t gofs = l == 0 ? 3 * (int64_t)m.p0 * L.nx * L.ny : 3 * (int64_t)L.zown0 * L.nx * L.ny;
+  double *x = L.x + ofs, *y = L.y + ofs, *d = L.d + ofs;
+  k_mg_fill_hash<<<mg_grid(h, n), 256, 0, h->stream>>>(n, (unsigned)l, gofs, x); MG_KCHECK(h);
+  if (l == 0) { k_mg_mask_copy<<<mg_grid(h, n), 256, 0, h->stream>>>(n, x, h->d_con, x); MG_KCHECK(h); }
   double lam = 1.0;
-  for (int it = 0; it < h->mg.power_its; ++it) {
+  for (int it = 0; it < m.power_its; ++it) {
     double nrm2;
-    { // local norm (the preconditioner is rank-local: no allreduce)
-      NLS_TRY(nls_dev_dot_local(h, n, L.x, L.x, &nrm2));
-    }
+    NLS_TRY(mg_dot(h, l, n, x, x, &nrm2));
     if (!(nrm2 > 0.0)) { lam = 1.0; break; }
-    k_mg_scale<<<mg_grid(h, n), 256, 0, h->stream>>>(n, 1.0 / sqrt(nrm2), L.x); MG_KCHECK(h);
+    k_mg_scale<<<mg_grid(h, n), 256, 0, h->stream>>>(n, 1.0 / sqrt(nrm2), x); MG_KCHECK(h);
     NLS_TRY(mg_apply_K(h, l, L.x, L.y));
-    k_mg_apply_dinv<<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv, L.y, L.d); MG_KCHECK(h);
+    k_mg_apply_dinv<<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, y, d); MG_KCHECK(h);
     double xd;
-    NLS_TRY(nls_dev_dot_local(h, n, L.x, L.d, &xd));
+    NLS_TRY(mg_dot(h, l, n, x, d, &xd));
     lam = xd;                                    // Rayleigh quotient of the normalised iterate
-    NLS_CUDA(h, cudaMemcpyAsync(L.x, L.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    NLS_CUDA(h, cudaMemcpyAsync(x, d, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
   }
-  NLS_CUDA(h, cudaMemsetAsync(L.x, 0, sizeof(double) * n, h->stream));
-  NLS_CUDA(h, cudaMemsetAsync(L.d, 0, sizeof(double) * n, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
+  NLS_CUDA(h, cudaMemsetAsync(d, 0, sizeof(double) * n, h->stream));
   *out = 1.1 * fabs(lam);
   return NLS_OK;
 }
 
-// Galerkin operators, block inverses and eigenvalue bounds for the current CSR values
+// Galerkin operators, block inverses and eigenvalue bounds for the current CSR values. Collective when distributed.
 int nls_mg_setup(nls_context *h) {
   MgPlan &m = h->mg;
   if (!m.ok) NLS_FAIL(h, NLS_ERR_STATE, "multigrid: no hierarchy for this mesh");
+  if (!m.laid_out || m.dist != (h->distributed && h->nranks > 1)) NLS_TRY(mg_layout(h));
   if (m.version == h->vals_version) return NLS_OK;
-  const MgFine F = mg_fine_args(h);
-  k_mg_fine_dinv<<<mg_grid(h, m.lev[0].nn), 256, 0, h->stream>>>(F, m.lev[0].dinv); MG_KCHECK(h);
+  {   // the constrained mask of every local node: ghost nodes are constrained by their owners only
+    const int64_t nl = h->ndof_local();
+    k_mg_con_to_f64<<<mg_grid(h, nl), 256, 0, h->stream>>>(nl, h->d_con, m.rf); MG_KCHECK(h);
+    if (m.dist) NLS_TRY(nls_halo_exchange(h, m.rf));
+    k_mg_f64_to_con<<<mg_grid(h, nl), 256, 0, h->stream>>>(nl, m.rf, m.conf); MG_KCHECK(h);
+    NLS_CUDA(h, cudaMemsetAsync(m.rf, 0, sizeof(double) * (size_t)nl, h->stream));
+  }
+  MgFine F = mg_fine_args(h);
+  k_mg_fine_dinv<<<mg_grid(h, (int64_t)F.nx * F.ny * F.nzo), 256, 0, h->stream>>>(F, m.lev[0].dinv); MG_KCHECK(h);
+  if (m.dist) {      // boundary row planes of the CSR matrix, in stencil format, to the neighbours
+    const size_t pr = (size_t)F.nx * F.ny * 243;
+    NcclApi *nc = h->nccl;
+    if (m.rank_below >= 0) { k_mg_export_rows<<<mg_grid(h, (int64_t)F.nx * F.ny * 27), 256, 0, h->stream>>>(F, 0, m.gsend); MG_KCHECK(h); }
+    if (m.rank_above >= 0) { k_mg_export_rows<<<mg_grid(h, (int64_t)F.nx * F.ny * 27), 256, 0, h->stream>>>(F, F.nzo - 1, m.gsend + pr); MG_KCHECK(h); }
+    if (nc->GroupStart() != 0) NLS_FAIL(h, NLS_ERR_NCCL, "ncclGroupStart failed");
+    int e = 0;
+    if (m.rank_below >= 0) { e |= nc->Send(m.gsend, pr, NCCL_DYN_FLOAT64, m.rank_below, h->comm, h->stream); e |= nc->Recv(m.gbelow, pr, NCCL_DYN_FLOAT64, m.rank_below, h->comm, h->stream); }
+    if (m.rank_above >= 0) { e |= nc->Send(m.gsend + pr, pr, NCCL_DYN_FLOAT64, m.rank_above, h->comm, h->stream); e |= nc->Recv(m.gabove, pr, NCCL_DYN_FLOAT64, m.rank_above, h->comm, h->stream); }
+    const int ge = nc->GroupEnd();
+    if (e || ge) NLS_FAIL(h, NLS_ERR_NCCL, "multigrid: row exchange (ncclSend/Recv) failed");
+  }
   for (int l = 1; l < m.nlev; ++l) {
     MgLevel &Lf = m.lev[l - 1], &Lc = m.lev[l];
-    if (l == 1 && m.rap_warp) k_mg_rap_fine_warp<<<mg_grid(h, Lc.nn * 32, 128), 128, 0, h->stream>>>(F, Lc.nx, Lc.ny, Lc.nz, Lc.K);
-    else if (l == 1) k_mg_rap<true><<<mg_grid(h, Lc.nn * 27, 128), 128, 0, h->stream>>>(F, nullptr, Lf.nx, Lf.ny, Lf.nz, Lc.nx, Lc.ny, Lc.nz, Lc.K);
-    else k_mg_rap<false><<<mg_grid(h, Lc.nn * 27, 128), 128, 0, h->stream>>>(F, Lf.K, Lf.nx, Lf.ny, Lf.nz, Lc.nx, Lc.ny, Lc.nz, Lc.K);
-    MG_KCHECK(h);
+    MgBox C = mg_box(Lc);
+    // levels >= 2 are replicated: every rank computes the rows whose fine planes it owns (all of them from level 3 on, where
+    // the fine operator is already whole on every rank), zeros elsewhere, and the ranks sum
+    const bool partial = l == 2 && m.dist;
+    if (partial) { C.zown0 = Lc.rown0; C.zown1 = Lc.rown1; NLS_CUDA(h, cudaMemsetAsync(Lc.K, 0, sizeof(double) * 243 * (size_t)Lc.nn, h->stream)); }
+    const int64_t nown = (int64_t)Lc.nx * Lc.ny * (C.zown1 - C.zown0);
+    if (nown > 0) {
+      if (l == 1) k_mg_rap_fine_warp<<<mg_grid(h, nown * 32, 128), 128, 0, h->stream>>>(F, C, Lc.K);
+      else k_mg_rap<<<mg_grid(h, nown * 27, 128), 128, 0, h->stream>>>(mg_box(Lf), Lf.K, C, Lc.K);
+      MG_KCHECK(h);
+    }
+    if (l == 1) NLS_TRY(mg_exchange(h, 1, Lc.K, 243));
+    else if (partial) NLS_TRY(mg_allsum(h, Lc.K, 243 * (size_t)Lc.nn));
     k_mg_dinv<<<mg_grid(h, Lc.nn), 256, 0, h->stream>>>(Lc.nn, Lc.K, Lc.dinv); MG_KCHECK(h);
   }
   if (m.fp32) {
@@ -489,10 +704,11 @@ int nls_mg_setup(nls_context *h) {
   return NLS_OK;
 }
 
-// Chebyshev smoothing of K_l x = b on [lmax / ratio, lmax]; zero = x starts from zero
+// Chebyshev smoothing of K_l x = b on [lmax / ratio, lmax]; zero = x starts from zero. x, b: whole level arrays.
 static int mg_cheb(nls_context *h, int l, const double *b, double *x, int degree, double ratio, bool zero) {
   MgLevel &L = h->mg.lev[l];
-  const int64_t nn = l == 0 ? h->n_owned : L.nn;
+  int64_t ofs, nn;
+  mg_owned(h, l, &ofs, &nn);
   const double lmax = L.lmax, lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double rho = 1.0 / sigma;
   for (int k = 0; k < degree; ++k) {
@@ -501,8 +717,8 @@ static int mg_cheb(nls_context *h, int l, const double *b, double *x, int degree
     double a, c;
     if (k == 0) { a = 0.0; c = 1.0 / theta; }
     else { const double rn = 1.0 / (2.0 * sigma - rho); a = rn * rho; c = 2.0 * rn / delta; rho = rn; }
-    // the first step of a run always restarts the direction d (a = 0); `first` also means x = 0 (no product, x = d)
-    k_mg_cheb<<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv, b, first ? nullptr : L.y, L.d, x, a, c, first ? 1 : (k == 0 ? 2 : 0));
+    k_mg_cheb<<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, b + ofs, first ? nullptr : L.y + ofs, L.d + ofs, x + ofs, a, c,
+                                                     first ? 1 : (k == 0 ? 2 : 0));
     MG_KCHECK(h);
   }
   return NLS_OK;
@@ -515,16 +731,31 @@ static int mg_vcycle(nls_context *h, int l, const double *b, double *x) {
   NLS_TRY(mg_cheb(h, l, b, x, m.degree, m.ratio, true));
   NLS_TRY(mg_apply_K(h, l, x, L.y));
   MgLevel &C = m.lev[l + 1];
-  k_mg_restrict<<<mg_grid(h, 3 * C.nn), 256, 0, h->stream>>>(L.nx, L.ny, L.nz, C.nx, C.ny, C.nz, l == 0 ? h->lplan.d_pbase : nullptr, m.z0, b, L.y, C.b);
-  MG_KCHECK(h);
+  int64_t ofs, nn;
+  mg_owned(h, l, &ofs, &nn);
+  // residual of the owned rows, its ghost planes, restriction to the coarse planes this rank owns
+  double *r = l == 0 ? m.rf : L.y;
+  k_mg_residual<<<mg_grid(h, 3 * nn), 256, 0, h->stream>>>(3 * nn, b + ofs, L.y + ofs, r + ofs); MG_KCHECK(h);
+  if (l == 0) { if (m.dist) NLS_TRY(nls_halo_exchange(h, r)); }
+  else NLS_TRY(mg_exchange(h, l, r, 3));
+  MgBox Cb = mg_box(C);
+  const bool partial = l + 1 == 2 && m.dist;      // first replicated level: this rank's planes, then the sum over the ranks
+  if (partial) { Cb.zown0 = C.rown0; Cb.zown1 = C.rown1; NLS_CUDA(h, cudaMemsetAsync(C.b, 0, sizeof(double) * 3 * (size_t)C.nn, h->stream)); }
+  const int64_t ncown = (int64_t)C.nx * C.ny * (Cb.zown1 - Cb.zown0);
+  if (ncown > 0) {
+    k_mg_restrict<<<mg_grid(h, 3 * ncown), 256, 0, h->stream>>>(mg_box(L), l == 0 ? h->lplan.d_pbase : nullptr, m.z0, m.p0, Cb, r, C.b);
+    MG_KCHECK(h);
+  }
+  if (partial) NLS_TRY(mg_allsum(h, C.b, 3 * (size_t)C.nn));
   NLS_TRY(mg_vcycle(h, l + 1, C.b, C.x));
-  k_mg_prolong<<<mg_grid(h, 3 * L.nn), 256, 0, h->stream>>>(L.nx, L.ny, L.nz, C.nx, C.ny, C.nz, l == 0 ? h->lplan.d_pbase : nullptr, m.z0,
-                                                            l == 0 ? h->d_con : nullptr, C.x, x);
+  NLS_TRY(mg_exchange(h, l + 1, C.x, 3));
+  k_mg_prolong<<<mg_grid(h, 3 * nn), 256, 0, h->stream>>>(mg_box(L), l == 0 ? h->lplan.d_pbase : nullptr, m.z0, m.p0,
+                                                          l == 0 ? h->d_con : nullptr, mg_box(C), C.x, x);
   MG_KCHECK(h);
   return mg_cheb(h, l, b, x, m.degree, m.ratio, false);
 }
 
-// z = M^-1 r (r masked, ghost entries of z stay zero)
+// z = M^-1 r (r masked; z's ghost entries are scratch)
 int nls_mg_apply(nls_context *h, const double *r, double *z) {
   if (h->mg.mode == 1) {        // block-Jacobi alone
     k_mg_apply_dinv<<<mg_grid(h, h->n_owned), 256, 0, h->stream>>>(h->n_owned, h->mg.lev[0].dinv, r, z);

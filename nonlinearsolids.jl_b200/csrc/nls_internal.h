@@ -105,24 +105,34 @@ struct Lines3Plan {
 // geometric multigrid preconditioner on grid-topology meshes (kernels_mg.cu)
 #define MG_MAX_LEVELS 10
 struct MgLevel {
-  int nx = 0, ny = 0, nz = 0;
-  int64_t nn = 0;
+  int nx = 0, ny = 0, NZ = 0;      // global grid of the level
+  int nzb = 0, zbase = 0;          // planes stored here: global [zbase, zbase + nzb) (levels >= 2: the whole grid)
+  int zown0 = 0, zown1 = 0;        // planes this rank works on (levels >= 2: all)
+  int rown0 = 0, rown1 = 0;        // planes whose fine planes this rank owns (its share of a replicated level's sums)
+  int64_t nn = 0;                  // nodes stored
   double *K = nullptr;             // [nn][27][9] Galerkin operator (levels >= 1; level 0 is the CSR Jacobian)
-  double *dinv = nullptr;          // [nn][9] inverse node blocks
+  double *dinv = nullptr;          // [nn][9] inverse node blocks (level 0: by node id)
   double *x = nullptr, *b = nullptr, *y = nullptr, *d = nullptr;
   double lmax = 1.0;               // largest eigenvalue of D^-1 K (power iteration, inflated)
 };
 struct MgPlan {
-  bool ok = false;
-  int nlev = 0, z0 = 0;
+  bool ok = false;                 // the mesh can have a hierarchy
+  bool laid_out = false;           // levels and buffers exist (first set-up; again when the communicator changes)
+  bool dist = false;
+  bool ghost_below = false, ghost_above = false;
+  int nlev = 0, z0 = 0, nzo = 0;   // line-table index of the first owned plane, owned planes
+  int p0 = 0, NZ0 = 0;             // global index of the first owned plane, global plane count
+  int rank_below = -1, rank_above = -1;
   int64_t version = -1;            // vals_version the operators were built for
   int mode = 2;                    // 1 block-Jacobi alone, 2 V-cycle
   int degree = 2, coarse_degree = 24, power_its = 10;
   double ratio = 8.0, coarse_ratio = 60.0;
-  int rap_warp = 1;                // level-1 Galerkin product: one warp per coarse node (0: one thread per stencil slot)
   int fp32 = 1;                    // the smoother's level-0 products read a single-precision copy of the CSR values
   float *vals32 = nullptr;
   int64_t power_version = -1000;   // vals_version of the last full power iteration
+  double *gbelow = nullptr, *gabove = nullptr, *gsend = nullptr;   // level-0 boundary row planes in stencil format
+  double *rf = nullptr;            // level-0 residual with ghost entries (restriction input)
+  uint8_t *conf = nullptr;         // constrained mask of all local nodes, ghost entries from their owners
   MgLevel lev[MG_MAX_LEVELS];
 };
 
@@ -363,6 +373,8 @@ int nls_dev_dot_local(nls_context *h, int64_t n, const double *x, const double *
 int nls_launch_vals_to_f32(nls_context *h, float *out);
 int nls_launch_spmv_f32(nls_context *h, const float *vals32, const double *x, double *y);
 void nls_mg_free(nls_context *h);
+void nls_mg_invalidate(nls_context *h);
 int nls_mg_build(nls_context *h);
+int nls_mg_prepare(nls_context *h, bool collective);
 int nls_mg_setup(nls_context *h);
 int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status);

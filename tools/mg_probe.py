@@ -29,6 +29,7 @@ for pc in pre:
     for k, v in kv.items():
         H.call("nls_set_option", k.encode(), int(v))
     H.call("nls_dev_upload_u", dp(Uaff))
+    H.call("nls_solver_prepare")
     opts = nls._lib.NewtonOpts(rtol=1e-10, atol=1e-14, dtol=1e6, maxits=25, type_modified=0, lin_rtol=lin_rtol, lin_maxits=100000)
     res = nls._lib.NewtonResult()
     hist = np.zeros(64)
