@@ -18,6 +18,9 @@
 // planes, zeros elsewhere) and every rank runs the same coarse cycle. The iteration count does not depend on the rank count.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "nls_internal.h"
 #include "nccl_dyn.h"
@@ -454,6 +457,8 @@ int nls_mg_build(nls_context *h) {
 // single GPU: lay the levels out right away (multi-GPU: at the first set-up, when the communicator exists, or through
 // nls_solver_prepare, which is collective)
 static int mg_layout(nls_context *h);
+static int mg_exchange(nls_context *h, int l, double *a, int npd);
+static int mg_allsum(nls_context *h, double *a, size_t n);
 int nls_mg_prepare(nls_context *h, bool collective) {
   MgPlan &m = h->mg;
   if (!m.ok || (m.laid_out && m.dist == (h->distributed && h->nranks > 1))) return NLS_OK;
@@ -462,6 +467,11 @@ int nls_mg_prepare(nls_context *h, bool collective) {
   if (h->distributed && !collective) return NLS_OK;
   NLS_TRY(mg_layout(h));
   if (m.fp32 && !m.vals32 && cudaMalloc((void **)&m.vals32, sizeof(float) * (size_t)h->nnz) != cudaSuccess) { cudaGetLastError(); m.vals32 = nullptr; }
+  if (m.dist) {      // NCCL opens its point-to-point channels at the first send/recv between two ranks (~0.3 s): do it here
+    NLS_TRY(mg_exchange(h, 1, m.lev[1].x, 3));
+    if (m.nlev > 2) NLS_TRY(mg_allsum(h, m.lev[2].b, 3 * (size_t)m.lev[2].nn));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return NLS_OK;
 }
 
@@ -769,7 +779,12 @@ int nls_mg_apply(nls_context *h, const double *r, double *z) {
 //      per iteration cost nothing beside them) ----
 int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status) {
   const int64_t n = h->nrows;
+  static const bool timing = std::getenv("NLS_B200_MG_TIMING") != nullptr;
+  auto now = [&]() { cudaStreamSynchronize(h->stream); return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = timing ? now() : 0.0;
   NLS_TRY(nls_mg_setup(h));
+  const double t1 = timing ? now() : 0.0;
+  double t_prec = 0.0, t_spmv = 0.0;
   MgLevel &L0 = h->mg.lev[0];
   double *x = h->d_dU, *r = h->d_r, *p = h->d_p, *Ap = h->d_Ap, *z = L0.x;
   k_mg_mask_copy<<<mg_grid(h, n), 256, 0, h->stream>>>(n, h->d_b, h->d_con, r); MG_KCHECK(h);
@@ -785,8 +800,10 @@ int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *
     NLS_CUDA(h, cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
     const double tol2 = rtol * rtol;
     while (it < maxits) {
+      const double ta = timing ? now() : 0.0;
       NLS_TRY(nls_halo_exchange(h, p));
       NLS_TRY(nls_launch_spmv(h, p, Ap, true, false));
+      if (timing) t_spmv += now() - ta;
       double pAp;
       NLS_TRY(nls_dev_dot(h, n, p, Ap, &pAp));
       if (!(pAp > 0.0) || !(rz == rz)) { st = 2; break; }
@@ -797,7 +814,9 @@ int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *
       NLS_TRY(nls_dev_dot(h, n, r, r, &rr));
       if (!(rr == rr)) { st = 2; break; }
       if (rr <= tol2 * bb) { st = 0; break; }
+      const double tb = timing ? now() : 0.0;
       NLS_TRY(nls_mg_apply(h, r, z));
+      if (timing) t_prec += now() - tb;
       double rzn;
       NLS_TRY(nls_dev_dot(h, n, r, z, &rzn));
       const double beta = rzn / rz;
@@ -805,6 +824,7 @@ int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *
       k_mg_xpby<<<mg_grid(h, n), 256, 0, h->stream>>>(n, z, beta, p); MG_KCHECK(h);
     }
   }
+  if (timing) fprintf(stderr, "[mg rank %d] set-up %.2f ms, %d iterations %.2f ms: V-cycles %.2f ms, Krylov products %.2f ms\n", h->rank, t1 - t0, it, now() - t1, t_prec, t_spmv);
   if (its) *its = it;
   if (relres) *relres = bb > 0.0 ? sqrt(rr / bb) : 0.0;
   if (status) *status = st;
