@@ -378,12 +378,19 @@ def run_ours(args):
         tot_ms = allmax(res.ms_total)
         its = max(1, res.iterations)
         spmv_bytes = 12 * nnz + 24 * nrows
-        pcg_iter_bytes = spmv_bytes + 128 * nrows
+        precond = int(L.nls_krylov_preconditioner(H.h))
+        if precond == 2:
+            # multigrid-preconditioned CG: one FP64 product, 2 x degree products on the single-precision copy of the values
+            # (4 B value + 4/9 B block column per nonzero), ~60 vector passes on level 0; coarser levels add about 1/7
+            pcg_iter_bytes = spmv_bytes + (8.0 / 7.0) * (4 * ((4 + 4.0 / 9.0) * nnz + 24 * nrows) + 60 * 8 * nrows)
+        else:
+            pcg_iter_bytes = spmv_bytes + 128 * nrows
         abytes = algorithmic_bytes(dim, mesh.nen, mesh.nel, mesh.nn, nrows, nnz)
         alg = (res.iterations + 1) * abytes + res.lin_its_total * pcg_iter_bytes + res.iterations * 32 * nrows
         hbm, _ = measured_peaks()
         newton = {"ms": tot_ms / its, "total_ms": tot_ms, "iterations": int(res.iterations), "reason": int(res.reason),
                   "converged": int(res.reason) in (1, 2), "pcg_iterations": int(res.lin_its_total),
+                  "preconditioner": {0: "Jacobi", 1: "block-Jacobi", 2: "geometric multigrid V-cycle (Chebyshev / block-Jacobi smoothing, Galerkin coarse operators)"}.get(precond, str(precond)),
                   "ms_assembly": allmax(res.ms_assembly), "ms_linear": allmax(res.ms_linear),
                   "rtol": 1e-10, "atol": 1e-14, "lin_rtol": args.lin_rtol,
                   "load": "face 0 of the slowest axis clamped, opposite face -0.1*t at t=0.1 (1 %% compression), affine initial guess",

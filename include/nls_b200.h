@@ -217,14 +217,21 @@ int32_t nls_assembly_scheme(nls_handle h);
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
  * {staging, element phase, 0, block-task phase, clusters, cp.async wait, barrier, issue of the next stage}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);
+/* preconditioner of the next Krylov solve: 0 Jacobi, 1 block-Jacobi, 2 geometric multigrid (nls_set_option "precond") */
+int32_t nls_krylov_preconditioner(nls_handle h);
 /* optional, collective after nls_comm_init: allocate the solver's work space (the multigrid hierarchy of the Krylov
  * preconditioner on grid-topology 3-D meshes) now instead of inside the first solve */
 int32_t nls_solver_prepare(nls_handle h);
 int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24); /* + per-warp phase cycles of the 3-D line kernel */
 /* selects a kernel variant for A/B measurement: key "assembly" -> 0 atomic scatter, 1 the default row-owner scheme
- * (2-D: shared-memory gather; 3-D: atomic scatter unless "twophase_3d" = 1), 2 element records + row owners;
+ * (2-D: shared-memory gather; 3-D grid-topology meshes: row-owner line kernel with TMA row stores, other 3-D meshes: atomic
+ * scatter unless "twophase_3d" = 1), 2 element records + row owners;
  * "scratch_mb" -> byte budget of the element-record scratch; "gather_ctas" -> persistent CTAs per SM;
- * "spmv" -> 0 scalar CSR, 1 block-aware; "spmv_lanes" -> lanes per node (0 = default) */
+ * "spmv" -> 0 scalar CSR, 1 block-aware; "spmv_lanes" -> lanes per node (0 = default);
+ * "precond" -> preconditioner of the Krylov solve that replaces `\`: -1 automatic (multigrid on grid-topology 3-D meshes of
+ * >= 10 000 nodes, else Jacobi), 0 Jacobi, 1 block-Jacobi, 2 multigrid; "mg_degree" / "mg_ratio_x10" / "mg_coarse_degree" /
+ * "mg_coarse_ratio" -> Chebyshev smoother (degree, eigenvalue interval), "mg_power_its" -> power iterations of the eigenvalue
+ * bound, "mg_fp32" -> 1: the smoother's level-0 products read a single-precision copy of the CSR values (default) */
 int32_t nls_set_option(nls_handle h, const char *key, int32_t value);
 
 /* ---- multi-GPU: one process per GPU, element-partitioned slabs ---------------- */

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "nls_debug_counters": (C.c_int32, [_H, _lp]),
     "nls_debug_counters_ext": (C.c_int32, [_H, _lp]),
     "nls_solver_prepare": (C.c_int32, [_H]),
+    "nls_krylov_preconditioner": (C.c_int32, [_H]),
     "nls_assembly_scheme": (C.c_int32, [_H]),
     "nls_partition": (C.c_int32, [C.c_int32, C.c_int64, _ip, C.c_int32, _lp, C.c_int32,
                                   _lp, _lp, _lp, _lp, _lp, _lp]),

@@ -941,6 +941,14 @@ extern "C" int32_t nls_debug_counters(nls_handle h, int64_t *out8) {
 }
 
 // the 3-D line kernel's per-warp phase-B cycles follow the 8 shared counters: 24 values in all
+// which preconditioner the next Krylov solve of this model uses: 0 Jacobi, 1 block-Jacobi, 2 multigrid
+extern "C" int32_t nls_krylov_preconditioner(nls_handle h) {
+  if (!h) return -1;
+  const bool mg_possible = h->mg.ok && (h->distributed || !(h->mg.ghost_below || h->mg.ghost_above));
+  if (mg_possible && (h->opt_precond >= 1 || (h->opt_precond < 0 && h->nn >= 10000))) return h->opt_precond == 1 ? 1 : 2;
+  return 0;
+}
+
 // Allocates what the first linear solve would otherwise allocate inside its timed region (the multigrid hierarchy of a
 // grid-topology 3-D mesh). Collective after nls_comm_init. Optional: the solvers do it themselves on first use.
 extern "C" int32_t nls_solver_prepare(nls_handle h) {
