@@ -36,10 +36,17 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--assembly", type=int, default=None)
     a = ap.parse_args()
+    # prescribed compression -0.1 t of the top face, PseudoTimeStepper steps of dt = 0.1 (1 % of the height per
+    # step), Newton rtol 1e-10. C3: the first step alone; C4: all ten (t = 0.1 ... 1.0, 10 % compression at the end).
     if a.config == "C3":
         a.dim, a.n, a.mode = 3, 150, "newton"
+        a.rtol = min(a.rtol, 1e-10)
+        if a.dstep <= 0: a.dstep = 0.01
     if a.config == "C4":
         a.dim, a.n, a.mode = 3, 216, "steps"
+        a.rtol = min(a.rtol, 1e-10)
+        if a.dstep <= 0: a.dstep = 0.01
+        if a.steps == 2: a.steps = 10
 
     real = os.dup(1); os.dup2(2, 1)         # NCCL prints to stdout
     import __graft_entry__ as g
@@ -152,6 +159,8 @@ def main():
         nsteps = a.steps if a.mode == "steps" else 1
         opts = nls._lib.NewtonOpts(0, 1e-14, a.rtol, 1e6, a.maxits, a.lin_rtol, 200000)
         U = np.zeros(fem.ndof)
+        H.call("nls_solver_prepare")
+        out["preconditioner"] = int(L.nls_krylov_preconditioner(H.h))
         steps = []
         for s in range(1, nsteps + 1):
             fem.updateboundaries(s * dstep)
