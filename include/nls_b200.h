@@ -44,7 +44,11 @@ typedef enum {
   NLS_MAT_LINEAR_ELASTIC_1D = 0,   /* params: E                       (linearelasticity.jl:11-19) */
   NLS_MAT_EXPONENTIAL_1D = 1,      /* params: sigma_sat, b            (exponential.jl:11-21) */
   NLS_MAT_ELASTOPLASTIC_1D = 2,    /* params: E, Hk, Ha, k0, a0, Eep  (linearelastoplasticity.jl:5-20) */
-  NLS_MAT_NEOHOOKEAN = 3           /* params: mu, lambda; dim 2 (plane strain) or 3 */
+  NLS_MAT_NEOHOOKEAN = 3,          /* params: mu, lambda; dim 2 (plane strain) or 3 */
+  NLS_MAT_J2_SMALL_STRAIN = 4      /* params: K (bulk), G (shear), sigma_y, H (isotropic hardening); dim 2 (plane strain) or 3.
+                                      The stateful-material protocol of linearelastoplasticity.jl:60-117 on Q1 elements
+                                      (SURVEY 8 f-2): per-qp committed / trial plastic strain and alpha, radial return in the
+                                      internal-force pass, stored consistent-tangent data read by the tangent pass */
 } nls_material_kind;
 
 /* src/nonlinearsolvers/types.jl:22-32 REASON_* singletons, 1:1 */
@@ -128,7 +132,8 @@ int32_t nls_set_body_force(nls_handle h, int32_t ncomp, const double *f);
 int32_t nls_init_state(nls_handle h);
 /* save_state!(material, fem, U, ctx), called from poststep! (timesteppers/types.jl:74-78) */
 int32_t nls_commit_state(nls_handle h, const double *U);
-/* read back one per-qp state array by name: "sig","alp","kap","gam","dsig" (+"_n") */
+/* read back one per-qp state array by name: 1-D elastoplasticity "sig","alp","kap","gam","dsig" (+"_n");
+ * J2: "epsp_xx","epsp_yy","epsp_zz","epsp_xy","epsp_yz","epsp_xz","alpha" (trial; +"_n" = committed) */
 int32_t nls_get_state(nls_handle h, const char *name, double *out /*[nelem][nq]*/);
 
 /* ---- CSR pattern (host-built; replaces the dense K of newton_fem.jl:41,52) ---- */

@@ -12,7 +12,7 @@ from .fem import (Dirichlet, Element, ElementBoundary, FEMModel, Lagrange, Mesh,
                   TimeDependent, dN, gauss_quadrature, getstate, integrate, interpolate, lagrange)
 from .gallery import (CSRMatrix, DistributedForce, Jacobian, Residual, applymass, assemblemass, compute_dinternalforce,
                       compute_internalforce, residual_jacobian)
-from .materials import (ExponentialMaterial, LinearElasticity1D, LinearElastoPlasticity1D, NeoHookean,
+from .materials import (ExponentialMaterial, J2Plasticity, LinearElasticity1D, LinearElastoPlasticity1D, NeoHookean,
                         initialize_state, save_state)
 from .meshes import bar_mesh, face_nodes, grid_mesh, slab_local_mesh, slab_planes, smooth_field
 from .solvers import (REASON_CONVERGED_ABSOLUTE, REASON_CONVERGED_RELATIVE, REASON_DIVERGED_LINEAR_SOLVE,

@@ -20,7 +20,7 @@ _bp = C.POINTER(C.c_uint8)
 STATUS = {0: "NLS_OK", 1: "NLS_ERR_ARG", 2: "NLS_ERR_STATE", 3: "NLS_ERR_CUDA", 4: "NLS_ERR_NCCL",
           5: "NLS_ERR_NOGPU", 6: "NLS_ERR_UNSUPPORTED"}
 
-MAT_LINEAR_ELASTIC_1D, MAT_EXPONENTIAL_1D, MAT_ELASTOPLASTIC_1D, MAT_NEOHOOKEAN = 0, 1, 2, 3
+MAT_LINEAR_ELASTIC_1D, MAT_EXPONENTIAL_1D, MAT_ELASTOPLASTIC_1D, MAT_NEOHOOKEAN, MAT_J2_SMALL_STRAIN = 0, 1, 2, 3, 4
 
 
 class NewtonOpts(C.Structure):

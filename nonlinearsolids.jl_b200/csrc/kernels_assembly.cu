@@ -488,6 +488,7 @@ int nls_launch_assembly(nls_context *h, bool want_r, bool want_k) {
       default: NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D elements support p = 1..7");
     }
   }
+  if (h->mat.kind == NLS_MAT_J2_SMALL_STRAIN) return nls_launch_j2(h, a, want_r, want_k);
   const int mode = nls_assembly_mode(h);
   if (mode == NLS_ASM_GATHER) return nls_launch_gather_2d(h, want_r, want_k);
   if (mode == NLS_ASM_TWOPHASE) return nls_launch_twophase(h, want_r, want_k);

@@ -332,7 +332,7 @@ k_asm_q1_2d_gather(const AsmArgs A, const GatherArgs P, const __grid_constant__ 
 
 // ---- host side: pack the cluster plan into fixed-stride device arrays ---------------------------
 int nls_assembly_mode(nls_context *h) {
-  if (h->opt_assembly == 0 || h->dim < 2) return NLS_ASM_ATOMIC;
+  if (h->opt_assembly == 0 || h->dim < 2 || h->mat.kind == NLS_MAT_J2_SMALL_STRAIN) return NLS_ASM_ATOMIC;
   if (h->dim == 2 && h->opt_assembly == 1 && h->have_plan) return NLS_ASM_GATHER;
   TwoPhasePlan &t = h->tplan;
   if (h->dim == 3 && h->opt_assembly == 1 && h->lplan.ok) return NLS_ASM_LINES;

@@ -43,6 +43,8 @@ __global__ void k_negate_into(int64_t n, const double *x, double *y) {
 }
 
 static void free_pattern(nls_context *h) {
+  nls_direct_free(h);
+  nls_j2_free(h);
   dev_free(&h->d_browptr); dev_free(&h->d_bcol); dev_free(&h->d_rowptr); dev_free(&h->d_colind);
   dev_free(&h->d_vals); dev_free(&h->d_pos); dev_free(&h->d_diag);
   nls_gather_free(h);
@@ -57,6 +59,7 @@ static void free_pattern(nls_context *h) {
 }
 
 static int alloc_state(nls_context *h) {
+  if (h->mat.kind == NLS_MAT_J2_SMALL_STRAIN && h->have_mesh) return nls_j2_init(h);      // initialize_state! on every (re)set of the material
   if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D || !h->have_mesh || !h->have_disc) return NLS_OK;
   if (h->d_state[0]) return NLS_OK;
   for (int i = 0; i < 9; ++i) NLS_TRY(dev_alloc(h, &h->d_state[i], (size_t)(h->nel * h->nq)));
@@ -199,12 +202,13 @@ extern "C" int32_t nls_set_discretization(nls_handle h, int32_t p_order, int32_t
 extern "C" int32_t nls_set_material(nls_handle h, int32_t kind, const double *params, int32_t nparams) {
   NLS_ENTER(h);
   if (!params) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: null params");
-  const int need[4] = {1, 2, 5, 2};
-  if (kind < 0 || kind > 3) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: unknown material kind");
+  const int need[5] = {1, 2, 5, 2, 4};
+  if (kind < 0 || kind > 4) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: unknown material kind");
   if (nparams < need[kind] || nparams > 8) NLS_FAIL(h, NLS_ERR_ARG, "nls_set_material: wrong number of parameters");
   if (h->have_mesh) {
-    if (kind == NLS_MAT_NEOHOOKEAN && h->dim == 1) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "Neo-Hookean needs a 2-D or 3-D mesh");
-    if (kind != NLS_MAT_NEOHOOKEAN && h->dim != 1) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D materials need a 1-D mesh");
+    const bool solid = kind == NLS_MAT_NEOHOOKEAN || kind == NLS_MAT_J2_SMALL_STRAIN;
+    if (solid && h->dim == 1) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "Neo-Hookean and J2 need a 2-D or 3-D mesh");
+    if (!solid && h->dim != 1) NLS_FAIL(h, NLS_ERR_UNSUPPORTED, "1-D materials need a 1-D mesh");
   }
   const double keep_area = h->mat.area;
   std::memset(&h->mat, 0, sizeof(h->mat));
@@ -306,6 +310,7 @@ extern "C" int32_t nls_set_body_force(nls_handle h, int32_t ncomp, const double 
 
 extern "C" int32_t nls_init_state(nls_handle h) {
   NLS_ENTER(h);
+  if (h->mat.kind == NLS_MAT_J2_SMALL_STRAIN) return h->have_mesh ? nls_j2_init(h) : NLS_OK;
   if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D) return NLS_OK;
   if (!h->d_state[0]) return alloc_state(h);  // allocates, then re-enters here
   const int64_t n = h->nel * h->nq;
@@ -325,6 +330,11 @@ extern "C" int32_t nls_init_state(nls_handle h) {
 
 extern "C" int32_t nls_commit_state(nls_handle h, const double *U) {
   NLS_ENTER(h);
+  if (h->mat.kind == NLS_MAT_J2_SMALL_STRAIN) {      // the trial state of the last internal-force pass becomes the committed one
+    NLS_TRY(nls_j2_commit(h));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NLS_OK;
+  }
   if (h->mat.kind != NLS_MAT_ELASTOPLASTIC_1D) return NLS_OK;
   if (!h->d_state[0]) NLS_FAIL(h, NLS_ERR_STATE, "nls_commit_state: state not initialised");
   if (U) NLS_CUDA(h, cudaMemcpyAsync(h->d_U, U, sizeof(double) * h->ndof_local(), cudaMemcpyHostToDevice, h->stream));
@@ -337,6 +347,7 @@ extern "C" int32_t nls_get_state(nls_handle h, const char *name, double *out) {
   NLS_ENTER(h);
   static const char *names[9] = {"sig", "alp", "kap", "gam", "dsig", "sig_n", "alp_n", "kap_n", "gam_n"};
   if (!name || !out) NLS_FAIL(h, NLS_ERR_ARG, "nls_get_state: null argument");
+  if (h->mat.kind == NLS_MAT_J2_SMALL_STRAIN) return nls_j2_get(h, name, out);
   if (!h->d_state[0]) NLS_FAIL(h, NLS_ERR_STATE, "nls_get_state: material has no state");
   for (int i = 0; i < 9; ++i)
     if (!std::strcmp(name, names[i])) {
@@ -412,7 +423,7 @@ static int check_ready(nls_context *h, const char *who) {
     h->err = std::string(who) + ": model incomplete (need mesh, discretization, material and pattern)";
     return NLS_ERR_STATE;
   }
-  if ((h->mat.kind == NLS_MAT_NEOHOOKEAN) != (h->dim > 1)) {
+  if ((h->mat.kind == NLS_MAT_NEOHOOKEAN || h->mat.kind == NLS_MAT_J2_SMALL_STRAIN) != (h->dim > 1)) {
     h->err = std::string(who) + ": material kind does not match the mesh dimension";
     return NLS_ERR_UNSUPPORTED;
   }
@@ -612,6 +623,8 @@ static int newton_linear(nls_context *h, double lin_rtol, int lin_maxits, int *l
   const unsigned g = (unsigned)std::max<int64_t>(1, std::min<int64_t>((h->nrows + 255) / 256, (int64_t)h->sm_count * 8));
   k_negate_into<<<g, 256, 0, h->stream>>>(h->nrows, h->d_R, h->d_b);
   h->launches++;
+  // small systems: the reference's `\` is exact; so is this (banded LU, kernels_direct.cu)
+  if (h->opt_direct && nls_direct_available(h)) { if (lin_its) *lin_its = 1; return nls_direct_solve(h, status); }
   double rr;
   return nls_pcg_solve(h, lin_rtol, lin_maxits, 0, lin_its, &rr, status);
 }
@@ -975,6 +988,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "assembly")) { h->opt_assembly = value; return NLS_OK; }
   // preconditioner of the Krylov solve: -1 auto, 0 Jacobi, 1 block-Jacobi, 2 multigrid V-cycle (1, 2: grid-topology 3-D meshes)
   if (!std::strcmp(key, "precond")) { h->opt_precond = value; return NLS_OK; }
+  if (!std::strcmp(key, "direct")) { h->opt_direct = value; return NLS_OK; }        // 0: Newton's linear solves are always Krylov
   if (!std::strcmp(key, "mg_degree")) { h->mg.degree = value < 1 ? 1 : value; return NLS_OK; }
   if (!std::strcmp(key, "mg_coarse_degree")) { h->mg.coarse_degree = value < 1 ? 1 : value; return NLS_OK; }
   if (!std::strcmp(key, "mg_ratio_x10")) { h->mg.ratio = value < 11 ? 1.1 : value / 10.0; return NLS_OK; }

@@ -254,6 +254,12 @@ struct nls_context {
   TwoPhasePlan tplan;
   Lines3Plan lplan;
   MgPlan mg;
+  // exact banded solve of small systems (kernels_direct.cu)
+  double *d_band = nullptr;
+  int *d_ipiv = nullptr;
+  size_t direct_cap = 0;
+  int direct_bw = -1;        // half bandwidth of the scalar matrix (-1: not computed yet)
+  int opt_direct = 1;        // Newton's linear solve: exact banded LU when the system is small enough
   int opt_precond = -1;    // -1 auto (multigrid on large grid-topology 3-D meshes, else Jacobi), 0 Jacobi, 1 block-Jacobi, 2 multigrid
   std::vector<double> h_coords;
 
@@ -282,6 +288,8 @@ struct nls_context {
 
   // plastic state [nel][nq]
   double *d_state[9] = {nullptr};       // sig, alp, kap, gam, dsig, sig_n, alp_n, kap_n, gam_n
+  double *d_j2 = nullptr;               // J2 material: [22][nel * nq] committed (7), trial (7), tangent data (8)  (kernels_j2.cu)
+  int64_t j2_nqp = 0;
   double *d_u_n = nullptr;              // [nel][nen]
 
   // per-handle (= per-device) record of the dynamic shared-memory limits already raised with cudaFuncSetAttribute
@@ -372,6 +380,15 @@ int nls_allreduce_sum(nls_context *h, double *dptr, int count);
 int nls_dev_dot_local(nls_context *h, int64_t n, const double *x, const double *y, double *out);   // this rank's part only
 int nls_launch_vals_to_f32(nls_context *h, float *out);
 int nls_launch_spmv_f32(nls_context *h, const float *vals32, const double *x, double *y);
+struct AsmArgs;
+void nls_j2_free(nls_context *h);
+int nls_j2_init(nls_context *h);
+int nls_j2_commit(nls_context *h);
+int nls_j2_get(nls_context *h, const char *name, double *out);
+int nls_launch_j2(nls_context *h, const AsmArgs &a, bool want_r, bool want_k);
+bool nls_direct_available(nls_context *h);
+int nls_direct_solve(nls_context *h, int *status);
+void nls_direct_free(nls_context *h);
 void nls_mg_free(nls_context *h);
 void nls_mg_invalidate(nls_context *h);
 int nls_mg_build(nls_context *h);

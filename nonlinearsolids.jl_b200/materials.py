@@ -92,6 +92,22 @@ class NeoHookean(AbstractMaterial):
         return [self.mu, self.lam]
 
 
+class J2Plasticity(AbstractMaterial):
+    """Small-strain J2 elastoplasticity with linear isotropic hardening on Q1 quads (plane strain) and hexahedra: the
+    stateful-material protocol of LinearElastoPlasticity1D (linearelastoplasticity.jl:60-117) generalised to 2-D / 3-D
+    (SURVEY 8 f-2). State per quadrature point: plastic strain `epsp_xx ... epsp_xz` and `alpha` (trial; `_n` = committed)."""
+    kind = _lib.MAT_J2_SMALL_STRAIN
+    has_state = True
+
+    def __init__(self, E, nu, sigma_y, H, rho=1.0):
+        self.E, self.nu, self.sigma_y, self.H, self.rho = map(float, (E, nu, sigma_y, H, rho))
+        self.K = self.E / (3.0 * (1.0 - 2.0 * self.nu))
+        self.G = self.E / (2.0 * (1.0 + self.nu))
+
+    def params(self):
+        return [self.K, self.G, self.sigma_y, self.H]
+
+
 def initialize_state(material, fem):
     """initialize_state!(material, fem) (linearelastoplasticity.jl:106-117)."""
     fem.handle(material).call("nls_init_state")

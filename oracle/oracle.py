@@ -6,6 +6,7 @@ package. See oracle/nls_oracle.h for what is restated and the reference
 file:line each function follows.
 """
 import ctypes as C
+import math
 import os
 import subprocess
 
@@ -449,3 +450,126 @@ def newtonarclength(om, F_ext, b=0.5, da=0.1, rtol=1e-16, ftol=1e-16, stol=0.0, 
             break
     return dict(d=d_hist[:nsteps], lam=lam[:nsteps], num_its=num_its[:nsteps], res_d=res_d[:nsteps], res_l=res_l[:nsteps],
                 num_steps=nsteps)
+
+
+class J2Oracle:
+    """CPU restatement (test infrastructure) of the stateful-material protocol of the reference's LinearElastoPlasticity1D
+    (src/materials/linearelastoplasticity.jl:60-117: return mapping from the committed state in the internal-force pass,
+    stored tangent read by the tangent pass, commit on save_state!) for small-strain J2 plasticity with linear isotropic
+    hardening on Q1 quads (plane strain) / hexahedra -- SURVEY 8 f-2. The reference has no 2-D / 3-D plastic material, so
+    parity of this extension is pinned by known answers only (tests/test_oracle.py: uniaxial yield stress, consistency of the
+    tangent with finite differences of the stress, elastic unloading). Written independently of the CUDA kernel: full 3 x 3
+    tensors and the 3 x 3 x 3 x 3 tangent, contracted with einsum; plain numpy, small cases only."""
+
+    def __init__(self, dim, conn, coords, K, G, sigma_y, H):
+        self.dim, self.nen = dim, 2 ** dim
+        self.conn = np.asarray(conn, dtype=np.int64).reshape(-1, self.nen)
+        self.coords = np.asarray(coords, dtype=np.float64).reshape(-1, dim)
+        self.nel, self.nn = len(self.conn), len(self.coords)
+        self.K, self.G, self.sy, self.H = float(K), float(G), float(sigma_y), float(H)
+        g = 1.0 / math.sqrt(3.0)
+        # shapefunctions.jl / quadrature.jl for p = 1, two Gauss points per direction; nodes and points x-fastest
+        self.dN = np.zeros((self.nen, self.nen, dim))           # [q][a][D]
+        for q in range(self.nen):
+            xi = [(-g if not (q >> d) & 1 else g) for d in range(dim)]
+            for a in range(self.nen):
+                s = [(-1.0 if not (a >> d) & 1 else 1.0) for d in range(dim)]
+                for D in range(dim):
+                    v = 1.0
+                    for d in range(dim):
+                        v *= 0.5 * s[d] if d == D else 0.5 * (1.0 + s[d] * xi[d])
+                    self.dN[q, a, D] = v
+        self.w = np.ones(self.nen)
+        self.dir_dofs, self.dir_vals = np.zeros(0, dtype=np.int64), np.zeros(0)
+        self.init_state()
+
+    def init_state(self):
+        nq = self.nen
+        self.epsp_n = np.zeros((self.nel, nq, 3, 3)); self.alpha_n = np.zeros((self.nel, nq))
+        self.epsp = np.zeros((self.nel, nq, 3, 3)); self.alpha = np.zeros((self.nel, nq))
+        self.C = None                                            # consistent tangent of the last internal-force pass
+
+    def set_dirichlet(self, dofs, vals):
+        self.dir_dofs, self.dir_vals = np.asarray(dofs, dtype=np.int64), np.asarray(vals, dtype=np.float64)
+
+    def commit_state(self):
+        self.epsp_n[:] = self.epsp; self.alpha_n[:] = self.alpha
+
+    def _kinematics(self, U):
+        dim = self.dim
+        X = self.coords[self.conn]                               # [e][a][d]
+        u = U.reshape(-1, dim)[self.conn]
+        J = np.einsum("ead,qaD->eqdD", X, self.dN)
+        detJ = np.linalg.det(J)
+        Gr = np.einsum("qaE,eqED->eqaD", self.dN, np.linalg.inv(J))       # dN/dX
+        gu = np.zeros((self.nel, self.nen, 3, 3))
+        gu[:, :, :dim, :dim] = np.einsum("eai,eqaj->eqij", u, Gr)
+        return Gr, detJ * self.w[None, :], 0.5 * (gu + gu.transpose(0, 1, 3, 2))
+
+    def return_map(self, eps):
+        """stress, new plastic strain, new alpha, tangent [..., 3,3,3,3] at strains eps [..., 3, 3] from the committed state"""
+        K, G, sy, H = self.K, self.G, self.sy, self.H
+        I = np.eye(3)
+        ee = eps - self.epsp_n
+        tr = np.trace(ee, axis1=-2, axis2=-1)
+        s_tr = 2.0 * G * (ee - tr[..., None, None] / 3.0 * I)
+        qn = np.sqrt(np.einsum("...ij,...ij->...", s_tr, s_tr))
+        f = qn - math.sqrt(2.0 / 3.0) * (sy + H * self.alpha_n)
+        plastic = f > 0.0
+        qsafe = np.where(plastic, qn, 1.0)
+        dg = np.where(plastic, f / (2.0 * G + 2.0 * H / 3.0), 0.0)
+        n = np.where(plastic[..., None, None], s_tr / qsafe[..., None, None], 0.0)
+        sig = K * tr[..., None, None] * I + s_tr - 2.0 * G * dg[..., None, None] * n
+        theta = 1.0 - 2.0 * G * dg / qsafe
+        thetab = np.where(plastic, 1.0 / (1.0 + H / (3.0 * G)) - (1.0 - theta), 0.0)
+        II = np.einsum("ij,kl->ijkl", I, I)
+        Is = 0.5 * (np.einsum("ik,jl->ijkl", I, I) + np.einsum("il,jk->ijkl", I, I))
+        C = (K * II + 2.0 * G * theta[..., None, None, None, None] * (Is - II / 3.0)
+             - 2.0 * G * thetab[..., None, None, None, None] * np.einsum("...ij,...kl->...ijkl", n, n))
+        return sig, self.epsp_n + dg[..., None, None] * n, self.alpha_n + math.sqrt(2.0 / 3.0) * dg, C
+
+    def residual(self, U):
+        """(U with the Dirichlet values written, internal force); runs the return mapping and stores the trial state."""
+        U = np.array(U, dtype=np.float64)
+        U[self.dir_dofs] = self.dir_vals
+        dim = self.dim
+        Gr, wd, eps = self._kinematics(U)
+        sig, self.epsp, self.alpha, self.C = self.return_map(eps)
+        fe = np.einsum("eq,eqij,eqaj->eai", wd, sig[:, :, :dim, :dim], Gr)
+        R = np.zeros(self.nn * dim)
+        np.add.at(R.reshape(-1, dim), self.conn, fe)
+        return U, R
+
+    def jacobian_dense(self, U):
+        """tangent from the data stored by the last internal-force pass (the reference's protocol)"""
+        assert self.C is not None, "residual first: the tangent pass reads the state of the internal-force pass"
+        U = np.array(U, dtype=np.float64)
+        U[self.dir_dofs] = self.dir_vals
+        dim = self.dim
+        Gr, wd, _ = self._kinematics(U)
+        Ke = np.einsum("eq,eqaj,eqijkl,eqbl->eaibk", wd, Gr, self.C[:, :, :dim, :dim, :dim, :dim], Gr)
+        n = self.nn * dim
+        Kd = np.zeros((n, n))
+        dofs = (self.conn[:, :, None] * dim + np.arange(dim)[None, None, :]).reshape(self.nel, -1)
+        for e in range(self.nel):
+            Kd[np.ix_(dofs[e], dofs[e])] += Ke[e].reshape(self.nen * dim, self.nen * dim)
+        return Kd
+
+    def newton(self, U0, rtol=1e-10, atol=1e-14, maxits=25):
+        """newton_fem.jl:132-190 with a dense solve on the free DoFs; returns (U, iterations, residual norms)"""
+        n = self.nn * self.dim
+        free = np.ones(n, dtype=bool); free[self.dir_dofs] = False
+        U, R = self.residual(U0)
+        hist = [float(np.linalg.norm(R[free]))]
+        r0 = hist[0] if hist[0] > 2.220446049250313e-16 else 1.0
+        its = 0
+        while its < maxits:
+            if hist[-1] / r0 < rtol or hist[-1] < atol:
+                break
+            Kd = self.jacobian_dense(U)
+            dU = np.zeros(n)
+            dU[free] = np.linalg.solve(Kd[np.ix_(free, free)], -R[free])
+            U, R = self.residual(U + dU)
+            hist.append(float(np.linalg.norm(R[free])))
+            its += 1
+        return U, its, hist

@@ -485,3 +485,37 @@ def test_dynamics_golden_regression(orc):
     out = om.newmark(nm["rho"], nm["dt"], nm["maxtime"], area=nm["area"], bc_update=lambda t: (None, [nm["tip_rate"] * t]),
                      rtol=1e-11, atol=1e-13, maxits=20)
     assert out["num_its"].tolist() == nm["num_its"] and np.allclose(out["U"], nm["U"], rtol=1e-12, atol=1e-16)
+
+
+def test_j2_oracle_known_answers():
+    """Pins for the J2 restatement (no reference counterpart): yield strain of uniaxial strain, stress on the yield surface
+    after the return, consistent tangent = finite difference of the internal force, elastic unloading after commit."""
+    import importlib
+    orc = importlib.import_module("oracle.oracle")
+    E, nu, sy, H = 100.0, 0.3, 0.5, 10.0
+    K, G = E / (3 * (1 - 2 * nu)), E / (2 * (1 + nu))
+    X = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1]], dtype=float)
+    o = orc.J2Oracle(3, np.arange(8)[None, :], X, K, G, sy, H)
+    for ezz, plastic in ((0.9 * sy / (2 * G), False), (3.0 * sy / (2 * G), True)):
+        U = np.zeros((8, 3)); U[:, 2] = ezz * X[:, 2]
+        o.residual(U.ravel())
+        assert bool(o.alpha.max() > 0) == plastic
+        eps = np.zeros((3, 3)); eps[2, 2] = ezz
+        ee = eps - o.epsp[0, 0]
+        s = 2 * G * (ee - np.trace(ee) / 3 * np.eye(3))
+        if plastic:      # on the (hardened) yield surface
+            assert abs(np.sqrt((s * s).sum()) - np.sqrt(2.0 / 3.0) * (sy + H * o.alpha[0, 0])) <= 1e-13
+            assert abs(np.trace(o.epsp[0, 0])) <= 1e-16          # plastic flow is isochoric
+    rng = np.random.default_rng(1)
+    U = 0.02 * rng.standard_normal(24)
+    _, R = o.residual(U)
+    Kd = o.jacobian_dense(U)
+    Kfd = np.zeros((24, 24))
+    for j in range(24):
+        Up, Um = U.copy(), U.copy()
+        Up[j] += 1e-7; Um[j] -= 1e-7
+        Kfd[:, j] = (o.residual(Up)[1] - o.residual(Um)[1]) / 2e-7
+    assert np.abs(Kd - Kfd).max() <= 1e-8 * np.abs(Kd).max() and np.abs(Kd - Kd.T).max() <= 1e-14 * np.abs(Kd).max()
+    o.residual(U); o.commit_state()
+    o.residual(0.999 * U)                                        # small step back: elastic
+    assert np.array_equal(o.alpha, o.alpha_n)
