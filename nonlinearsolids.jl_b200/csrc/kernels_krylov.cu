@@ -578,12 +578,13 @@ int nls_launch_vals_to_f32(nls_context *h, float *out) {
   return NLS_OK;
 }
 int nls_launch_spmv_f32(nls_context *h, const float *vals32, const double *x, double *y) {
-  if (h->dim != 3 || h->nrows == 0) NLS_FAIL(h, NLS_ERR_STATE, "single-precision product: 3-D only");
+  if (h->dim < 2 || h->nrows == 0) NLS_FAIL(h, NLS_ERR_STATE, "single-precision product: 2-D and 3-D models only");
   int64_t g = (h->n_owned * 4 + 255) / 256;
   const int64_t cap = (int64_t)h->sm_count * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
-  k_bspmv<3, 4, false, float><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, vals32, x, y, h->d_con, h->d_ctl, red_of(h));
+  if (h->dim == 2) k_bspmv<2, 4, false, float><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, vals32, x, y, h->d_con, h->d_ctl, red_of(h));
+  else k_bspmv<3, 4, false, float><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, vals32, x, y, h->d_con, h->d_ctl, red_of(h));
   NLS_KCHECK(h);
   return NLS_OK;
 }

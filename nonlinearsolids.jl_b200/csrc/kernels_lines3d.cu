@@ -805,6 +805,83 @@ int nls_lines3_build(nls_context *h) {
   NLS_CUDA(h, cudaMemsetAsync(p.d_counter, 0, 2 * sizeof(unsigned), h->stream));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   p.ok = true;
+  p.tables = true;
+  p.h_pown = pown; p.h_pbase = pbase;
+  { const int rc = nls_mg_build(h); if (rc) return rc; }
+  return nls_mg_prepare(h, false);
+}
+
+// 2-D meshes with grid topology (x-fastest rows; full grids and slab-local meshes): the same per-line addressing tables with
+// one line per node row (ny = 1, the row index plays z). No assembly kernel uses them -- the 2-D default is the gather kernel --
+// they give the multigrid preconditioner (kernels_mg.cu) the closed-form positions of the CSR blocks. p.ok stays false.
+int nls_lines2_build(nls_context *h) {
+  nls_lines3_free(h);
+  Lines3Plan &p = h->lplan;
+  if (h->dim != 2 || h->nen != 4 || h->nel == 0 || h->n_owned == 0) return NLS_OK;
+  const int32_t *c = h->h_conn.data();
+  const int64_t nel = h->nel, nn = h->nn;
+  if (c[1] != c[0] + 1) return NLS_OK;
+  const int64_t nx = (int64_t)c[2] - c[0];
+  if (nx < 2 || nx > 1000000 || nel % (nx - 1)) return NLS_OK;
+  const int64_t epr = nx - 1, nlay = nel / epr, nzp = nlay + 1;
+  if (nn != nx * nzp || nzp > 1000000) return NLS_OK;
+  std::vector<int32_t> pbase((size_t)nzp);
+  for (int64_t k = 0; k < nlay; ++k) pbase[k] = c[k * epr * 4];
+  pbase[nlay] = c[(nlay - 1) * epr * 4 + 2];
+  for (int64_t k = 0; k < nzp; ++k) if (pbase[k] < 0 || (int64_t)pbase[k] + nx > nn) return NLS_OK;
+  {
+    std::vector<int32_t> s(pbase);
+    std::sort(s.begin(), s.end());
+    for (int64_t k = 1; k < nzp; ++k) if ((int64_t)s[k] - s[k - 1] < nx) return NLS_OK;
+  }
+  for (int64_t k = 0; k < nlay; ++k)
+    for (int64_t i = 0; i < epr; ++i) {
+      const int32_t *ce = c + (k * epr + i) * 4;
+      const int64_t n0 = pbase[k] + i, n1 = pbase[k + 1] + i;
+      if (ce[0] != n0 || ce[1] != n0 + 1 || ce[2] != n1 || ce[3] != n1 + 1) return NLS_OK;
+    }
+  std::vector<uint8_t> pown((size_t)nzp);
+  for (int64_t k = 0; k < nzp; ++k) {
+    pown[k] = pbase[k] < h->n_owned;
+    if (pown[k] && (int64_t)pbase[k] + nx > h->n_owned) return NLS_OK;
+  }
+  std::vector<L3Line> info((size_t)nzp);
+  const int64_t *bp = h->h_browptr.data();
+  const int32_t *bc = h->h_bcol.data();
+  for (int64_t z = 0; z < nzp; ++z) {
+    L3Line &li = info[z];
+    std::memset(&li, 0, sizeof(li));
+    for (int k = 0; k < 9; ++k) li.rank[k] = -1;
+    if (!pown[z]) continue;
+    std::pair<int64_t, int> nb[3];
+    int nl = 0;
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int64_t z2 = z + dz;
+      if (z2 < 0 || z2 >= nzp) continue;
+      nb[nl++] = {(int64_t)pbase[z2], (dz + 1) * 3 + 1};
+    }
+    std::sort(nb, nb + nl);
+    for (int k = 0; k < nl; ++k) li.rank[nb[k].second] = (int8_t)k;
+    li.nl = nl;
+    const int64_t first = pbase[z];
+    li.lb = bp[first];
+    for (int64_t i = 0; i < nx; ++i) {
+      const int64_t a = first + i;
+      const int w = (i == 0 || i == nx - 1) ? 2 : 3;
+      const int64_t b0 = li.lb + (int64_t)nl * (i == 0 ? 0 : 3 * i - 1);
+      if (bp[a] != b0 || bp[a + 1] - bp[a] != (int64_t)nl * w) return NLS_OK;
+      for (int k = 0; k < nl; ++k)
+        for (int dx = (i == 0 ? 0 : -1); dx <= (i == nx - 1 ? 0 : 1); ++dx)
+          if (bc[b0 + k * w + dx + (i == 0 ? 0 : 1)] != nb[k].first + i + dx) return NLS_OK;
+    }
+  }
+  p.nx = (int)nx; p.ny = 1; p.nzp = (int)nzp; p.nunits = 0;
+  NLS_CUDA(h, cudaMalloc((void **)&p.d_pbase, sizeof(int32_t) * pbase.size()));
+  NLS_CUDA(h, cudaMemcpyAsync(p.d_pbase, pbase.data(), sizeof(int32_t) * pbase.size(), cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaMalloc((void **)&p.d_info, sizeof(L3Line) * info.size()));
+  NLS_CUDA(h, cudaMemcpyAsync(p.d_info, info.data(), sizeof(L3Line) * info.size(), cudaMemcpyHostToDevice, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  p.tables = true;
   p.h_pown = pown; p.h_pbase = pbase;
   { const int rc = nls_mg_build(h); if (rc) return rc; }
   return nls_mg_prepare(h, false);

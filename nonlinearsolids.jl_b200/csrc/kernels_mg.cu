@@ -1,4 +1,4 @@
-// kernels_mg.cu -- geometric multigrid preconditioner of the Krylov solve on 3-D meshes with grid topology.
+// kernels_mg.cu -- geometric multigrid preconditioner of the Krylov solve on 2-D and 3-D meshes with grid topology.
 //
 // Replaces, together with kernels_krylov.cu:  dofs(K) \ dofs(-R)  (src/nonlinearsolvers/newton_fem.jl:158). The reference
 // factorises K; at 10^7 DoF the B200 path iterates, and Jacobi-PCG needs O(n) iterations per solve (1 600 at C3). Here the
@@ -7,6 +7,8 @@
 //     even node count), P = trilinear interpolation (weights 1, 1/2 per axis), the same for the three displacement components;
 //   * level 0 is the assembled CSR Jacobian itself (block positions from the line tables of kernels_lines3d.cu, Dirichlet
 //     rows and columns masked out = the free block dofs(K)); coarser operators are stored as 27 dense 3 x 3 blocks per node;
+//   * 2-D models run the same code: the node rows play the z-planes (ny = 1), every node carries a decoupled dummy third DoF on
+//     the stencil levels (identity on the diagonal, zero right-hand side), level 0 keeps its two-component vectors;
 //   * smoother: Chebyshev polynomial in D^-1 K (D = the 3 x 3 node blocks), largest eigenvalue by a few power iterations;
 //     the coarsest grid (<= 6 nodes per axis) gets a long Chebyshev run instead of a factorisation;
 //   * the Galerkin products are gathers: every coarse block is the sum of its <= 343 weighted fine blocks in a fixed order:
@@ -34,6 +36,7 @@
 struct MgL3Line { int64_t lb; int32_t nl; int8_t rank[9]; int8_t pad[3]; };   // = L3Line of kernels_lines3d.cu
 
 struct MgFine {          // level 0: the CSR Jacobian of a grid-topology mesh
+  int dim;               // 3, or 2: the node rows of a 2-D mesh play the planes (ny = 1) and every node gets a decoupled dummy third DoF
   int nx, ny, nzo;       // owned planes
   int z0;                // line-table index of the first owned plane
   int p0, NZ;            // global index of the first owned plane, global plane count
@@ -93,14 +96,18 @@ __device__ __forceinline__ bool mg_fine_block(const MgFine &F, int x, int y, int
   const int nl = li->nl, w = (x == 0 || x == F.nx - 1) ? 2 : 3;
   const int64_t b0 = li->lb + (int64_t)nl * (x == 0 ? 0 : 3 * x - 1);
   const int pos = rank * w + dx + (x == 0 ? 0 : 1);
-  const double *p = F.vals + 9 * b0 + 3 * pos;
-  const int64_t stride = 3 * (int64_t)nl * w;
+  const int D = F.dim;
+  const double *p = F.vals + (int64_t)D * D * b0 + D * pos;
+  const int64_t stride = (int64_t)D * nl * w;
   const int64_t ni = (int64_t)F.pbase[zp] + (int64_t)y * F.nx + x, nj = (int64_t)F.pbase[zp + dz] + (int64_t)y2 * F.nx + x2;
-  const uint8_t *ci = F.con + 3 * ni, *cj = F.con + 3 * nj;
+  const uint8_t *ci = F.con + D * ni, *cj = F.con + D * nj;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) B[r * 3 + c] = (ci[r] | cj[c]) ? 0.0 : p[r * stride + c];
+    for (int c = 0; c < 3; ++c) {
+      if (r < D && c < D) B[r * 3 + c] = (ci[r] | cj[c]) ? 0.0 : p[r * stride + c];
+      else B[r * 3 + c] = (r == c && dx == 0 && dy == 0 && dz == 0) ? 1.0 : 0.0;      // the dummy DoF of a 2-D node: identity
+    }
   return true;
 }
 
@@ -112,11 +119,13 @@ __global__ void __launch_bounds__(256) k_mg_fine_dinv(const MgFine F, double *__
     double B[9], Bi[9];
     mg_fine_block(F, x, y, F.p0 + z, 0, 0, 0, B);
     const int64_t ni = (int64_t)F.pbase[F.z0 + z] + (int64_t)y * F.nx + x;
-    const uint8_t *ci = F.con + 3 * ni;
-    for (int r = 0; r < 3; ++r) if (ci[r]) B[r * 3 + r] = 1.0;
+    const uint8_t *ci = F.con + F.dim * ni;
+    bool cr[3] = {false, false, false};
+    for (int r = 0; r < F.dim; ++r) cr[r] = ci[r] != 0;
+    for (int r = 0; r < 3; ++r) if (cr[r]) B[r * 3 + r] = 1.0;
     mg_inv3(B, Bi);
     for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) dinv[9 * ni + r * 3 + c] = (ci[r] | ci[c]) ? 0.0 : Bi[r * 3 + c];
+      for (int c = 0; c < 3; ++c) dinv[9 * ni + r * 3 + c] = (cr[r] | cr[c]) ? 0.0 : Bi[r * 3 + c];
   }
 }
 
@@ -285,30 +294,49 @@ __global__ void __launch_bounds__(256) k_mg_spmv(const MgBox B, const double *__
 }
 
 // one Chebyshev step on nodes [0, nn): d = a d + c D^-1 (b - y), x += d  (y = K x of the current x, or absent while x = 0).
-// mode 1: x = 0 on entry (x = d), 2: new run (d restarts), 0: inside a run
+// mode 1: x = 0 on entry (x = d), 2: new run (d restarts), 0: inside a run. NC = components per node of the vectors (2: the
+// level-0 vectors of a 2-D model; D^-1 is block diagonal there, its leading 2 x 2 block is the inverse of the node block).
+template <int NC>
 __global__ void __launch_bounds__(256) k_mg_cheb(int64_t nn, const double *__restrict__ dinv, const double *__restrict__ b,
                                                   const double *__restrict__ y, double *__restrict__ d, double *__restrict__ x,
                                                   double a, double c, int mode) {
   const bool first = mode == 1, restart = mode != 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
-    double r0 = b[3 * i], r1 = b[3 * i + 1], r2 = b[3 * i + 2];
-    if (y) { r0 -= y[3 * i]; r1 -= y[3 * i + 1]; r2 -= y[3 * i + 2]; }
+    double r[NC], z[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { r[k] = b[NC * i + k]; if (y) r[k] -= y[NC * i + k]; }
     const double *D = dinv + 9 * i;
-    const double z0 = D[0] * r0 + D[1] * r1 + D[2] * r2, z1 = D[3] * r0 + D[4] * r1 + D[5] * r2, z2 = D[6] * r0 + D[7] * r1 + D[8] * r2;
-    double d0 = c * z0, d1 = c * z1, d2 = c * z2;
-    if (!restart) { d0 = fma(a, d[3 * i], d0); d1 = fma(a, d[3 * i + 1], d1); d2 = fma(a, d[3 * i + 2], d2); }
-    d[3 * i] = d0; d[3 * i + 1] = d1; d[3 * i + 2] = d2;
-    if (first) { x[3 * i] = d0; x[3 * i + 1] = d1; x[3 * i + 2] = d2; }
-    else { x[3 * i] += d0; x[3 * i + 1] += d1; x[3 * i + 2] += d2; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      z[k] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) z[k] = fma(D[3 * k + j], r[j], z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      double dk = c * z[k];
+      if (!restart) dk = fma(a, d[NC * i + k], dk);
+      d[NC * i + k] = dk;
+      if (first) x[NC * i + k] = dk; else x[NC * i + k] += dk;
+    }
   }
 }
 
 // z = D^-1 r on nodes [0, nn) (block-Jacobi alone, and the power iteration)
+template <int NC>
 __global__ void __launch_bounds__(256) k_mg_apply_dinv(int64_t nn, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ z) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x) {
-    const double r0 = r[3 * i], r1 = r[3 * i + 1], r2 = r[3 * i + 2];
     const double *D = dinv + 9 * i;
-    z[3 * i] = D[0] * r0 + D[1] * r1 + D[2] * r2; z[3 * i + 1] = D[3] * r0 + D[4] * r1 + D[5] * r2; z[3 * i + 2] = D[6] * r0 + D[7] * r1 + D[8] * r2;
+    double rr[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) rr[k] = r[NC * i + k];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) s = fma(D[3 * k + j], rr[j], s);
+      z[NC * i + k] = s;
+    }
   }
 }
 
@@ -320,7 +348,7 @@ __global__ void __launch_bounds__(256) k_mg_residual(int64_t n, const double *__
 // restriction bc = P^T r on the coarse planes [zown0, zown1): one thread per coarse DoF gathers its <= 27 fine nodes (ghost
 // planes of r filled beforehand). Level 0: r is indexed by node id through the line tables (pbase; z0 = table index of the
 // rank's first owned plane, global plane p0).
-__global__ void __launch_bounds__(256) k_mg_restrict(const MgBox Fb, const int32_t *__restrict__ pbase, int z0, int p0,
+__global__ void __launch_bounds__(256) k_mg_restrict(const MgBox Fb, const int32_t *__restrict__ pbase, int z0, int p0, int fnc,
                                                       const MgBox C, const double *__restrict__ r, double *__restrict__ bc) {
   const int fnx = Fb.nx, fny = Fb.ny, fnz = Fb.NZ, cnx = C.nx, cny = C.ny;
   const int64_t total = (int64_t)cnx * cny * (C.zown1 - C.zown0) * 3;
@@ -330,7 +358,7 @@ __global__ void __launch_bounds__(256) k_mg_restrict(const MgBox Fb, const int32
     const int X = (int)(I % cnx), Y = (int)((I / cnx) % cny), Z = C.zown0 + (int)(I / ((int64_t)cnx * cny));
     const int fx = mg_fx(X, fnx), fy = mg_fx(Y, fny), fz = mg_fx(Z, fnz);
     double s = 0.0;
-    for (int z = max(fz - 1, 0); z <= min(fz + 1, fnz - 1); ++z) {
+    for (int z = max(fz - 1, 0); z <= min(fz + 1, fnz - 1) && c < fnc; ++z) {      // c >= fnc: the dummy DoF of a 2-D model
       const double wz = mg_w(z, Z, fnz);
       if (wz == 0.0) continue;
       for (int yy = max(fy - 1, 0); yy <= min(fy + 1, fny - 1); ++yy) {
@@ -340,7 +368,7 @@ __global__ void __launch_bounds__(256) k_mg_restrict(const MgBox Fb, const int32
           const double w = wy * mg_w(x, X, fnx);
           if (w == 0.0) continue;
           const int64_t i = pbase ? (int64_t)pbase[z0 + z - p0] + (int64_t)yy * fnx + x : ((int64_t)(z - Fb.zbase) * fny + yy) * fnx + x;
-          s = fma(w, r[3 * i + c], s);
+          s = fma(w, r[(int64_t)fnc * i + c], s);
         }
       }
     }
@@ -350,16 +378,16 @@ __global__ void __launch_bounds__(256) k_mg_restrict(const MgBox Fb, const int32
 
 // prolongation x += P xc on the fine planes [zown0, zown1): one thread per fine DoF gathers its <= 8 coarse parents (ghost
 // planes of xc filled beforehand); constrained DoFs (level 0) stay zero
-__global__ void __launch_bounds__(256) k_mg_prolong(const MgBox Fb, const int32_t *__restrict__ pbase, int z0, int p0,
+__global__ void __launch_bounds__(256) k_mg_prolong(const MgBox Fb, const int32_t *__restrict__ pbase, int z0, int p0, int fnc,
                                                      const uint8_t *__restrict__ con, const MgBox C, const double *__restrict__ xc, double *__restrict__ x) {
   const int fnx = Fb.nx, fny = Fb.ny, fnz = Fb.NZ, cnx = C.nx, cny = C.ny;
-  const int64_t total = (int64_t)fnx * fny * (Fb.zown1 - Fb.zown0) * 3;
+  const int64_t total = (int64_t)fnx * fny * (Fb.zown1 - Fb.zown0) * fnc;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t il = t / 3;
-    const int r = (int)(t - 3 * il);
+    const int64_t il = t / fnc;
+    const int r = (int)(t - fnc * il);
     const int xx = (int)(il % fnx), yy = (int)((il / fnx) % fny), zz = Fb.zown0 + (int)(il / ((int64_t)fnx * fny));     // zz: global plane
     const int64_t i = pbase ? (int64_t)pbase[z0 + zz - p0] + (int64_t)yy * fnx + xx : ((int64_t)(zz - Fb.zbase) * fny + yy) * fnx + xx;
-    if (con && con[3 * i + r]) continue;
+    if (con && con[(int64_t)fnc * i + r]) continue;
     // parents per axis: the coarse node at v (weight 1), or the two at v - 1 and v + 1 (weight 1/2 each)
     int px[2], py[2], pz[2];
     auto parents = [](int v, int n, int *p) -> int {
@@ -375,7 +403,7 @@ __global__ void __launch_bounds__(256) k_mg_prolong(const MgBox Fb, const int32_
     for (int c = 0; c < npz; ++c)
       for (int bq = 0; bq < npy; ++bq)
         for (int a = 0; a < npx; ++a) s += xc[3 * ((((int64_t)(pz[c] - C.zbase) * cny) + py[bq]) * cnx + px[a]) + r];
-    x[3 * i + r] += w * s;
+    x[(int64_t)fnc * i + r] += w * s;
   }
 }
 
@@ -391,11 +419,11 @@ __global__ void __launch_bounds__(256) k_mg_con_to_f64(int64_t n, const uint8_t 
 __global__ void __launch_bounds__(256) k_mg_f64_to_con(int64_t n, const double *__restrict__ v, uint8_t *__restrict__ con) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) con[i] = v[i] != 0.0;
 }
-__global__ void __launch_bounds__(256) k_mg_fill_hash(int64_t n, unsigned seed, int64_t gofs, double *__restrict__ v) {   // fixed pseudo-random start vector
+__global__ void __launch_bounds__(256) k_mg_fill_hash(int64_t n, unsigned seed, int64_t gofs, int zero_third, double *__restrict__ v) {   // fixed pseudo-random start vector
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     unsigned long long s = (unsigned long long)(i + gofs) * 0x9E3779B97F4A7C15ull + seed;
     s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
-    v[i] = (double)(s & 0xffff) / 65536.0 - 0.5;
+    v[i] = (zero_third && i % 3 == 2) ? 0.0 : (double)(s & 0xffff) / 65536.0 - 0.5;      // 2-D models: the dummy DoF stays out of the eigenvalue estimate
   }
 }
 __global__ void __launch_bounds__(256) k_mg_scale(int64_t n, double a, double *__restrict__ v) {
@@ -440,7 +468,7 @@ int nls_mg_build(nls_context *h) {
   nls_mg_free(h);
   MgPlan &m = h->mg;
   const Lines3Plan &p = h->lplan;
-  if (!p.ok || h->dim != 3 || p.h_pown.empty()) return NLS_OK;
+  if (!p.tables || (h->dim != 3 && h->dim != 2) || p.h_pown.empty()) return NLS_OK;
   int z0 = -1, z1 = -1;
   for (int z = 0; z < p.nzp; ++z) if (p.h_pown[z]) { if (z0 < 0) z0 = z; z1 = z + 1; }
   if (z0 < 0) return NLS_OK;
@@ -563,6 +591,7 @@ static MgFine mg_fine_args(nls_context *h) {
   const Lines3Plan &p = h->lplan;
   const MgPlan &m = h->mg;
   MgFine F;
+  F.dim = h->dim;
   F.nx = p.nx; F.ny = p.ny; F.nzo = m.nzo; F.z0 = m.z0; F.p0 = m.p0; F.NZ = m.NZ0;
   F.pbase = p.d_pbase; F.info = reinterpret_cast<const MgL3Line *>(p.d_info);
   F.vals = h->d_vals; F.con = m.conf;
@@ -614,6 +643,9 @@ static int mg_apply_K(nls_context *h, int l, double *x, double *y) {
   return NLS_OK;
 }
 
+// components per node of a level's vectors: the model's on level 0, three on the stencil levels (2-D: two + the dummy)
+static inline int mg_nc(nls_context *h, int l) { return l == 0 ? h->dim : 3; }
+
 // owned part of a level's vectors: offset (doubles) and node count
 static void mg_owned(nls_context *h, int l, int64_t *ofs, int64_t *nn) {
   const MgLevel &L = h->mg.lev[l];
@@ -632,10 +664,11 @@ static int mg_lambda_max(nls_context *h, int l, double *out) {
   MgLevel &L = m.lev[l];
   int64_t ofs, nn;
   mg_owned(h, l, &ofs, &nn);
-  const int64_t n = 3 * nn;
-  const int64_t gofs = l == 0 ? 3 * (int64_t)m.p0 * L.nx * L.ny : 3 * (int64_t)L.zown0 * L.nx * L.ny;
+  const int nc = mg_nc(h, l);
+  const int64_t n = nc * nn;
+  const int64_t gofs = l == 0 ? nc * (int64_t)m.p0 * L.nx * L.ny : 3 * (int64_t)L.zown0 * L.nx * L.ny;
   double *x = L.x + ofs, *y = L.y + ofs, *d = L.d + ofs;
-  k_mg_fill_hash<<<mg_grid(h, n), 256, 0, h->stream>>>(n, (unsigned)l, gofs, x); MG_KCHECK(h);
+  k_mg_fill_hash<<<mg_grid(h, n), 256, 0, h->stream>>>(n, (unsigned)l, gofs, (h->dim == 2 && l >= 1) ? 1 : 0, x); MG_KCHECK(h);
   if (l == 0) { k_mg_mask_copy<<<mg_grid(h, n), 256, 0, h->stream>>>(n, x, h->d_con, x); MG_KCHECK(h); }
   double lam = 1.0;
   for (int it = 0; it < m.power_its; ++it) {
@@ -644,7 +677,9 @@ static int mg_lambda_max(nls_context *h, int l, double *out) {
     if (!(nrm2 > 0.0)) { lam = 1.0; break; }
     k_mg_scale<<<mg_grid(h, n), 256, 0, h->stream>>>(n, 1.0 / sqrt(nrm2), x); MG_KCHECK(h);
     NLS_TRY(mg_apply_K(h, l, L.x, L.y));
-    k_mg_apply_dinv<<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, y, d); MG_KCHECK(h);
+    if (nc == 2) k_mg_apply_dinv<2><<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, y, d);
+    else k_mg_apply_dinv<3><<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, y, d);
+    MG_KCHECK(h);
     double xd;
     NLS_TRY(mg_dot(h, l, n, x, d, &xd));
     lam = xd;                                    // Rayleigh quotient of the normalised iterate
@@ -727,8 +762,9 @@ static int mg_cheb(nls_context *h, int l, const double *b, double *x, int degree
     double a, c;
     if (k == 0) { a = 0.0; c = 1.0 / theta; }
     else { const double rn = 1.0 / (2.0 * sigma - rho); a = rn * rho; c = 2.0 * rn / delta; rho = rn; }
-    k_mg_cheb<<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, b + ofs, first ? nullptr : L.y + ofs, L.d + ofs, x + ofs, a, c,
-                                                     first ? 1 : (k == 0 ? 2 : 0));
+    const int mode = first ? 1 : (k == 0 ? 2 : 0);
+    if (mg_nc(h, l) == 2) k_mg_cheb<2><<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, b + ofs, first ? nullptr : L.y + ofs, L.d + ofs, x + ofs, a, c, mode);
+    else k_mg_cheb<3><<<mg_grid(h, nn), 256, 0, h->stream>>>(nn, L.dinv + 3 * ofs, b + ofs, first ? nullptr : L.y + ofs, L.d + ofs, x + ofs, a, c, mode);
     MG_KCHECK(h);
   }
   return NLS_OK;
@@ -745,7 +781,8 @@ static int mg_vcycle(nls_context *h, int l, const double *b, double *x) {
   mg_owned(h, l, &ofs, &nn);
   // residual of the owned rows, its ghost planes, restriction to the coarse planes this rank owns
   double *r = l == 0 ? m.rf : L.y;
-  k_mg_residual<<<mg_grid(h, 3 * nn), 256, 0, h->stream>>>(3 * nn, b + ofs, L.y + ofs, r + ofs); MG_KCHECK(h);
+  const int nc = mg_nc(h, l);
+  k_mg_residual<<<mg_grid(h, nc * nn), 256, 0, h->stream>>>(nc * nn, b + ofs, L.y + ofs, r + ofs); MG_KCHECK(h);
   if (l == 0) { if (m.dist) NLS_TRY(nls_halo_exchange(h, r)); }
   else NLS_TRY(mg_exchange(h, l, r, 3));
   MgBox Cb = mg_box(C);
@@ -753,13 +790,13 @@ static int mg_vcycle(nls_context *h, int l, const double *b, double *x) {
   if (partial) { Cb.zown0 = C.rown0; Cb.zown1 = C.rown1; NLS_CUDA(h, cudaMemsetAsync(C.b, 0, sizeof(double) * 3 * (size_t)C.nn, h->stream)); }
   const int64_t ncown = (int64_t)C.nx * C.ny * (Cb.zown1 - Cb.zown0);
   if (ncown > 0) {
-    k_mg_restrict<<<mg_grid(h, 3 * ncown), 256, 0, h->stream>>>(mg_box(L), l == 0 ? h->lplan.d_pbase : nullptr, m.z0, m.p0, Cb, r, C.b);
+    k_mg_restrict<<<mg_grid(h, 3 * ncown), 256, 0, h->stream>>>(mg_box(L), l == 0 ? h->lplan.d_pbase : nullptr, m.z0, m.p0, nc, Cb, r, C.b);
     MG_KCHECK(h);
   }
   if (partial) NLS_TRY(mg_allsum(h, C.b, 3 * (size_t)C.nn));
   NLS_TRY(mg_vcycle(h, l + 1, C.b, C.x));
   NLS_TRY(mg_exchange(h, l + 1, C.x, 3));
-  k_mg_prolong<<<mg_grid(h, 3 * nn), 256, 0, h->stream>>>(mg_box(L), l == 0 ? h->lplan.d_pbase : nullptr, m.z0, m.p0,
+  k_mg_prolong<<<mg_grid(h, nc * nn), 256, 0, h->stream>>>(mg_box(L), l == 0 ? h->lplan.d_pbase : nullptr, m.z0, m.p0, nc,
                                                           l == 0 ? h->d_con : nullptr, mg_box(C), C.x, x);
   MG_KCHECK(h);
   return mg_cheb(h, l, b, x, m.degree, m.ratio, false);
@@ -768,7 +805,8 @@ static int mg_vcycle(nls_context *h, int l, const double *b, double *x) {
 // z = M^-1 r (r masked; z's ghost entries are scratch)
 int nls_mg_apply(nls_context *h, const double *r, double *z) {
   if (h->mg.mode == 1) {        // block-Jacobi alone
-    k_mg_apply_dinv<<<mg_grid(h, h->n_owned), 256, 0, h->stream>>>(h->n_owned, h->mg.lev[0].dinv, r, z);
+    if (h->dim == 2) k_mg_apply_dinv<2><<<mg_grid(h, h->n_owned), 256, 0, h->stream>>>(h->n_owned, h->mg.lev[0].dinv, r, z);
+    else k_mg_apply_dinv<3><<<mg_grid(h, h->n_owned), 256, 0, h->stream>>>(h->n_owned, h->mg.lev[0].dinv, r, z);
     MG_KCHECK(h);
     return NLS_OK;
   }

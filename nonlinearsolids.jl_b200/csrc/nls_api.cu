@@ -394,7 +394,7 @@ extern "C" int32_t nls_build_pattern(nls_handle h) {
     NLS_TRY(nls_gather_build(h, plan));
   }
   NLS_TRY(nls_twophase_build(h));
-  NLS_TRY(nls_lines3_build(h));
+  NLS_TRY(h->dim == 2 ? nls_lines2_build(h) : nls_lines3_build(h));
   NLS_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_pattern = true;
   return NLS_OK;

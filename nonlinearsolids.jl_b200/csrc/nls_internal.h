@@ -86,7 +86,8 @@ struct TwoPhasePlan {
 
 // plan of the pair-owner assembly of 3-D meshes with grid topology (kernels_lines3d.cu)
 struct Lines3Plan {
-  bool ok = false;                 // the mesh has grid topology and the closed-form row addresses match the pattern
+  bool ok = false;                 // the mesh has grid topology and the closed-form row addresses match the pattern (3-D: the line kernel runs)
+  bool tables = false;             // the addressing tables exist (3-D as above; 2-D: for the multigrid preconditioner only)
   bool lap_valid = false;          // the Laplacian table holds the current mesh
   int nx = 0, ny = 0, nzp = 0, nunits = 0;
   int64_t lap_doubles = 0;
@@ -341,6 +342,7 @@ int nls_twophase_build(nls_context *h);
 void nls_twophase_free(nls_context *h);
 int nls_launch_twophase(nls_context *h, bool want_r, bool want_k);
 int nls_lines3_build(nls_context *h);
+int nls_lines2_build(nls_context *h);
 void nls_lines3_free(nls_context *h);
 int nls_launch_lines3(nls_context *h, bool want_r, bool want_k);
 int nls_gather_nc(void);

@@ -123,7 +123,7 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
 # third case: interior + boundary clusters (overlapped halo); fourth: the multigrid preconditioner forced on (rank-local V-cycles)
-for dim, shape, comp, precond in [(2, (9, 14), -0.02, -1), (3, (5, 4, 9), -0.05, -1), (2, (40, 46), -0.004, -1), (3, (11, 9, 23), -0.02, 2)]:
+for dim, shape, comp, precond in [(2, (9, 14), -0.02, -1), (3, (5, 4, 9), -0.05, -1), (2, (40, 46), -0.004, -1), (3, (11, 9, 23), -0.02, 2), (2, (27, 44), -0.01, 2)]:
     uid = nls.distributed.broadcast_unique_id(dist, rank, device="cuda")   # one NCCL id per communicator
     mat = nls.NeoHookean(E=1.0, nu=0.3)
     fem, part = nls.distributed.slab_model(nls.FEMModel, shape, dim, world, rank, lr, uid)

@@ -7,13 +7,15 @@ import __graft_entry__ as g
 nls = g.build()
 dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
 n = int(sys.argv[1])
+dim = 3
+if n < 0:           # negative: 2-D, -n nodes per side
+    n, dim = -n, 2
 pre = [int(a) for a in sys.argv[2:] if "=" not in a] or [0, 1, 2]
 kv = dict(a.split("=") for a in sys.argv[2:] if "=" in a)
 lin_rtol = float(kv.pop("lin_rtol", 1e-8))
-dim = 3
 mesh = nls.grid_mesh(n, dim)
 fem = nls.FEMModel(mesh)
-plane = n * n
+plane = n ** (dim - 1)
 d = (np.arange(plane)[:, None] * dim + np.arange(dim)[None, :]).ravel()
 fem.addboundary(nls.Dirichlet(d, np.zeros(len(d))))
 t_nodes = (n - 1) * plane + np.arange(plane)
@@ -21,7 +23,7 @@ d = t_nodes * dim + (dim - 1)
 fem.addboundary(nls.Dirichlet(d, np.full(len(d), -0.01)))
 mat = nls.NeoHookean(E=1.0, nu=0.3)
 H = fem.handle(mat)
-Uaff = np.zeros((mesh.nn, dim)); Uaff[:, 2] = -0.01 * mesh.coords[:, 2]
+Uaff = np.zeros((mesh.nn, dim)); Uaff[:, dim - 1] = -0.01 * mesh.coords[:, dim - 1]
 Uaff = Uaff.ravel()
 ref = None
 for pc in pre:
