@@ -415,6 +415,19 @@ def run_ours(args):
             tr2, _src = ncu_traffic("C2", None)
             c2 = {"workload": workload_string(cfg2, world, "weak"), "value": dof2 / (ms2 * 1e-3), "unit": "DoF/s", "ms_per_step": ms2,
                   "roofline_frac": ab2 / (float(np.mean(t2)) * 1e-3) / 1e9 / hbm, "algorithmic_bytes": ab2, "traffic": tr2}
+            if not args.skip_newton:     # the same load step on C2: Newton-step time of BASELINE config 2
+                U2 = np.zeros((mesh2.nn, 2)); U2[:, 1] = -0.1 * LOAD_T * mesh2.coords[:, 1]
+                H2.call("nls_dev_upload_u", dp(np.ascontiguousarray(U2.ravel())))
+                H2.call("nls_solver_prepare")
+                o2 = nls._lib.NewtonOpts(rtol=1e-10, atol=1e-14, dtol=1e6, maxits=25, type_modified=0, lin_rtol=args.lin_rtol, lin_maxits=100000)
+                r2 = nls._lib.NewtonResult()
+                h2 = np.zeros(64)
+                H2.call("nls_sync"); barrier()
+                H2.call("nls_dev_newton_solve", C.byref(o2), dp(h2), C.byref(r2))
+                tot2 = allmax(r2.ms_total)
+                c2["newton_step"] = {"ms": tot2 / max(1, r2.iterations), "total_ms": tot2, "iterations": int(r2.iterations),
+                                     "converged": int(r2.reason) in (1, 2), "krylov_iterations": int(r2.lin_its_total),
+                                     "preconditioner": int(L.nls_krylov_preconditioner(H2.h)), "rtol": 1e-10, "lin_rtol": args.lin_rtol}
             del H2, fem2
         except Exception as e:      # noqa: BLE001
             c2 = {"error": repr(e)}

@@ -885,6 +885,7 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
 // bordered dense `\` of newtonarclength_fem.jl:104 becomes two of these). Vectors stay on the device; the
 // Lanczos / Givens scalars are 3 doubles per iteration on the host (one synchronisation per dot product): this
 // solver serves continuation runs, not the throughput path. rhs = h->d_b (masked inside), solution -> h->d_dU.
+// (Round 2: the scalars moved to a device control block; the comment above describes round 1.)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_lincomb3(int64_t n, double *y, double a, const double *x1, double b, const double *x2, double c, const double *x3) {
@@ -901,6 +902,91 @@ k_prec_abs(int64_t n, const double *__restrict__ dinv, const uint8_t *__restrict
     y[i] = con[i] ? 0.0 : fabs(dinv[i]) * r[i];
 }
 
+// MINRES control block: the Lanczos / Givens recurrences live on the device (no host synchronisation per iteration;
+// the host reads the block back once per chunk of 16 iterations, like the PCG loop)
+struct MinresCtl {
+  double beta, oldb, dbar, epsln, phibar, cs, sn, beta1, rtol;
+  double c_w0, c_w1, c_w2, phi;      // coefficients of the direction update, set by k_minres_scalars
+  double red[2];                     // [0] = v.y (alfa), [1] = r2.y (beta^2)
+  int done;                          // 0 running, 1 converged, 2 breakdown
+  int itn;
+};
+
+__global__ void k_minres_start(MinresCtl *c, double rtol) {       // red[1] = beta1^2 on entry
+  const double b1 = c->red[1];
+  c->rtol = rtol; c->itn = 0;
+  c->done = (b1 > 0.0) ? 0 : (b1 == 0.0 ? 1 : 2);
+  c->beta1 = b1 > 0.0 ? sqrt(b1) : 0.0;
+  c->beta = c->beta1; c->oldb = 0.0; c->dbar = 0.0; c->epsln = 0.0; c->phibar = c->beta1; c->cs = -1.0; c->sn = 0.0;
+}
+// v = y / beta
+__global__ void __launch_bounds__(256) k_minres_v(int64_t n, const MinresCtl *c, const double *__restrict__ y, double *__restrict__ v) {
+  if (c->done) return;
+  const double s = 1.0 / c->beta;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = s * y[i];
+}
+// y -= (beta / oldb) r1 (from the second iteration on), then alfa = v.y
+__global__ void __launch_bounds__(256) k_minres_y1(int64_t n, MinresCtl *c, const double *__restrict__ r1, const double *__restrict__ v,
+                                                    double *__restrict__ y, RedScratch rs) {
+  if (c->done) return;
+  const bool sub = c->itn >= 1;
+  const double f = sub ? c->beta / c->oldb : 0.0;
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double yi = y[i];
+    if (sub) { yi = fma(-f, r1[i], yi); y[i] = yi; }
+    acc[0] += v[i] * yi;
+  }
+  grid_reduce<1>(acc, rs.partial, rs.counter, &c->red[0]);
+}
+// y -= (alfa / beta) r2; r1 <- r2 is a pointer swap on the host; r2new = y; y = M^-1 r2new; beta^2 = r2new.y
+__global__ void __launch_bounds__(256) k_minres_y2(int64_t n, MinresCtl *c, const double *__restrict__ r2, double *__restrict__ r2new,
+                                                    const double *__restrict__ dinv, const uint8_t *__restrict__ con, double *__restrict__ y, RedScratch rs) {
+  if (c->done) return;
+  const double f = c->red[0] / c->beta;
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double t = fma(-f, r2[i], y[i]);
+    r2new[i] = t;
+    const double z = con[i] ? 0.0 : fabs(dinv[i]) * t;
+    y[i] = z;
+    acc[0] += t * z;
+  }
+  grid_reduce<1>(acc, rs.partial, rs.counter, &c->red[1]);
+}
+// the scalar recurrences of one iteration (Paige & Saunders), convergence test
+__global__ void k_minres_scalars(MinresCtl *c) {
+  if (c->done) return;
+  const double alfa = c->red[0], b2 = c->red[1];
+  c->itn += 1;
+  if (!(b2 >= 0.0)) { c->done = 2; return; }                       // NaN or an indefinite preconditioner
+  c->oldb = c->beta;
+  const double beta = sqrt(b2);
+  c->beta = beta;
+  const double oldeps = c->epsln, delta = c->cs * c->dbar + c->sn * alfa, gbar = c->sn * c->dbar - c->cs * alfa;
+  c->epsln = c->sn * beta; c->dbar = -c->cs * beta;
+  const double gamma = fmax(sqrt(gbar * gbar + beta * beta), 2.220446049250313e-16);
+  c->cs = gbar / gamma; c->sn = beta / gamma;
+  c->phi = c->cs * c->phibar;
+  c->phibar = c->sn * c->phibar;
+  c->c_w0 = 1.0 / gamma; c->c_w1 = -oldeps / gamma; c->c_w2 = -delta / gamma;
+}
+// w = c0 v + c1 w1 + c2 w2; x += phi w; then the convergence flag (after the update, like the host loop did)
+__global__ void __launch_bounds__(256) k_minres_w(int64_t n, MinresCtl *c, const double *__restrict__ v, const double *__restrict__ w1,
+                                                   const double *__restrict__ w2, double *__restrict__ w, double *__restrict__ x) {
+  if (c->done) return;
+  const double c0 = c->c_w0, c1 = c->c_w1, c2 = c->c_w2, phi = c->phi;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double wi = fma(c0, v[i], fma(c1, w1[i], c2 * w2[i]));
+    w[i] = wi;
+    x[i] = fma(phi, wi, x[i]);
+  }
+}
+__global__ void k_minres_test(MinresCtl *c) {
+  if (c->done) return;
+  if (fabs(c->phibar) <= c->rtol * c->beta1 || c->beta == 0.0) c->done = 1;
+}
+
 int nls_minres_solve(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status) {
   int rc;
   const int64_t n = h->nrows, nl = h->ndof_local();
@@ -909,61 +995,58 @@ int nls_minres_solve(nls_context *h, double rtol, int maxits, int *its, double *
       NLS_CUDA(h, cudaMalloc((void **)&h->d_mr[i], sizeof(double) * (size_t)std::max<int64_t>(1, nl)));
       NLS_CUDA(h, cudaMemsetAsync(h->d_mr[i], 0, sizeof(double) * (size_t)std::max<int64_t>(1, nl), h->stream));
     }
+  if (!h->d_mctl) {
+    NLS_CUDA(h, cudaMalloc((void **)&h->d_mctl, sizeof(MinresCtl)));
+    NLS_CUDA(h, cudaHostAlloc((void **)&h->h_mctl, sizeof(MinresCtl), cudaHostAllocDefault));
+  }
+  MinresCtl *ctl = reinterpret_cast<MinresCtl *>(h->d_mctl), *hctl = reinterpret_cast<MinresCtl *>(h->h_mctl);
   double *r1 = h->d_mr[0], *r2 = h->d_mr[1], *y = h->d_mr[2], *v = h->d_mr[3], *w = h->d_mr[4], *w1 = h->d_mr[5], *w2 = h->d_mr[6];
   double *x = h->d_dU;
   const unsigned g = vec_grid(h, n);
+  RedScratch rs = red_of(h);
   if ((rc = nls_launch_extract_dinv(h))) return rc;
   if ((rc = nls_sym_prepare(h))) return rc;
   struct SymScope { nls_context *h; ~SymScope() { h->sym_active = false; } } sym_scope{h};
+  NLS_CUDA(h, cudaMemsetAsync(ctl, 0, sizeof(MinresCtl), h->stream));
   NLS_CUDA(h, cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
   NLS_CUDA(h, cudaMemsetAsync(w, 0, sizeof(double) * n, h->stream));
   NLS_CUDA(h, cudaMemsetAsync(w2, 0, sizeof(double) * n, h->stream));
-  // r1 = masked b (constrained rows carry no equation)
-  k_prec_abs<<<g, 256, 0, h->stream>>>(n, h->d_dinv, h->d_con, h->d_b, y); NLS_KCHECK(h);          // y = M^-1 b (0 on constrained)
+  // r1 = r2 = b, y = M^-1 b (0 on constrained rows: they carry no equation), beta1^2 = b.y
   k_lincomb3<<<g, 256, 0, h->stream>>>(n, r1, 1.0, h->d_b, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
-  double beta1sq = 0.0;
-  if ((rc = nls_dev_dot(h, n, r1, y, &beta1sq))) return rc;     // y is zero on constrained rows, so the mask is implied
-  if (its) *its = 0;
-  if (relres) *relres = 0.0;
-  if (status) *status = 0;
-  if (!(beta1sq > 0.0)) { if (status) *status = (beta1sq == 0.0) ? 0 : 2; return NLS_OK; }   // b = 0 -> x = 0; NaN/negative -> breakdown
-  const double beta1 = sqrt(beta1sq);
-  k_lincomb3<<<g, 256, 0, h->stream>>>(n, r2, 1.0, r1, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
-  double oldb = 0.0, beta = beta1, dbar = 0.0, epsln = 0.0, phibar = beta1, cs = -1.0, sn = 0.0;
-  int itn = 0, st = 1;
-  while (itn < maxits) {
-    ++itn;
-    k_lincomb3<<<g, 256, 0, h->stream>>>(n, v, 1.0 / beta, y, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
-    if (h->distributed) { NLS_CUDA(h, cudaMemcpyAsync(h->d_p, v, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream)); if ((rc = nls_halo_exchange(h, h->d_p))) return rc; }
-    if ((rc = nls_launch_spmv(h, h->distributed ? h->d_p : v, y, true, false))) return rc;      // y = A v on the free block
-    if (itn >= 2) { k_lincomb3<<<g, 256, 0, h->stream>>>(n, y, 1.0, y, -beta / oldb, r1, 0.0, nullptr); NLS_KCHECK(h); }
-    double alfa = 0.0;
-    if ((rc = nls_dev_dot(h, n, v, y, &alfa))) return rc;
-    k_lincomb3<<<g, 256, 0, h->stream>>>(n, y, 1.0, y, -alfa / beta, r2, 0.0, nullptr); NLS_KCHECK(h);
-    std::swap(r1, r2);                                   // r1 <- r2
-    k_lincomb3<<<g, 256, 0, h->stream>>>(n, r2, 1.0, y, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);   // r2 <- y
-    k_prec_abs<<<g, 256, 0, h->stream>>>(n, h->d_dinv, h->d_con, r2, y); NLS_KCHECK(h);
-    oldb = beta;
-    double b2 = 0.0;
-    if ((rc = nls_dev_dot(h, n, r2, y, &b2))) return rc;
-    if (!(b2 >= 0.0)) { st = 2; break; }                 // NaN or an indefinite preconditioner
-    beta = sqrt(b2);
-    const double oldeps = epsln, delta = cs * dbar + sn * alfa, gbar = sn * dbar - cs * alfa;
-    epsln = sn * beta; dbar = -cs * beta;
-    const double gamma = std::max(sqrt(gbar * gbar + beta * beta), 2.220446049250313e-16);
-    cs = gbar / gamma; sn = beta / gamma;
-    const double phi = cs * phibar;
-    phibar = sn * phibar;
-    std::swap(w1, w2); std::swap(w2, w);                 // w1 <- w2, w2 <- w (old w is recycled as the new one)
-    k_lincomb3<<<g, 256, 0, h->stream>>>(n, w, 1.0 / gamma, v, -oldeps / gamma, w1, -delta / gamma, w2); NLS_KCHECK(h);
-    if ((rc = nls_launch_axpy(h, n, phi, w, x))) return rc;
-    if (fabs(phibar) <= rtol * beta1) { st = 0; break; }
-    if (beta == 0.0) { st = 0; break; }                  // exact Krylov subspace
+  k_lincomb3<<<g, 256, 0, h->stream>>>(n, r2, 1.0, h->d_b, 0.0, nullptr, 0.0, nullptr); NLS_KCHECK(h);
+  k_prec_abs<<<g, 256, 0, h->stream>>>(n, h->d_dinv, h->d_con, h->d_b, y); NLS_KCHECK(h);
+  k_dot<<<g, 256, 0, h->stream>>>(n, r1, y, nullptr, &ctl->red[1], rs); NLS_KCHECK(h);
+  if ((rc = nls_allreduce_sum(h, &ctl->red[1], 1))) return rc;
+  k_minres_start<<<1, 1, 0, h->stream>>>(ctl, rtol); NLS_KCHECK(h);
+  int queued = 0;
+  hctl->done = 0; hctl->itn = 0;
+  while (queued < maxits) {
+    const int todo = std::min(16, maxits - queued);
+    for (int k = 0; k < todo; ++k) {
+      k_minres_v<<<g, 256, 0, h->stream>>>(n, ctl, y, v); NLS_KCHECK(h);
+      if (h->distributed) {
+        NLS_CUDA(h, cudaMemcpyAsync(h->d_p, v, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        if ((rc = nls_halo_exchange(h, h->d_p))) return rc;
+      }
+      if ((rc = nls_launch_spmv(h, h->distributed ? h->d_p : v, y, true, false))) return rc;      // y = A v on the free block
+      k_minres_y1<<<g, 256, 0, h->stream>>>(n, ctl, r1, v, y, rs); NLS_KCHECK(h);
+      if ((rc = nls_allreduce_sum(h, &ctl->red[0], 1))) return rc;
+      k_minres_y2<<<g, 256, 0, h->stream>>>(n, ctl, r2, r1, h->d_dinv, h->d_con, y, rs); NLS_KCHECK(h);   // the new r2 overwrites the old r1
+      std::swap(r1, r2);                                 // r1 <- old r2, r2 <- the vector just written
+      if ((rc = nls_allreduce_sum(h, &ctl->red[1], 1))) return rc;
+      k_minres_scalars<<<1, 1, 0, h->stream>>>(ctl); NLS_KCHECK(h);
+      std::swap(w1, w2); std::swap(w2, w);               // w1 <- w2, w2 <- w (old w1 is recycled as the new w)
+      k_minres_w<<<g, 256, 0, h->stream>>>(n, ctl, v, w1, w2, w, x); NLS_KCHECK(h);
+      k_minres_test<<<1, 1, 0, h->stream>>>(ctl); NLS_KCHECK(h);
+    }
+    queued += todo;
+    NLS_CUDA(h, cudaMemcpyAsync(hctl, ctl, sizeof(MinresCtl), cudaMemcpyDeviceToHost, h->stream));
+    NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const int rcp = nls_p2p_failed(h); if (rcp) return rcp; }
+    if (hctl->done) break;
   }
-  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
-  { const int rcp = nls_p2p_failed(h); if (rcp) return rcp; }
-  if (its) *its = itn;
-  if (relres) *relres = fabs(phibar) / beta1;
-  if (status) *status = st;
+  if (its) *its = hctl->itn;
+  if (relres) *relres = hctl->beta1 > 0.0 ? fabs(hctl->phibar) / hctl->beta1 : 0.0;
+  if (status) *status = hctl->done == 1 ? 0 : (hctl->done == 2 ? 2 : 1);
   return NLS_OK;
 }

@@ -124,6 +124,8 @@ extern "C" int32_t nls_destroy(nls_handle h) {
   dev_free(&h->d_Ap); dev_free(&h->d_dinv); dev_free(&h->d_b); dev_free(&h->d_tmp);
   dev_free(&h->d_partial); dev_free(&h->d_ctl); dev_free(&h->d_scal); dev_free(&h->d_prof);
   for (int i = 0; i < 7; ++i) dev_free(&h->d_mr[i]);
+  if (h->d_mctl) { cudaFree(h->d_mctl); h->d_mctl = nullptr; }
+  if (h->h_mctl) { cudaFreeHost(h->h_mctl); h->h_mctl = nullptr; }
   for (int i = 0; i < 9; ++i) dev_free(&h->d_state[i]);
   dev_free(&h->d_u_n);
   dev_free(&h->d_send_nodes); dev_free(&h->d_recv_nodes); dev_free(&h->d_sendbuf); dev_free(&h->d_recvbuf);

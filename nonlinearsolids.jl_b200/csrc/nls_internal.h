@@ -272,6 +272,7 @@ struct nls_context {
   int opt_pcg_graph = 1;
   int opt_pcg_small = 1;   // systems of <= 8192 rows: the whole PCG solve in one thread block
   double *d_mr[7] = {nullptr};          // MINRES work vectors (allocated on first use)
+  void *d_mctl = nullptr, *h_mctl = nullptr;   // MINRES control block (device, pinned mirror)
   double *d_partial = nullptr;          // block partial sums
   PcgCtl *d_ctl = nullptr;
   PcgCtl *h_ctl = nullptr;              // pinned mirror
