@@ -109,6 +109,37 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(gpu):
+    """Pin this process (and so the pinned host buffers it first-touches) to the CPUs of the GPU's NUMA node: at N > 1 every
+    rank moves gigabytes of CSR values to the host at once, and remote-socket buffers halve that rate. What `numactl
+    --cpunodebind --membind` would do for a user of the C ABI. Returns a short description for the JSON line."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:            # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "numa node %d (%d cpus)" % (node, len(allowed))
+        return "numa node %d (no allowed cpu)" % node
+    except Exception as e:      # noqa: BLE001
+        return "not bound: %s" % e
+
+
 def algorithmic_bytes(dim, nen, nel, nn, ndof_rows, nnz):
     """conn + coords + U read + R write + vals write (colind / slot maps not counted)."""
     return 4 * nen * nel + 8 * dim * nn + 8 * ndof_rows + 8 * ndof_rows + 8 * nnz
@@ -237,6 +268,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = CONFIGS[args.config]
     dim = cfg["dim"]
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch
@@ -356,7 +388,7 @@ def run_ours(args):
             H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))
         e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
         barrier()
-        e2e = {"value": total_dof / e2e_s, "unit": "DoF/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+        e2e = {"value": total_dof / e2e_s, "unit": "DoF/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "host_buffers": "pinned, " + numa,
                "h2d_bytes_per_step": 8 * fem.ndof, "d2h_bytes_per_step": 8 * (fem.ndof + nrows + nnz)}
         del Uh, Rh, Vh
 
