@@ -446,39 +446,43 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         // ---------------- phase B: line pairs, four quadrature points ----------------
         if (on) {
           if (ptype == 0) {
-            auto self_col = [&](const int col, const int oa) {
-              if (col == L3_ZCOL) return;
-              const double2 *base = REC + col;
-#pragma unroll 2
-              for (int q = 0; q < L3_QH; ++q) {
-                const double2 *rq = base + q * NARR * L3_NCOLP;
-                const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
-                const double2 cc = rq[CC];
-                const double glo[3] = {a0.x, a0.y, a1.x}, ghi[3] = {a1.y, a2.x, a2.y};
-                if (DO_K) {
-                  const double plo[3] = {cc.x * glo[0], cc.x * glo[1], cc.x * glo[2]};
-                  const double mlo[3] = {cc.y * glo[0], cc.y * glo[1], cc.y * glo[2]};
-                  const double phi[3] = {cc.x * ghi[0], cc.x * ghi[1], cc.x * ghi[2]};
-                  // (lo, lo) and (hi, hi): symmetric, K_ik = 2 cs g_i g_k
-                  Kd[0] = fma(plo[0], glo[0], Kd[0]); Kd[1] = fma(plo[1], glo[1], Kd[1]); Kd[2] = fma(plo[2], glo[2], Kd[2]);
-                  Kd[3] = fma(plo[0], glo[1], Kd[3]); Kd[4] = fma(plo[0], glo[2], Kd[4]); Kd[5] = fma(plo[1], glo[2], Kd[5]);
-                  Kn[0] = fma(phi[0], ghi[0], Kn[0]); Kn[1] = fma(phi[1], ghi[1], Kn[1]); Kn[2] = fma(phi[2], ghi[2], Kn[2]);
-                  Kn[3] = fma(phi[0], ghi[1], Kn[3]); Kn[4] = fma(phi[0], ghi[2], Kn[4]); Kn[5] = fma(phi[1], ghi[2], Kn[5]);
-                  l3_acc(Ku, plo, mlo, ghi);
-                }
-                if (DO_R && !LAP_BUILD) {
-                  const double2 t0 = rq[13 * L3_NCOLP], t1 = rq[14 * L3_NCOLP], t2 = rq[15 * L3_NCOLP];
-                  // tau = {xx, yy | zz, xy | xz, yz}
-                  Kl[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], Kl[0])));
-                  Kl[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], Kl[1])));
-                  Kl[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], Kl[2])));
-                  Kl[3] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], Kl[3])));
-                  Kl[4] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], Kl[4])));
-                  Kl[5] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], Kl[5])));
-                }
+            // two of the line's four element columns per loop trip (a missing column reads the all-zero record): twice the
+            // independent loads and FMAs per trip -- the self pairs are the long pole of phase B and latency-bound
+            auto self_one = [&](const double2 *rq, const int oa) {
+              const double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP];
+              const double2 cc = rq[CC];
+              const double glo[3] = {a0.x, a0.y, a1.x}, ghi[3] = {a1.y, a2.x, a2.y};
+              if (DO_K) {
+                const double plo[3] = {cc.x * glo[0], cc.x * glo[1], cc.x * glo[2]};
+                const double mlo[3] = {cc.y * glo[0], cc.y * glo[1], cc.y * glo[2]};
+                const double phi[3] = {cc.x * ghi[0], cc.x * ghi[1], cc.x * ghi[2]};
+                // (lo, lo) and (hi, hi): symmetric, K_ik = 2 cs g_i g_k
+                Kd[0] = fma(plo[0], glo[0], Kd[0]); Kd[1] = fma(plo[1], glo[1], Kd[1]); Kd[2] = fma(plo[2], glo[2], Kd[2]);
+                Kd[3] = fma(plo[0], glo[1], Kd[3]); Kd[4] = fma(plo[0], glo[2], Kd[4]); Kd[5] = fma(plo[1], glo[2], Kd[5]);
+                Kn[0] = fma(phi[0], ghi[0], Kn[0]); Kn[1] = fma(phi[1], ghi[1], Kn[1]); Kn[2] = fma(phi[2], ghi[2], Kn[2]);
+                Kn[3] = fma(phi[0], ghi[1], Kn[3]); Kn[4] = fma(phi[0], ghi[2], Kn[4]); Kn[5] = fma(phi[1], ghi[2], Kn[5]);
+                l3_acc(Ku, plo, mlo, ghi);
+              }
+              if (DO_R && !LAP_BUILD) {
+                const double2 t0 = rq[13 * L3_NCOLP], t1 = rq[14 * L3_NCOLP], t2 = rq[15 * L3_NCOLP];
+                // tau = {xx, yy | zz, xy | xz, yz}
+                Kl[0] = fma(t0.x, glo[0], fma(t1.y, glo[1], fma(t2.x, glo[2], Kl[0])));
+                Kl[1] = fma(t1.y, glo[0], fma(t0.y, glo[1], fma(t2.y, glo[2], Kl[1])));
+                Kl[2] = fma(t2.x, glo[0], fma(t2.y, glo[1], fma(t1.x, glo[2], Kl[2])));
+                Kl[3] = fma(t0.x, ghi[0], fma(t1.y, ghi[1], fma(t2.x, ghi[2], Kl[3])));
+                Kl[4] = fma(t1.y, ghi[0], fma(t0.y, ghi[1], fma(t2.y, ghi[2], Kl[4])));
+                Kl[5] = fma(t2.x, ghi[0], fma(t2.y, ghi[1], fma(t1.x, ghi[2], Kl[5])));
               }
             };
-            self_col(c0, 3 * PR); self_col(c1, 2 * PR); self_col(c2, PR); self_col(c3, 0);
+            auto self_two = [&](const int colA, const int oaA, const int colB, const int oaB) {
+              const double2 *ba = REC + colA, *bb = REC + colB;
+#pragma unroll 1
+              for (int q = 0; q < L3_QH; ++q) {
+                self_one(ba + q * NARR * L3_NCOLP, oaA);
+                self_one(bb + q * NARR * L3_NCOLP, oaB);
+              }
+            };
+            self_two(c0, 3 * PR, c1, 2 * PR); self_two(c2, PR, c3, 0);
           } else if (DO_K) {
             // one loop over the (column, point) pairs of the pair's one or two columns; the A-side operands and the scalars
             // of the next pair are loaded as soon as the products that consume the current ones have been formed
