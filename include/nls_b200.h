@@ -114,6 +114,7 @@ int32_t nls_set_mesh(nls_handle h, int32_t dim, int64_t nnodes, int64_t nelem, i
  * (:chebyshev2 nodes). Shape tables are tabulated on the host with the reference's own
  * formulas (shapefunctions.jl:23-81, quadrature.jl:29-50). */
 int32_t nls_set_discretization(nls_handle h, int32_t p_order, int32_t nq);
+/* Setting a stateful material (kinds 2 and 4) also (re)initialises its per-qp state: initialize_state!. */
 int32_t nls_set_material(nls_handle h, int32_t kind, const double *params, int32_t nparams);
 /* fem.data[:A] (materials/defaults.jl:3,16; default 3e-4) */
 int32_t nls_set_area(nls_handle h, double area);
@@ -121,7 +122,9 @@ int32_t nls_set_area(nls_handle h, double area);
 int32_t nls_set_dirichlet(nls_handle h, int64_t n, const int64_t *dofs0, const double *vals);
 /* TimeDependent update! (boundary.jl:86-92): new values for the same DoF list */
 int32_t nls_set_dirichlet_values(nls_handle h, int64_t n, const double *vals);
-/* addboundary!(fem, Neumann(nodes, values)) (boundary.jl:32-39) */
+/* addboundary!(fem, Neumann(nodes, values)) (boundary.jl:32-39). The list is the concatenation of all Neumann boundaries
+ * of the model; a DoF listed more than once receives the SUM of its values (fem.jl:84-90 adds boundary after boundary; inside
+ * ONE reference boundary `F[nodes] .+= values` would keep only the last duplicate -- do not list a DoF twice in one boundary). */
 int32_t nls_set_neumann(nls_handle h, int64_t n, const int64_t *dofs0, const double *vals);
 int32_t nls_set_neumann_values(nls_handle h, int64_t n, const double *vals);
 /* DistributedForce(fdist) (src/gallery/distributedforce.jl:3-27): body-force density per component at the

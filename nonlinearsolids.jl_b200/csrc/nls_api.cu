@@ -222,6 +222,9 @@ extern "C" int32_t nls_set_material(nls_handle h, int32_t kind, const double *pa
     h->mat.p[5] = E * (Hk + Ha) / (E + Hk + Ha);
   }
   h->have_mat = true;
+  // a (new) stateful material starts from its initial state, like the reference's initialize_state! -- also when the handle
+  // already holds state arrays from a previous material object with other hardening parameters
+  if (kind == NLS_MAT_ELASTOPLASTIC_1D && h->d_state[0]) return nls_init_state(h);
   return alloc_state(h);
 }
 

@@ -43,14 +43,28 @@ Base.@kwdef struct NeoHookean <: NonlinearSolids.AbstractMaterial
     ρ::Float64 = 1.0
 end
 
+"""Small-strain J2 plasticity with linear isotropic hardening on Q1 quads (plane strain) / hexahedra: the stateful-material
+protocol of LinearElastoPlasticity1D (trial state in the internal-force pass, stored tangent, `save_state!` on `poststep!`)
+on 2-D / 3-D elements (SURVEY 8 f-2; params K, G, sigma_y, H). State arrays: `epsp_xx … epsp_xz`, `alpha` (+ `_n`)."""
+Base.@kwdef struct J2Plasticity <: NonlinearSolids.AbstractMaterial
+    E::Float64
+    ν::Float64
+    σy::Float64
+    H::Float64
+    ρ::Float64 = 1.0
+end
+NonlinearSolids.has_state(::J2Plasticity) = true
+
 matkind(::LinearElasticity1D) = Int32(0)
 matkind(::ExponentialMaterial) = Int32(1)
 matkind(::LinearElastoPlasticity1D) = Int32(2)
 matkind(::NeoHookean) = Int32(3)
+matkind(::J2Plasticity) = Int32(4)
 matparams(m::LinearElasticity1D) = [m.E]
 matparams(m::ExponentialMaterial) = [m.σ_sat, m.b]
 matparams(m::LinearElastoPlasticity1D) = [m.E, m.Hκ, m.Hα, m.κ₀, m.α₀, m.Eep]
 matparams(m::NeoHookean) = [m.μ, m.λ]
+matparams(m::J2Plasticity) = [m.E / (3 * (1 - 2 * m.ν)), m.E / (2 * (1 + m.ν)), m.σy, m.H]
 
 """Device-resident mirror of a FEMModel (one GPU). Indices are converted 1-based -> 0-based once."""
 mutable struct B200Model
