@@ -225,7 +225,8 @@ int32_t nls_assembly_scheme(nls_handle h);
 /* debug: cycle counters of the gather kernel phases after nls_set_option(h, "profile_phases", 1):
  * {staging, element phase, 0, block-task phase, clusters, cp.async wait, barrier, issue of the next stage}, summed over CTAs */
 int32_t nls_debug_counters(nls_handle h, int64_t *out8);
-/* preconditioner of the next Krylov solve: 0 Jacobi, 1 block-Jacobi, 2 geometric multigrid (nls_set_option "precond") */
+/* preconditioner of the next Krylov solve: 0 Jacobi, 1 block-Jacobi, 2 geometric multigrid (nls_set_option "precond").
+ * COLLECTIVE after nls_comm_init: the ranks agree (a rank whose slab has no grid hierarchy vetoes the multigrid for all). */
 int32_t nls_krylov_preconditioner(nls_handle h);
 /* optional, collective after nls_comm_init: allocate the solver's work space (the multigrid hierarchy of the Krylov
  * preconditioner on grid-topology 3-D meshes) now instead of inside the first solve */

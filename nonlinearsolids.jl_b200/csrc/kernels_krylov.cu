@@ -789,10 +789,13 @@ int nls_pcg_solve(nls_context *h, double rtol, int maxits, int fixed_iters, int 
   const int64_t n = h->nrows;
   RedScratch rs = red_of(h);
   // grid-topology 3-D meshes: multigrid (or block-Jacobi) preconditioner, kernels_mg.cu
-  if (fixed_iters == 0 && h->mg.ok && (h->distributed || !(h->mg.ghost_below || h->mg.ghost_above)) &&
-      (h->opt_precond >= 1 || (h->opt_precond < 0 && h->nn >= 10000))) {
-    h->mg.mode = h->opt_precond == 1 ? 1 : 2;
-    return nls_pcg_solve_mg(h, rtol, maxits, its, relres, status);
+  if (fixed_iters == 0) {
+    bool use = false;
+    if ((rc = nls_mg_agreed(h, &use))) return rc;       // collective when distributed: all ranks take the same path
+    if (use) {
+      h->mg.mode = h->opt_precond == 1 ? 1 : 2;
+      return nls_pcg_solve_mg(h, rtol, maxits, its, relres, status);
+    }
   }
   if (!h->distributed && h->opt_pcg_small && fixed_iters == 0 && n > 0 && n <= (int64_t)PCG_SMALL_THREADS * PCG_SMALL_RPT &&
       h->nnz <= (int64_t)1 << 21) {

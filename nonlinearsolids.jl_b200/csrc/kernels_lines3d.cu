@@ -825,9 +825,13 @@ int nls_lines2_build(nls_context *h) {
   const int32_t *c = h->h_conn.data();
   const int64_t nel = h->nel, nn = h->nn;
   if (c[1] != c[0] + 1) return NLS_OK;
-  const int64_t nx = (int64_t)c[2] - c[0];
-  if (nx < 2 || nx > 1000000 || nel % (nx - 1)) return NLS_OK;
-  const int64_t epr = nx - 1, nlay = nel / epr, nzp = nlay + 1;
+  // elements per row: the run of elements whose first node advances by one (the node above may sit in a ghost row with
+  // an unrelated base id, so the row length cannot be read off one element)
+  int64_t epr = 1;
+  while (epr < nel && c[epr * 4] == c[0] + epr && c[epr * 4 + 1] == c[0] + epr + 1) ++epr;
+  const int64_t nx = epr + 1;
+  if (nx < 2 || nx > 1000000 || nel % epr) return NLS_OK;
+  const int64_t nlay = nel / epr, nzp = nlay + 1;
   if (nn != nx * nzp || nzp > 1000000) return NLS_OK;
   std::vector<int32_t> pbase((size_t)nzp);
   for (int64_t k = 0; k < nlay; ++k) pbase[k] = c[k * epr * 4];

@@ -30,6 +30,8 @@
 #ifndef NLS_TRY
 #define NLS_TRY(call) do { int rc_ = (call); if (rc_ != NLS_OK) return rc_; } while (0)
 #endif
+static const bool mg_trace_on = std::getenv("NLS_B200_MG_TRACE") != nullptr;
+#define MG_TRACE(h, ...) do { if (mg_trace_on) { cudaStreamSynchronize((h)->stream); fprintf(stderr, "[mg %d] ", (h)->rank); fprintf(stderr, __VA_ARGS__); fprintf(stderr, " (%s)\n", cudaGetErrorString(cudaGetLastError())); fflush(stderr); } } while (0)
 #define MG_KCHECK(h) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
   (h)->err = std::string("multigrid kernel launch: ") + cudaGetErrorString(e_); return NLS_ERR_CUDA; } (h)->launches++; } while (0)
 
@@ -449,6 +451,8 @@ static void mg_free_levels(nls_context *h) {
   if (m.vals32) cudaFree(m.vals32);
   for (double *v : {m.gbelow, m.gabove, m.gsend, m.rf}) if (v) cudaFree(v);
   if (m.conf) cudaFree(m.conf);
+  if (m.d_vote) cudaFree(m.d_vote);
+  m.d_vote = nullptr;
   m.vals32 = nullptr; m.gbelow = m.gabove = m.gsend = m.rf = nullptr; m.conf = nullptr;
   m.laid_out = false; m.version = -1; m.power_version = -1000; m.nlev = 0;
 }
@@ -535,6 +539,7 @@ static int mg_layout(nls_context *h) {
     NLS_FAIL(h, NLS_ERR_STATE, "multigrid: ghost planes without a communicator");
   }
   m.p0 = p0; m.NZ0 = NZ;
+  MG_TRACE(h, "layout: dist %d p0 %d nzo %d NZ %d below %d above %d", (int)m.dist, p0, m.nzo, NZ, m.rank_below, m.rank_above);
   int nx = p.nx, ny = p.ny, nz = NZ, l = 0;
   int own0 = p0, own1 = p0 + m.nzo;       // owned global planes on the current level
   for (;;) {
@@ -571,6 +576,7 @@ static int mg_layout(nls_context *h) {
     own0 = c0; own1 = c1;
     nx = cx; ny = cy; nz = cz;
   }
+  MG_TRACE(h, "layout: %d levels", l);
   m.nlev = l;
   if (m.nlev < 2) { m.ok = false; NLS_FAIL(h, NLS_ERR_STATE, "multigrid: the grid is too small for a hierarchy"); }
   const size_t plane_rows = (size_t)p.nx * p.ny * 243;
@@ -704,6 +710,7 @@ int nls_mg_setup(nls_context *h) {
     k_mg_f64_to_con<<<mg_grid(h, nl), 256, 0, h->stream>>>(nl, m.rf, m.conf); MG_KCHECK(h);
     NLS_CUDA(h, cudaMemsetAsync(m.rf, 0, sizeof(double) * (size_t)nl, h->stream));
   }
+  MG_TRACE(h, "setup: masks done");
   MgFine F = mg_fine_args(h);
   k_mg_fine_dinv<<<mg_grid(h, (int64_t)F.nx * F.ny * F.nzo), 256, 0, h->stream>>>(F, m.lev[0].dinv); MG_KCHECK(h);
   if (m.dist) {      // boundary row planes of the CSR matrix, in stencil format, to the neighbours
@@ -718,9 +725,11 @@ int nls_mg_setup(nls_context *h) {
     const int ge = nc->GroupEnd();
     if (e || ge) NLS_FAIL(h, NLS_ERR_NCCL, "multigrid: row exchange (ncclSend/Recv) failed");
   }
+  MG_TRACE(h, "setup: rows exchanged");
   for (int l = 1; l < m.nlev; ++l) {
     MgLevel &Lf = m.lev[l - 1], &Lc = m.lev[l];
     MgBox C = mg_box(Lc);
+    MG_TRACE(h, "setup: level %d grid %d x %d x %d own [%d,%d) box base %d planes %d", l, Lc.nx, Lc.ny, Lc.NZ, Lc.zown0, Lc.zown1, Lc.zbase, Lc.nzb);
     // levels >= 2 are replicated: every rank computes the rows whose fine planes it owns (all of them from level 3 on, where
     // the fine operator is already whole on every rank), zeros elsewhere, and the ranks sum
     const bool partial = l == 2 && m.dist;
@@ -742,7 +751,7 @@ int nls_mg_setup(nls_context *h) {
   // eigenvalue bounds: the Jacobian of consecutive Newton iterations changes by a few per cent at most, well inside the
   // 10 % safety margin: a full power iteration every eighth set of values, in between the bounds are kept
   if (m.power_version < 0 || h->vals_version - m.power_version >= 8 || h->vals_version < m.power_version) {
-    for (int l = 0; l < m.nlev; ++l) NLS_TRY(mg_lambda_max(h, l, &m.lev[l].lmax));
+    for (int l = 0; l < m.nlev; ++l) { NLS_TRY(mg_lambda_max(h, l, &m.lev[l].lmax)); MG_TRACE(h, "setup: lambda_max level %d = %g", l, m.lev[l].lmax); }
     m.power_version = h->vals_version;
   }
   m.version = h->vals_version;
@@ -800,6 +809,26 @@ static int mg_vcycle(nls_context *h, int l, const double *b, double *x) {
                                                           l == 0 ? h->d_con : nullptr, mg_box(C), C.x, x);
   MG_KCHECK(h);
   return mg_cheb(h, l, b, x, m.degree, m.ratio, false);
+}
+
+// Does this solve take the multigrid path? Single GPU: the local answer. Multi-GPU: the path is a sequence of collectives,
+// so either every rank takes it or none does -- one allreduce per solve turns the ranks' votes (hierarchy available, option,
+// size rule) into a common decision; a rank whose slab has no hierarchy vetoes it for all. COLLECTIVE when distributed.
+int nls_mg_agreed(nls_context *h, bool *use) {
+  MgPlan &m = h->mg;
+  const int64_t nodes = h->distributed ? h->n_owned * (int64_t)h->nranks : h->nn;
+  const bool mine = m.ok && (h->distributed || !(m.ghost_below || m.ghost_above)) &&
+                    (h->opt_precond >= 1 || (h->opt_precond < 0 && nodes >= 10000));
+  if (!h->distributed || h->nranks < 2) { *use = mine; return NLS_OK; }
+  if (!m.d_vote) NLS_CUDA(h, cudaMalloc((void **)&m.d_vote, sizeof(double)));
+  double v = mine ? 1.0 : 0.0;
+  NLS_CUDA(h, cudaMemcpyAsync(m.d_vote, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (h->nccl->AllReduce(m.d_vote, m.d_vote, 1, NCCL_DYN_FLOAT64, NCCL_DYN_SUM, h->comm, h->stream) != 0)
+    NLS_FAIL(h, NLS_ERR_NCCL, "multigrid: ncclAllReduce (agreement) failed");
+  NLS_CUDA(h, cudaMemcpyAsync(&v, m.d_vote, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NLS_CUDA(h, cudaStreamSynchronize(h->stream));
+  *use = v == (double)h->nranks;
+  return NLS_OK;
 }
 
 // z = M^-1 r (r masked; z's ghost entries are scratch)

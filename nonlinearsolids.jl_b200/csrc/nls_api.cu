@@ -962,9 +962,9 @@ extern "C" int32_t nls_debug_counters(nls_handle h, int64_t *out8) {
 // which preconditioner the next Krylov solve of this model uses: 0 Jacobi, 1 block-Jacobi, 2 multigrid
 extern "C" int32_t nls_krylov_preconditioner(nls_handle h) {
   if (!h) return -1;
-  const bool mg_possible = h->mg.ok && (h->distributed || !(h->mg.ghost_below || h->mg.ghost_above));
-  if (mg_possible && (h->opt_precond >= 1 || (h->opt_precond < 0 && h->nn >= 10000))) return h->opt_precond == 1 ? 1 : 2;
-  return 0;
+  bool use = false;                                  // collective when distributed (one small allreduce)
+  if (nls_mg_agreed(h, &use) != NLS_OK) return -1;
+  return use ? (h->opt_precond == 1 ? 1 : 2) : 0;
 }
 
 // Allocates what the first linear solve would otherwise allocate inside its timed region (the multigrid hierarchy of a
@@ -972,8 +972,9 @@ extern "C" int32_t nls_krylov_preconditioner(nls_handle h) {
 extern "C" int32_t nls_solver_prepare(nls_handle h) {
   NLS_ENTER(h);
   NLS_TRY(check_ready(h, "nls_solver_prepare"));
-  if (h->opt_precond == 0 || (h->opt_precond < 0 && h->nn < 10000)) return NLS_OK;
-  return nls_mg_prepare(h, true);
+  bool use = false;
+  NLS_TRY(nls_mg_agreed(h, &use));
+  return use ? nls_mg_prepare(h, true) : NLS_OK;
 }
 
 extern "C" int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24) {

@@ -120,6 +120,7 @@ struct MgPlan {
   bool ok = false;                 // the mesh can have a hierarchy
   bool laid_out = false;           // levels and buffers exist (first set-up; again when the communicator changes)
   bool dist = false;
+  double *d_vote = nullptr;        // multi-GPU: scratch of the per-solve agreement on the preconditioner
   bool ghost_below = false, ghost_above = false;
   int nlev = 0, z0 = 0, nzo = 0;   // line-table index of the first owned plane, owned planes
   int p0 = 0, NZ0 = 0;             // global index of the first owned plane, global plane count
@@ -395,6 +396,7 @@ void nls_direct_free(nls_context *h);
 void nls_mg_free(nls_context *h);
 void nls_mg_invalidate(nls_context *h);
 int nls_mg_build(nls_context *h);
+int nls_mg_agreed(nls_context *h, bool *use);   // collective when distributed
 int nls_mg_prepare(nls_context *h, bool collective);
 int nls_mg_setup(nls_context *h);
 int nls_pcg_solve_mg(nls_context *h, double rtol, int maxits, int *its, double *relres, int *status);

@@ -180,7 +180,7 @@ def test_two_rank_nccl_parity(tmp_path):
     script.write_text(_NCCL_WORKER)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script), ROOT],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2
 
