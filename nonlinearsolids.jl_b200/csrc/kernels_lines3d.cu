@@ -171,42 +171,6 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
   const double mu = LAP_BUILD ? 0.0 : mp.p[0], lam = mp.p[1];
   const int nx = P.nx, ny = P.ny, nzp = P.nzp, nxm1 = nx - 1;
 
-  // ---- phase-B role of this thread (fixed for the whole launch): pair type and the tile-relative line A = (ay, az) ----
-  // warps {0,1} self pairs; {2,3,6,7,11} pairs with two common element columns, d = (1,0) and (0,1); {4,5,8,9,10} pairs with
-  // one, d = (1,1) and (-1,1): per SM sub-partition (warp & 3) the roles add up to about the same DFMA count
-  int ptype = -1, ay = 0, az = 0;
-  {
-    int role, ord;
-    switch (warp) {
-      case 0: role = 0; ord = 0; break;  case 1: role = 0; ord = 1; break;
-      case 2: role = 1; ord = 0; break;  case 3: role = 1; ord = 1; break;
-      case 6: role = 1; ord = 2; break;  case 7: role = 1; ord = 3; break;  case 11: role = 1; ord = 4; break;
-      case 4: role = 2; ord = 0; break;  case 5: role = 2; ord = 1; break;
-      case 8: role = 2; ord = 2; break;  case 9: role = 2; ord = 3; break;  default: role = 2; ord = 4; break;
-    }
-    int k = ord * 32 + lane;
-    if (role == 0) { ptype = 0; ay = k & 7; az = k >> 3; }
-    else if (role == 1) {
-      if (k < 72) { ptype = 1; ay = k % 9 - 1; az = k / 9; }                       // A from y = -1: the pair (-1, 0) belongs to line 0's rows
-      else if (k < 144) { k -= 72; ptype = 3; ay = k & 7; az = (k >> 3) - 1; }
-    } else if (k < 158) {
-      if (k < 79) ptype = 4; else { ptype = 2; k -= 79; }
-      if (k < 64) { ay = k & 7; az = k >> 3; }
-      else if (k < 72) { ay = ptype == 4 ? -1 : 8; az = k - 65; }                  // B in the tile, A beside it
-      else { az = -1; ay = ptype == 4 ? k - 72 : k - 71; }                         // ... A below it
-    }
-  }
-  const int dy = (ptype == 1 || ptype == 4) ? 1 : (ptype == 2 ? -1 : 0), dz = ptype >= 2 ? 1 : 0;
-  const bool two = (ptype == 1 || ptype == 3);
-  // corner pair (dy' + 2 dz') of line A and of line B inside the first and the second common element column
-  const int oa0 = (ptype == 1 ? 2 : (ptype == 4 ? 0 : 1)) * PR, ob0 = (ptype == 2 ? 2 : 3) * PR, ob1 = (ptype == 1 ? 1 : 2) * PR;   // oa1 = 0
-  // row issuers: cp.async.bulk blocks its issuer while the TMA queue (about eight requests) is full, and one interval's rows
-  // keep the SM's store path busy for about 4 k cycles (32 B per clock; profiles/r2_ubench_bulk.txt). The hand-off therefore
-  // sits where warps idle anyway: warp 11 holds none of the 324 phase-A items and issues 32 rows during the first half of
-  // phase A; the five warps of one-column pairs finish the first half of phase B long before the others and issue 6-7 rows each.
-  const int oord = (warp == 4) ? 0 : (warp == 5) ? 1 : (warp == 8) ? 2 : (warp == 9) ? 3 : (warp == 10) ? 4 : -1;
-  const int iline = (warp == 11) ? lane : 32 + oord * 7 + lane;
-  const bool isslot = STAGE && (warp == 11 || (oord >= 0 && lane < 7 && iline < L3_NL));
   for (;;) {
     if (tid == 0) { const int uu = (int)atomicAdd(P.counter, 1u); s_unit = uu; s_lapoff = uu < P.nunits ? (long long)P.lapoff[uu] : 0ll; }
     __syncthreads();
@@ -216,6 +180,43 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     const int y0 = un.x, z0 = un.y, i0 = un.z, i1 = un.w;
     const int ifirst = i0 > 0 ? i0 - 1 : 0;    // a chunk that starts inside the line first runs one interval without stores
     const int ilast = (i1 == nxm1) ? nxm1 : i1 - 1;   // last node plane whose rows this unit writes
+
+    // ---- phase-B role of this thread (the same for every unit; derived again per unit so that it does not occupy registers across the interval loop): pair type and the tile-relative line A = (ay, az) ----
+    // warps {0,1} self pairs; {2,3,6,7,11} pairs with two common element columns, d = (1,0) and (0,1); {4,5,8,9,10} pairs with
+    // one, d = (1,1) and (-1,1): per SM sub-partition (warp & 3) the roles add up to about the same DFMA count
+    int ptype = -1, ay = 0, az = 0;
+    {
+      int role, ord;
+      switch (warp) {
+        case 0: role = 0; ord = 0; break;  case 1: role = 0; ord = 1; break;
+        case 2: role = 1; ord = 0; break;  case 3: role = 1; ord = 1; break;
+        case 6: role = 1; ord = 2; break;  case 7: role = 1; ord = 3; break;  case 11: role = 1; ord = 4; break;
+        case 4: role = 2; ord = 0; break;  case 5: role = 2; ord = 1; break;
+        case 8: role = 2; ord = 2; break;  case 9: role = 2; ord = 3; break;  default: role = 2; ord = 4; break;
+      }
+      int k = ord * 32 + lane;
+      if (role == 0) { ptype = 0; ay = k & 7; az = k >> 3; }
+      else if (role == 1) {
+        if (k < 72) { ptype = 1; ay = k % 9 - 1; az = k / 9; }                       // A from y = -1: the pair (-1, 0) belongs to line 0's rows
+        else if (k < 144) { k -= 72; ptype = 3; ay = k & 7; az = (k >> 3) - 1; }
+      } else if (k < 158) {
+        if (k < 79) ptype = 4; else { ptype = 2; k -= 79; }
+        if (k < 64) { ay = k & 7; az = k >> 3; }
+        else if (k < 72) { ay = ptype == 4 ? -1 : 8; az = k - 65; }                  // B in the tile, A beside it
+        else { az = -1; ay = ptype == 4 ? k - 72 : k - 71; }                         // ... A below it
+      }
+    }
+    const int dy = (ptype == 1 || ptype == 4) ? 1 : (ptype == 2 ? -1 : 0), dz = ptype >= 2 ? 1 : 0;
+    const bool two = (ptype == 1 || ptype == 3);
+    // corner pair (dy' + 2 dz') of line A and of line B inside the first and the second common element column
+    const int oa0 = (ptype == 1 ? 2 : (ptype == 4 ? 0 : 1)) * PR, ob0 = (ptype == 2 ? 2 : 3) * PR, ob1 = (ptype == 1 ? 1 : 2) * PR;   // oa1 = 0
+    // row issuers: cp.async.bulk blocks its issuer while the TMA queue (about eight requests) is full, and one interval's rows
+    // keep the SM's store path busy for about 4 k cycles (32 B per clock; profiles/r2_ubench_bulk.txt). The hand-off therefore
+    // sits where warps idle anyway: warp 11 holds none of the 324 phase-A items and issues 32 rows during the first half of
+    // phase A; the five warps of one-column pairs finish the first half of phase B long before the others and issue 6-7 rows each.
+    const int oord = (warp == 4) ? 0 : (warp == 5) ? 1 : (warp == 8) ? 2 : (warp == 9) ? 3 : (warp == 10) ? 4 : -1;
+    const int iline = (warp == 11) ? lane : 32 + oord * 7 + lane;
+    const bool isslot = STAGE && (warp == 11 || (oord >= 0 && lane < 7 && iline < L3_NL));
 
     // ---- per-unit role of this thread in phase B ----
     // geoA / geoB: where the pair's blocks go in the staging image -- staging offset of the line | neighbour lines << 16 |
@@ -662,7 +663,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     // the staging image is next rewritten at the end of the next unit's first interval; its issuers wait for these copies
     // in the second half of that interval (above), and the barrier that follows holds everyone else back
   }
-  if (isslot) l3_bulk_wait_read();
+  if (STAGE) l3_bulk_wait_read();       // (a thread without outstanding bulk groups returns at once)
   // the last CTA to run out of units rearms the counters for the next launch
   if (tid == 0) {
     __threadfence();

@@ -6,24 +6,31 @@ import numpy as np
 import __graft_entry__ as g
 nls = g.build()
 dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-n = int(sys.argv[1])
-dim = 3
-if n < 0:           # negative: 2-D, -n nodes per side
-    n, dim = -n, 2
+shape = None
+if "," in sys.argv[1]:      # nx,ny,nz: a box (the top displacement stays 1 % of one nx-sided block)
+    shape = tuple(int(v) for v in sys.argv[1].split(","))
+    n, dim = shape[0], len(shape)
+else:
+    n = int(sys.argv[1])
+    dim = 3
+    if n < 0:           # negative: 2-D, -n nodes per side
+        n, dim = -n, 2
 pre = [int(a) for a in sys.argv[2:] if "=" not in a] or [0, 1, 2]
 kv = dict(a.split("=") for a in sys.argv[2:] if "=" in a)
 lin_rtol = float(kv.pop("lin_rtol", 1e-8))
-mesh = nls.grid_mesh(n, dim)
+mesh = nls.grid_mesh(shape if shape else n, dim)
 fem = nls.FEMModel(mesh)
-plane = n ** (dim - 1)
+plane = int(np.prod(shape[:-1])) if shape else n ** (dim - 1)
+nslow = shape[-1] if shape else n
+height = (nslow - 1) / (n - 1)
 d = (np.arange(plane)[:, None] * dim + np.arange(dim)[None, :]).ravel()
 fem.addboundary(nls.Dirichlet(d, np.zeros(len(d))))
-t_nodes = (n - 1) * plane + np.arange(plane)
+t_nodes = (nslow - 1) * plane + np.arange(plane)
 d = t_nodes * dim + (dim - 1)
 fem.addboundary(nls.Dirichlet(d, np.full(len(d), -0.01)))
 mat = nls.NeoHookean(E=1.0, nu=0.3)
 H = fem.handle(mat)
-Uaff = np.zeros((mesh.nn, dim)); Uaff[:, dim - 1] = -0.01 * mesh.coords[:, dim - 1]
+Uaff = np.zeros((mesh.nn, dim)); Uaff[:, dim - 1] = -0.01 * mesh.coords[:, dim - 1] / height
 Uaff = Uaff.ravel()
 ref = None
 for pc in pre:
