@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnls_b200.so")
+# NLS_B200_LIB: a developer override used by tools/ to time kernel variants built side by side
+LIB_PATH = os.environ.get("NLS_B200_LIB") or os.path.join(_HERE, "libnls_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

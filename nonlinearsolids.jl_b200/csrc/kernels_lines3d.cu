@@ -46,6 +46,13 @@
 #define L3_THREADS 384                   // 12 warps: 2 of self pairs, 5 of two-column pairs, 5 of one-column pairs
 #define L3_NPT L3_THREADS                // Laplacian-table slots per interval: one per thread
 #define L3_QH 4                          // quadrature points per half interval
+#ifndef L3_PAIR_UNROLL
+#define L3_PAIR_UNROLL 2                 // unroll factors of the two phase-B loops (measured)
+#endif
+#ifndef L3_SELF_UNROLL
+#define L3_SELF_UNROLL 2
+#endif
+static constexpr int kL3PairUnroll = L3_PAIR_UNROLL, kL3SelfUnroll = L3_SELF_UNROLL;
 #define L3_SLOT 246                      // staging doubles per line: 243 (27 blocks x 9) + alignment slack, 16-byte multiple
 
 struct L3Line {                          // per node line (y, z): closed-form CSR addressing of its rows
@@ -372,30 +379,43 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
                 }
               }
             }
-            // one division for both inverses: r = 1 / (det J det M), J^-1 = adj J (det M r), M^-1 = adj M (det J r), det F = det M^2 r
-            double Ji[9], Mi[9];
-            const double detJ = l3_adj(J, Ji);
+            // one division for both inverses: r = 1 / (det J det M), J^-1 = adj J (det M r), M^-1 = adj M (det J r), det F = det M^2 r.
+            // Order chosen for register pressure (the pair accumulators stay live through this phase): H adj(J) is formed
+            // before M overwrites J, so that J, H and adj J are dead when adj M is built.
+            double Mi[9], Hp[9];
             double cs, cw, lnJ = 0.0, c1 = 0.0, c2 = 0.0, wdet;
-            if (LAP_BUILD) {
-              const double id = 1.0 / detJ;
-#pragma unroll
-              for (int k = 0; k < 9; ++k) Mi[k] = Ji[k] * id;
+            {
+              double Ji[9];
+              const double detJ = l3_adj(J, Ji);
               wdet = TAB[192 + q] * detJ;
-              cs = 0.5 * wdet; cw = 0.5 * wdet;
-            } else {
-              double M[9];
+              if (LAP_BUILD) {
+                const double id = 1.0 / detJ;
 #pragma unroll
-              for (int k = 0; k < 9; ++k) M[k] = J[k] + H[k];
-              const double detM = l3_adj(M, Mi);
-              const double r = 1.0 / (detJ * detM);
-              const double sj = detM * r, sm_ = detJ * r;
+                for (int k = 0; k < 9; ++k) Mi[k] = Ji[k] * id;
+                cs = 0.5 * wdet; cw = 0.5 * wdet;
+              } else {
+                if (DO_R) {
 #pragma unroll
-              for (int k = 0; k < 9; ++k) { Ji[k] *= sj; Mi[k] *= sm_; }
-              wdet = TAB[192 + q] * detJ;
-              lnJ = log(detM * sj);
-              c1 = wdet * mu; c2 = wdet * lam;
-              const double c3 = c1 - c2 * lnJ;
-              cs = 0.5 * (c2 + c3); cw = 0.5 * (c2 - c3);
+                  for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Hp[r * 3 + c] = fma(H[r * 3], Ji[c], fma(H[r * 3 + 1], Ji[3 + c], H[r * 3 + 2] * Ji[6 + c]));
+                }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) J[k] += H[k];                    // J <- M = J + H
+                const double detM = l3_adj(J, Mi);
+                const double r = 1.0 / (detJ * detM);
+                const double sj = detM * r, sm_ = detJ * r;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Mi[k] *= sm_;
+                if (DO_R) {
+#pragma unroll
+                  for (int k = 0; k < 9; ++k) Hp[k] *= sj;                   // Hp = H J^-1 = F - I
+                }
+                lnJ = log(detM * sj);
+                c1 = wdet * mu; c2 = wdet * lam;
+                const double c3 = c1 - c2 * lnJ;
+                cs = 0.5 * (c2 + c3); cw = 0.5 * (c2 - c3);
+              }
             }
             double2 *rq = REC + ql * NARR * L3_NCOLP + col;
             rq[CC] = make_double2(cs, cw);
@@ -415,11 +435,6 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
             }
             if (DO_R && !LAP_BUILD) {
               // Kirchhoff stress times w detJ: tau = mu (b - I) + lam lnJ I, b - I = Hp + Hp^T + Hp Hp^T, Hp = H J^-1 = F - I
-              double Hp[9];
-#pragma unroll
-              for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) Hp[r * 3 + c] = fma(H[r * 3], Ji[c], fma(H[r * 3 + 1], Ji[3 + c], H[r * 3 + 2] * Ji[6 + c]));
               const double cl = c2 * lnJ;
               auto ee = [&](int r, int c) {
                 return (Hp[r * 3 + c] + Hp[c * 3 + r]) + fma(Hp[r * 3], Hp[c * 3], fma(Hp[r * 3 + 1], Hp[c * 3 + 1], Hp[r * 3 + 2] * Hp[c * 3 + 2]));
@@ -477,7 +492,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
             };
             auto self_two = [&](const int colA, const int oaA, const int colB, const int oaB) {
               const double2 *ba = REC + colA, *bb = REC + colB;
-#pragma unroll 1
+#pragma unroll kL3SelfUnroll
               for (int q = 0; q < L3_QH; ++q) {
                 self_one(ba + q * NARR * L3_NCOLP, oaA);
                 self_one(bb + q * NARR * L3_NCOLP, oaB);
@@ -491,7 +506,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
             const double2 *rq = REC + c0;
             int oa = oa0, ob = ob0;
             double2 a0 = rq[oa], a1 = rq[oa + L3_NCOLP], a2 = rq[oa + 2 * L3_NCOLP], cc = rq[CC];
-#pragma unroll 1
+#pragma unroll kL3PairUnroll
             for (int it = 0; it < n; ++it) {
               const double2 b0 = rq[ob], b1 = rq[ob + L3_NCOLP], b2 = rq[ob + 2 * L3_NCOLP];
               const double plo[3] = {cc.x * a0.x, cc.x * a0.y, cc.x * a1.x}, mlo[3] = {cc.y * a0.x, cc.y * a0.y, cc.y * a1.x};
