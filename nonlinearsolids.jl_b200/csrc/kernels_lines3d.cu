@@ -42,7 +42,11 @@
 #define L3_NCOLP (L3_NCOL + 1)
 #define L3_NY2 (L3_TY + 2)               // node lines cached per row
 #define L3_NLC (L3_NY2 * (L3_TZ + 2))    // 100 node lines touch those columns
-#define L3_NLCP 104
+#define L3_NLCP 110
+// first cell of row lz of the cached node lines in XU: 9 lz mod 16 is the residue, so that the lanes of phase A (consecutive
+// element columns, 9 per row) read 16 different 8-byte bank pairs per half-warp; rows laid out without overlap in 110 cells
+// (a plain 10-cell row stride made every XU load a two-way bank conflict: 96 M of the 139 M excess wavefronts at C3)
+__constant__ unsigned char c_l3_xrow[L3_TZ + 2] = {0, 89, 66, 11, 100, 45, 22, 79, 56, 33};
 #define L3_THREADS 384                   // 12 warps: 2 of self pairs, 5 of two-column pairs, 5 of one-column pairs
 #define L3_NPT L3_THREADS                // Laplacian-table slots per interval: one per thread
 #define L3_QH 4                          // quadrature points per half interval
@@ -206,8 +210,8 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
       else if (role == 1) {
         if (k < 72) { ptype = 1; ay = k % 9 - 1; az = k / 9; }                       // A from y = -1: the pair (-1, 0) belongs to line 0's rows
         else if (k < 144) { k -= 72; ptype = 3; ay = k & 7; az = (k >> 3) - 1; }
-      } else if (k < 158) {
-        if (k < 79) ptype = 4; else { ptype = 2; k -= 79; }
+      } else if (k < 159 && k != 79) {
+        if (k < 79) ptype = 4; else { ptype = 2; k -= 80; }      // from a multiple of 8: the lanes of a quarter-warp read 8 consecutive columns
         if (k < 64) { ay = k & 7; az = k >> 3; }
         else if (k < 72) { ay = ptype == 4 ? -1 : 8; az = k - 65; }                  // B in the tile, A beside it
         else { az = -1; ay = ptype == 4 ? k - 72 : k - 71; }                         // ... A below it
@@ -306,7 +310,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         if (y < 0 || y >= ny || z < 0 || z >= nzp) continue;
         const int64_t node = (int64_t)P.pbase[z] + (int64_t)y * nx + ip;
         const double *src = (half ? P.U : P.coords) + 3 * node;
-        double *dst = XU + (slot * 6 + 3 * half) * L3_NLCP + c;
+        double *dst = XU + (slot * 6 + 3 * half) * L3_NLCP + c_l3_xrow[c / L3_NY2] + c % L3_NY2;
         l3_cp8(dst, src); l3_cp8(dst + L3_NLCP, src + 1); l3_cp8(dst + 2 * L3_NLCP, src + 2);
       }
     };
@@ -360,10 +364,11 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
           const int ey = y0 - 1 + cyi, ez = z0 - 1 + czi;
           if (ey >= 0 && ey < ny - 1 && ez >= 0 && ez < nzp - 1) {
             const double *tq = TAB + q * 24;
+            const int xr[2] = {c_l3_xrow[czi] + cyi, c_l3_xrow[czi + 1] + cyi};
             double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
-              const int cl = (czi + (a >> 2)) * L3_NY2 + cyi + ((a >> 1) & 1);
+              const int cl = xr[a >> 2] + ((a >> 1) & 1);
               const double *xs = XU + ((a & 1) ? shi : slo) * 6 * L3_NLCP + cl;
               const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
 #pragma unroll
