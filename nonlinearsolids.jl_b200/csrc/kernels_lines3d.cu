@@ -170,7 +170,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *STG = reinterpret_cast<double *>(smem_raw);                                  // [L3_NL][L3_SLOT]
   double2 *REC = reinterpret_cast<double2 *>(STG + L3_NL * L3_SLOT);                    // [L3_QH][NARR][L3_NCOLP]
-  double *XU = reinterpret_cast<double *>(REC + L3_QH * 16 * L3_NCOLP);                 // [2 planes][6][L3_NLCP]: X, u of the cached node lines
+  double *XU = reinterpret_cast<double *>(REC + L3_QH * 16 * L3_NCOLP);                 // [2 planes][3][L3_NLCP] double2: X, u of the cached node lines
   double *LAPS = XU + 2 * 6 * L3_NLCP;                                                  // [3][L3_THREADS] Laplacian parts of this interval's blocks
   double *TAB = LAPS + 3 * L3_THREADS;                                                  // dN[8][8][3], w[8]
   __shared__ int s_unit;
@@ -310,8 +310,10 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         if (y < 0 || y >= ny || z < 0 || z >= nzp) continue;
         const int64_t node = (int64_t)P.pbase[z] + (int64_t)y * nx + ip;
         const double *src = (half ? P.U : P.coords) + 3 * node;
-        double *dst = XU + (slot * 6 + 3 * half) * L3_NLCP + c_l3_xrow[c / L3_NY2] + c % L3_NY2;
-        l3_cp8(dst, src); l3_cp8(dst + L3_NLCP, src + 1); l3_cp8(dst + 2 * L3_NLCP, src + 2);
+        // component j of {X, u} of a line sits in double2 array j >> 1, half j & 1: phase A takes a node with three 16-byte loads
+        double *dst = XU + 2 * (slot * 3 * L3_NLCP + c_l3_xrow[c / L3_NY2] + c % L3_NY2);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const int j = 3 * half + d; l3_cp8(dst + 2 * (j >> 1) * L3_NLCP + (j & 1), src + d); }
       }
     };
 
@@ -369,18 +371,20 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
               const int cl = xr[a >> 2] + ((a >> 1) & 1);
-              const double *xs = XU + ((a & 1) ? shi : slo) * 6 * L3_NLCP + cl;
+              const double2 *xs = reinterpret_cast<const double2 *>(XU) + ((a & 1) ? shi : slo) * 3 * L3_NLCP + cl;
               const double dn0 = tq[a * 3], dn1 = tq[a * 3 + 1], dn2 = tq[a * 3 + 2];
+              const double2 v0 = xs[0], v1 = xs[L3_NLCP];
+              const double x[3] = {v0.x, v0.y, v1.x};
 #pragma unroll
               for (int d = 0; d < 3; ++d) {
-                const double x = xs[d * L3_NLCP];
-                J[d * 3 + 0] = fma(x, dn0, J[d * 3 + 0]); J[d * 3 + 1] = fma(x, dn1, J[d * 3 + 1]); J[d * 3 + 2] = fma(x, dn2, J[d * 3 + 2]);
+                J[d * 3 + 0] = fma(x[d], dn0, J[d * 3 + 0]); J[d * 3 + 1] = fma(x[d], dn1, J[d * 3 + 1]); J[d * 3 + 2] = fma(x[d], dn2, J[d * 3 + 2]);
               }
               if (!LAP_BUILD) {
+                const double2 v2 = xs[2 * L3_NLCP];
+                const double v[3] = {v1.y, v2.x, v2.y};
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                  const double v = xs[(3 + d) * L3_NLCP];
-                  H[d * 3 + 0] = fma(v, dn0, H[d * 3 + 0]); H[d * 3 + 1] = fma(v, dn1, H[d * 3 + 1]); H[d * 3 + 2] = fma(v, dn2, H[d * 3 + 2]);
+                  H[d * 3 + 0] = fma(v[d], dn0, H[d * 3 + 0]); H[d * 3 + 1] = fma(v[d], dn1, H[d * 3 + 1]); H[d * 3 + 2] = fma(v[d], dn2, H[d * 3 + 2]);
                 }
               }
             }
