@@ -304,7 +304,8 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
     auto load_plane = [&](int ip) {            // X, u of node plane ip of the cached lines -> ring slot ip & 1
       if (ip > nxm1) return;
       const int slot = ip & 1;
-      for (int k = tid; k < 2 * L3_NLC; k += L3_THREADS) {
+      if (oord < 0) return;                    // the one-column pair warps fetch: they have the slack (phase B is half as long for them)
+      for (int k = oord * 32 + lane; k < 2 * L3_NLC; k += 5 * 32) {
         const int c = k >> 1, half = k & 1;
         const int y = y0 - 1 + c % L3_NY2, z = z0 - 1 + c / L3_NY2;
         if (y < 0 || y >= ny || z < 0 || z >= nzp) continue;
@@ -347,7 +348,7 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
 
     for (int i = ifirst; i < i1; ++i) {
       const long long tp0 = PROF ? clock64() : 0;
-      long long tA = 0, tB = 0;
+      long long tA = 0, tB = 0, tAw = 0, tFc = 0, tMid = 0;
       const bool store = i >= i0 && !P.dbg_nostore;
       if (!LAP_BUILD && DO_K && on) {            // this interval's Laplacian parts -> shared memory, read when the blocks are finished
         const double *lq = P.lap + s_lapoff + tid + (int64_t)(i - ifirst) * 3 * L3_NPT;
@@ -456,18 +457,25 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
         }
         // last interval's bulk copies have long finished reading the staging image; make that a fact before anyone rewrites it
         if (half == 1 && isslot) l3_bulk_wait_read();
+        if (PROF) tAw += clock64() - ta0;
         // The fence is required, not decoration: without it the phase-B loads of some warps returned the previous
         // interval's records although every STS above precedes this barrier in program order (found on a 3 x 2 x 3-node
         // mesh by the parity tests; profiles/r2_lines3d_notes.md). membar.cta costs nothing here.
         __threadfence_block();
         __syncthreads();
         if (PROF) tA += clock64() - ta0;
+        // Fetches sit off the critical path: all warps leaving the barrier and issuing ~20 cp.async each cost 2.7 k cycles per
+        // interval (tools/lines_probe.py). Node plane i+2 is fetched by the one-column warps only; the self-pair warps (the
+        // long pole, 9 copies each) fetch their carried blocks here, the others after their pair loop, where the warps have
+        // drifted apart and the copies of one overlap the arithmetic of the others.
+        const bool fetch = half == 1 && STAGE && on && store && i > 0;
         if (half == 1) {
           load_plane(i + 2);       // both halves have read node plane i: its slot takes plane i+2
-          if (STAGE && on && store && i > 0) fetch_carry(i);
+          if (fetch && ptype == 0) fetch_carry(i);
           l3_commit();
         }
         const long long tb0 = PROF ? clock64() : 0;
+        if (PROF) tFc += tb0 - ta0;
         // ---------------- phase B: line pairs, four quadrature points ----------------
         if (on) {
           if (ptype == 0) {
@@ -528,12 +536,14 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
               l3_acc(Kl, phi, mhi, blo); l3_acc(Kn, phi, mhi, bhi);
             }
           }
+          if (fetch && ptype != 0) { fetch_carry(i); l3_commit(); }
         }
         if (PROF) tB += clock64() - tb0;
         if (half == 0) {
           if (iss && pend >= 0 && warp != 11) flush_row(pend);
           pend = -1;
           __threadfence_block(); __syncthreads();      // the records are rewritten by the second half
+          if (PROF) tMid += clock64() - tb0;
         }
       }
       // ---- interval i completes (A_i, B_i), (A_i, B_i+1), (A_i+1, B_i): with the two blocks carried from interval i-1 they
@@ -623,6 +633,8 @@ k_asm_q1_3d_lines(const L3Args P, const __grid_constant__ TabQ1 T, const __grid_
           atomicAdd(P.prof + 0, (unsigned long long)tA); atomicAdd(P.prof + 1, (unsigned long long)(tp3 - tp0 - tA)); atomicAdd(P.prof + 2, 1ull);
           atomicAdd(P.prof + 3, (unsigned long long)(tf1 - tf0)); atomicAdd(P.prof + 4, (unsigned long long)(tf2 - tf1));
           atomicAdd(P.prof + 5, (unsigned long long)(tf3 - tf2)); atomicAdd(P.prof + 6, (unsigned long long)(tp3 - tf3));
+          // own phase-A work before its barrier; phase A + barrier + node-plane / carry fetch issue; first phase B + hand-off + its barrier
+          atomicAdd(P.prof + 20, (unsigned long long)tAw); atomicAdd(P.prof + 21, (unsigned long long)tFc); atomicAdd(P.prof + 22, (unsigned long long)tMid);
         }
       }
     }

@@ -22,3 +22,4 @@ for n in [int(v) for v in sys.argv[1:]] or [70]:
         ni = max(1, out[2])
         print("n %d mode %d (2 = no global stores): %.3f ms; intervals %d; per interval (warp 0): phase A to barrier %.0f clk, rest %.0f clk [cp.async wait %.0f, finalize %.0f, last barrier %.0f, row hand-off %.0f]; per-warp own phase-B clk: %s" % (
             n, mode, ms.value, ni, out[0] / ni, out[1] / ni, out[3] / ni, out[4] / ni, out[5] / ni, out[6] / ni, " ".join("%.0f" % (v / ni) for v in out[8:20])), flush=True)
+        print("   warp 0: own phase-A work %.0f, phase A + barrier + plane/carry fetch issue %.0f (fetch issue = this - 'phase A to barrier'), first phase B to its barrier %.0f" % (out[20] / ni, out[21] / ni, out[22] / ni), flush=True)
