@@ -566,7 +566,16 @@ static int mg_layout(nls_context *h) {
     }
     ++l;
     const int cx = mg_coarse_n(nx), cy = mg_coarse_n(ny), cz = mg_coarse_n(nz);
-    if (l >= MG_MAX_LEVELS || std::max(nx, std::max(ny, nz)) <= 6 || (cx == nx && cy == ny && cz == nz)) break;
+    if (l >= std::min(MG_MAX_LEVELS, m.max_levels) || std::max(nx, std::max(ny, nz)) <= 6 || (cx == nx && cy == ny && cz == nz)) break;
+    // Slender domains (the weak-scaled column: 150 x 150 x 150 N nodes): once the thinnest axis is down to 6 nodes, further
+    // levels have trilinear elements longer than the body is thick; they lock in bending and the coarse correction of the
+    // bending modes is too small (48 x 48 x 384 nodes: 20 Krylov iterations per solve against 9 for the cube; 13 with the
+    // hierarchy cut here). The cut level is small enough for the Chebyshev coarse solve, whose degree follows its length.
+    {
+      int thin = 1 << 30;
+      for (int n : {nx, ny, nz}) if (n > 2) thin = std::min(thin, n);
+      if (l >= 2 && thin <= 6 && (int64_t)nx * ny * nz <= 4096) break;      // (a hierarchy has at least two levels)
+    }
     // coarse planes of this rank: those whose fine plane it owns
     int c0 = 0, c1 = 0;
     while (c0 < cz && mg_fx(c0, nz) < own0) ++c0;
@@ -782,7 +791,11 @@ static int mg_cheb(nls_context *h, int l, const double *b, double *x, int degree
 static int mg_vcycle(nls_context *h, int l, const double *b, double *x) {
   MgPlan &m = h->mg;
   MgLevel &L = m.lev[l];
-  if (l == m.nlev - 1) return mg_cheb(h, l, b, x, m.coarse_degree, m.coarse_ratio, true);
+  if (l == m.nlev - 1) {
+    // the coarsest grid is "solved" by Chebyshev iteration: condition number ~ length^2, degree ~ length (6 nodes: the defaults)
+    const double f = std::max(1.0, std::max(L.nx, std::max(L.ny, L.NZ)) / 6.0);
+    return mg_cheb(h, l, b, x, (int)std::ceil(m.coarse_degree * f), m.coarse_ratio * f * f, true);
+  }
   NLS_TRY(mg_cheb(h, l, b, x, m.degree, m.ratio, true));
   NLS_TRY(mg_apply_K(h, l, x, L.y));
   MgLevel &C = m.lev[l + 1];

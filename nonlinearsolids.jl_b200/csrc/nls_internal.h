@@ -127,7 +127,7 @@ struct MgPlan {
   int rank_below = -1, rank_above = -1;
   int64_t version = -1;            // vals_version the operators were built for
   int mode = 2;                    // 1 block-Jacobi alone, 2 V-cycle
-  int degree = 2, coarse_degree = 24, power_its = 10;
+  int degree = 2, coarse_degree = 24, power_its = 10, max_levels = MG_MAX_LEVELS;
   double ratio = 8.0, coarse_ratio = 60.0;
   int fp32 = 1;                    // the smoother's level-0 products read a single-precision copy of the CSR values
   float *vals32 = nullptr;
