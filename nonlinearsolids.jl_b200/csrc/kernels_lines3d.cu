@@ -44,8 +44,9 @@
 #define L3_NLC (L3_NY2 * (L3_TZ + 2))    // 100 node lines touch those columns
 #define L3_NLCP 110
 // first cell of row lz of the cached node lines in XU: 9 lz mod 16 is the residue, so that the lanes of phase A (consecutive
-// element columns, 9 per row) read 16 different 8-byte bank pairs per half-warp; rows laid out without overlap in 110 cells
-// (a plain 10-cell row stride made every XU load a two-way bank conflict: 96 M of the 139 M excess wavefronts at C3)
+// element columns, 9 per row) read consecutive cells modulo 16 -- 8 different 16-byte bank groups per quarter-warp for the
+// double2 loads; rows laid out without overlap in 110 cells (a plain 10-cell row stride made every XU load a two-way bank
+// conflict: 96 M of the 139 M excess wavefronts at C3)
 __constant__ unsigned char c_l3_xrow[L3_TZ + 2] = {0, 89, 66, 11, 100, 45, 22, 79, 56, 33};
 #define L3_THREADS 384                   // 12 warps: 2 of self pairs, 5 of two-column pairs, 5 of one-column pairs
 #define L3_NPT L3_THREADS                // Laplacian-table slots per interval: one per thread
