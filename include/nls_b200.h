@@ -241,7 +241,8 @@ int32_t nls_debug_counters_ext(nls_handle h, int64_t *out24); /* + per-warp phas
  * >= 10 000 nodes, else Jacobi), 0 Jacobi, 1 block-Jacobi, 2 multigrid; "mg_degree" / "mg_ratio_x10" / "mg_coarse_degree" /
  * "mg_coarse_ratio" -> Chebyshev smoother (degree, eigenvalue interval), "mg_power_its" -> power iterations of the eigenvalue
  * bound, "mg_fp32" -> 1: the smoother's level-0 products read a single-precision copy of the CSR values (default),
- * "mg_max_levels" -> cap on the number of grid levels (default: coarsen until the thinnest axis has <= 6 nodes) */
+ * "mg_max_levels" -> cap on the number of grid levels (default: coarsen until the thinnest axis has <= 6 nodes),
+ * "mg_graph" -> 1: on one GPU the V-cycle is replayed as a CUDA graph (default), 0: plain launches */
 int32_t nls_set_option(nls_handle h, const char *key, int32_t value);
 
 /* ---- multi-GPU: one process per GPU, element-partitioned slabs ---------------- */

@@ -439,8 +439,15 @@ static unsigned mg_grid(nls_context *h, int64_t n, int threads = 256) {
   return (unsigned)std::max<int64_t>(1, std::min(g, cap));
 }
 
+static void mg_drop_graph(nls_context *h) {
+  MgPlan &m = h->mg;
+  if (m.vgraph) { cudaGraphExecDestroy(m.vgraph); m.vgraph = nullptr; }
+  m.vgraph_version = -1;
+}
+
 static void mg_free_levels(nls_context *h) {
   MgPlan &m = h->mg;
+  mg_drop_graph(h);               // it holds the addresses of the level buffers
   for (int l = 0; l < MG_MAX_LEVELS; ++l) {
     MgLevel &L = m.lev[l];
     if (L.K) cudaFree(L.K);
@@ -852,7 +859,31 @@ int nls_mg_apply(nls_context *h, const double *r, double *z) {
     MG_KCHECK(h);
     return NLS_OK;
   }
-  return mg_vcycle(h, 0, r, z);
+  MgPlan &m = h->mg;
+  if (!m.use_graph || m.dist || m.graph_off) return mg_vcycle(h, 0, r, z);
+  const double key[6] = {(double)m.degree, m.ratio, (double)m.coarse_degree, m.coarse_ratio, (double)(m.fp32 && m.vals32), (double)m.nlev};
+  if (!m.vgraph || m.vgraph_version != m.version || m.vgraph_r != r || m.vgraph_z != z || std::memcmp(key, m.vgraph_key, sizeof(key)) != 0) {
+    mg_drop_graph(h);
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); m.graph_off = true; return mg_vcycle(h, 0, r, z); }
+    const int64_t l0 = h->launches;
+    const int rc = mg_vcycle(h, 0, r, z);
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    m.vgraph_launches = h->launches - l0;
+    h->launches = l0;                       // nothing ran yet
+    if (rc != NLS_OK || e != cudaSuccess || !g || cudaGraphInstantiate(&m.vgraph, g, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      m.vgraph = nullptr; m.graph_off = true;
+      return rc != NLS_OK ? rc : mg_vcycle(h, 0, r, z);
+    }
+    cudaGraphDestroy(g);
+    m.vgraph_version = m.version; m.vgraph_r = r; m.vgraph_z = z;
+    std::memcpy(m.vgraph_key, key, sizeof(key));
+  }
+  NLS_CUDA(h, cudaGraphLaunch(m.vgraph, h->stream));
+  h->launches += m.vgraph_launches;
+  return NLS_OK;
 }
 
 // ---- preconditioned conjugate gradients around it (host-driven: an iteration is tens of launches, the three reductions

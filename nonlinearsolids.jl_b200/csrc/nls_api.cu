@@ -998,6 +998,7 @@ extern "C" int32_t nls_set_option(nls_handle h, const char *key, int32_t value) 
   if (!std::strcmp(key, "mg_degree")) { h->mg.degree = value < 1 ? 1 : value; return NLS_OK; }
   if (!std::strcmp(key, "mg_coarse_degree")) { h->mg.coarse_degree = value < 1 ? 1 : value; return NLS_OK; }
   if (!std::strcmp(key, "mg_ratio_x10")) { h->mg.ratio = value < 11 ? 1.1 : value / 10.0; return NLS_OK; }
+  if (!std::strcmp(key, "mg_graph")) { h->mg.use_graph = value != 0; h->mg.graph_off = false; return NLS_OK; }
   if (!std::strcmp(key, "mg_max_levels")) { h->mg.max_levels = value < 2 ? 2 : value; nls_mg_invalidate(h); return NLS_OK; }
   if (!std::strcmp(key, "mg_coarse_ratio")) { h->mg.coarse_ratio = value < 2 ? 2.0 : (double)value; return NLS_OK; }
   if (!std::strcmp(key, "mg_fp32")) { h->mg.fp32 = value; h->mg.version = -1; return NLS_OK; }

@@ -136,6 +136,15 @@ struct MgPlan {
   double *rf = nullptr;            // level-0 residual with ghost entries (restriction input)
   uint8_t *conf = nullptr;         // constrained mask of all local nodes, ghost entries from their owners
   MgLevel lev[MG_MAX_LEVELS];
+  // single GPU: the V-cycle (~100 launches, most of them microseconds long on the coarse levels) replayed as one CUDA graph;
+  // captured again whenever the operators, the eigenvalue bounds, the smoother options or the vectors it was captured on change
+  int use_graph = 1;
+  bool graph_off = false;          // capture failed once: plain launches from then on
+  cudaGraphExec_t vgraph = nullptr;
+  int64_t vgraph_version = -1, vgraph_launches = 0;
+  const double *vgraph_r = nullptr;
+  double *vgraph_z = nullptr;
+  double vgraph_key[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // ---- device control block of the PCG loop (lives in device memory) ----

@@ -20,7 +20,7 @@ def _solve(H, n, b, rtol=1e-12, maxits=20000):
     return x, its.value, st.value, rr.value
 
 
-@pytest.mark.parametrize("shape", [(9, 9, 9), (12, 7, 10), (17, 10, 12), (6, 14, 21), (24, 24, 24), (9, 9, 70), (25, 31), (40, 18), (7, 50), (64, 64)])
+@pytest.mark.parametrize("shape", [(9, 9, 9), (12, 7, 10), (17, 10, 12), (6, 14, 21), (24, 24, 24), (9, 9, 25), (25, 31), (40, 18), (7, 50), (64, 64)])
 def test_multigrid_solve_matches_oracle(nls, orc, shape):
     mat = nls.NeoHookean(E=1.0, nu=0.3)
     fem, om = grid_problem(nls, orc, shape, len(shape), mat, compress=-0.01)
