@@ -140,6 +140,56 @@ def bind_to_gpu_numa_node(gpu):
         return "not bound: %s" % e
 
 
+def _set_preferred_node(node):
+    """set_mempolicy(MPOL_PREFERRED, {node}) for the calling thread (node < 0: the default policy); errno, 0 = ok."""
+    import ctypes
+    libc = ctypes.CDLL(None, use_errno=True)
+    if node < 0:
+        r = libc.syscall(238, 0, None, 0)                      # SYS_set_mempolicy (x86_64), MPOL_DEFAULT
+    else:
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        r = libc.syscall(238, 1, mask, 16 * 64 + 1)            # MPOL_PREFERRED: soft, falls back to other nodes
+    return 0 if r == 0 else ctypes.get_errno()
+
+
+def choose_host_node(numa):
+    """Where should this rank's pinned host buffers live? If sysfs could not say (`numa` = "numa node unknown": the boxes
+    report numa_node = -1) and the machine has several NUMA nodes, measure: a 256 MB pinned buffer per node under a
+    preferred-node memory policy, device -> host copies into it, the fastest node wins (tools/numa_probe.py is the same
+    probe stand-alone). Returns (node or None, description). Never raises."""
+    try:
+        import glob
+        import torch
+        nodes = sorted(int(q.rsplit("node", 1)[1]) for q in glob.glob("/sys/devices/system/node/node[0-9]*"))
+        if numa != "numa node unknown" or (len(nodes) < 2 and not os.environ.get("NLS_BENCH_FORCE_NUMA_MEASURE")):
+            return None, numa if numa != "numa node unknown" else "single NUMA node"
+        n = 32 << 20
+        dev = torch.ones(n, dtype=torch.float64, device="cuda")
+        rate = {}
+        for node in nodes:
+            if _set_preferred_node(node):
+                continue
+            try:
+                host = torch.empty(n, dtype=torch.float64).pin_memory()
+            finally:
+                _set_preferred_node(-1)
+            best = 0.0
+            for _ in range(3):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                host.copy_(dev, non_blocking=True); torch.cuda.synchronize()
+                best = max(best, 8.0 * n / (time.perf_counter() - t0) / 1e9)
+            rate[node] = best
+            del host
+        del dev
+        if not rate:
+            return None, "numa node unknown (set_mempolicy refused)"
+        node = max(rate, key=rate.get)
+        return node, "numa node %d by measured D2H rate (%s GB/s)" % (node, ", ".join("%d: %.1f" % kv for kv in sorted(rate.items())))
+    except Exception as e:      # noqa: BLE001
+        return None, "numa node unknown (%s)" % e
+
+
 def algorithmic_bytes(dim, nen, nel, nn, ndof_rows, nnz):
     """conn + coords + U read + R write + vals write (colind / slot maps not counted)."""
     return 4 * nen * nel + 8 * dim * nn + 8 * ndof_rows + 8 * ndof_rows + 8 * nnz
@@ -380,7 +430,14 @@ def run_ours(args):
             pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()     # noqa: E731
         except Exception:       # noqa: BLE001
             pin = lambda n: np.empty(n)     # noqa: E731
-        Uh, Rh, Vh = pin(fem.ndof), pin(nrows), pin(nnz)
+        node, numa = choose_host_node(numa)
+        if node is not None:
+            _set_preferred_node(node)
+        try:
+            Uh, Rh, Vh = pin(fem.ndof), pin(nrows), pin(nnz)
+        finally:
+            if node is not None:
+                _set_preferred_node(-1)
         Uh[:] = U0
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         H.call("nls_residual_jacobian", dp(Uh), dp(Rh), dp(Vh))          # warm-up (page-in of the pinned buffers)
