@@ -462,10 +462,21 @@ static int spmv_t(nls_context *h, const double *x, double *y, const uint8_t *con
   return NLS_OK;
 }
 
+// Grid cap of the grid-stride products: exactly the blocks that are resident at once. With the former cap of 8 blocks per SM
+// and 40 registers per thread only 6 fit, and the kernel ran 1.33 waves -- the last third of the blocks at a third of the
+// memory parallelism of a latency-bound kernel (profiles/r2_ncu_spmv_f32_c3.txt: long_scoreboard 52.9, 57.8 % warps active).
+template <typename Kern>
+static int64_t resident_blocks(nls_context *h, Kern kernel) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 6; }
+  return (int64_t)h->sm_count * nb;
+}
+
 template <int DIM, int T>
 static int bspmv_t(nls_context *h, const double *x, double *y, const uint8_t *con, bool dot) {
   int64_t g = (h->n_owned * T + 255) / 256;
-  const int64_t cap = (int64_t)h->sm_count * 8;
+  static const int64_t cap_dot = resident_blocks(h, k_bspmv<DIM, T, true>), cap_plain = resident_blocks(h, k_bspmv<DIM, T, false>);
+  const int64_t cap = dot ? cap_dot : cap_plain;
   if (g > cap) g = cap;
   if (g > RED_BLOCKS_MAX) g = RED_BLOCKS_MAX;
   if (g < 1) g = 1;
@@ -580,7 +591,8 @@ int nls_launch_vals_to_f32(nls_context *h, float *out) {
 int nls_launch_spmv_f32(nls_context *h, const float *vals32, const double *x, double *y) {
   if (h->dim < 2 || h->nrows == 0) NLS_FAIL(h, NLS_ERR_STATE, "single-precision product: 2-D and 3-D models only");
   int64_t g = (h->n_owned * 4 + 255) / 256;
-  const int64_t cap = (int64_t)h->sm_count * 8;
+  static const int64_t cap2 = resident_blocks(h, k_bspmv<2, 4, false, float>), cap3 = resident_blocks(h, k_bspmv<3, 4, false, float>);
+  const int64_t cap = h->dim == 2 ? cap2 : cap3;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   if (h->dim == 2) k_bspmv<2, 4, false, float><<<(unsigned)g, 256, 0, h->stream>>>(h->n_owned, h->d_browptr, h->d_bcol, vals32, x, y, h->d_con, h->d_ctl, red_of(h));
